@@ -1,0 +1,203 @@
+/*
+ * ppb200.h — C ABI of libppb200.so: the B200-native checkpointed gzip-FASTQ
+ * decode path (CreateIndex / Decompress(checkpoint) / DecompressAll /
+ * Serialize / Deserialize) of Quantumzhao/ParallelParsing.
+ *
+ * This is the drop-in boundary.  The reference reaches its only native code
+ * (system zlib) through a static class of [DllImport] externs
+ * (Interop/PlatformInterop.cs:6-35) wrapped by the Compat facade
+ * (Interop/Conventions.cs:129-196); this library is bound the same way (see
+ * INTEGRATION.md for the C# stub).  Conventions kept from that boundary:
+ *   - only blittable types cross it: pointers, sizes, int32/int64;
+ *   - the caller owns every data buffer, native code owns only opaque handles
+ *     released by an explicit *_free / pp_close (Conventions.cs:121-126);
+ *   - every call returns a ZResult-compatible int (Conventions.cs:9-20):
+ *     0 OK, 1 STREAM_END, 2 NEED_DICT, negatives are errors; the C# side turns
+ *     negatives into ZException(code) as Core.cs:33,74,149,179 do today;
+ *   - no callbacks, no errno, no exceptions across the boundary;
+ *   - calls on one pp_ctx are serialised internally, so they may be issued from
+ *     thread-pool tasks as BatchedFASTQ.cs:62 does (README.md:50).
+ *
+ * There is NO CPU fallback: every decode/parse entry point runs hand-written
+ * sm_100a CUDA kernels and fails with PP_E_NO_DEVICE / PP_E_CUDA otherwise.
+ * Index creation and (de)serialisation are host code, as in the reference
+ * (Core.BuildDeflateIndex is a serial zlib Z_BLOCK scan, Core.cs:14-131).
+ */
+#ifndef PPB200_H
+#define PPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+#define PP_WINSIZE 32768 /* Common/Constants.cs:9 */
+
+/* ZResult (Interop/Conventions.cs:9-20) */
+#define PP_OK 0
+#define PP_STREAM_END 1
+#define PP_NEED_DICT 2
+#define PP_ERRNO (-1)
+#define PP_STREAM_ERROR (-2)
+#define PP_DATA_ERROR (-3)
+#define PP_MEM_ERROR (-4)
+#define PP_BUF_ERROR (-5)
+#define PP_VERSION_ERROR (-6)
+/* new codes, outside zlib's range */
+#define PP_E_CUDA (-100)            /* a CUDA runtime call or kernel failed */
+#define PP_E_NO_DEVICE (-101)       /* no usable sm_100 device: there is no CPU fallback */
+#define PP_E_ARG (-102)             /* bad argument */
+#define PP_E_IO (-103)              /* file open/read/write failed */
+#define PP_E_RECORD_TOO_LONG (-104) /* Core.cs:93 IndexOutOfRangeException: record > 32768 B */
+#define PP_E_FORMAT (-105)          /* malformed IndexIO file */
+
+typedef struct pp_index pp_index; /* Common/Index.cs:5  Index  */
+typedef struct pp_ctx pp_ctx;     /* one GPU + stream + scratch */
+typedef struct pp_job pp_job;     /* one DecompressAll plan over a chunk range */
+
+/* Common/Index.cs:51-82  Point (a view; pointers stay valid until the index is freed/modified) */
+typedef struct pp_point {
+    int64_t output;        /* Point.Output: offset in uncompressed data          */
+    int64_t input;         /* Point.Input : offset in the file of first full byte */
+    int32_t bits;          /* Point.Bits  : 0, or 1-7 bits taken from byte input-1 */
+    int32_t offset_len;    /* Point.offset.Length                                 */
+    const uint8_t *window; /* Point.Window: preceding 32768 uncompressed bytes    */
+    const uint8_t *offset; /* Point.offset: partial record before the point       */
+} pp_point;
+
+int pp_abi_version(void);
+const char *pp_strerror(int code);
+
+/* ------------------------------------------------------------------ Index */
+
+/* flags for pp_index_create */
+#define PP_INDEX_LIFT_RECORD_CAP 1u /* extension: do not fail on records > 32768 B */
+
+/* CreateIndex — Core.BuildDeflateIndex(FileStream, uint chunksize), Decompressor/Core.cs:14-131. */
+int pp_index_create(const uint8_t *gz, size_t gz_len, uint32_t chunksize, uint32_t flags, pp_index **out);
+int pp_index_create_file(const char *gz_path, uint32_t chunksize, uint32_t flags, pp_index **out);
+/* new Index() — Common/Index.cs:11 */
+int pp_index_new(pp_index **out);
+/* Index.AddPoint(bits, input, output, left, window, offset) — Common/Index.cs:24-48 */
+int pp_index_add_point(pp_index *ix, int32_t bits, int64_t input, int64_t output, uint32_t left,
+                       const uint8_t *window, const uint8_t *offset, int32_t offset_len);
+/* IndexIO.Serialize / Deserialize — Common/IndexIO.cs:7-27 / :29-53 (same bytes on disk) */
+int pp_index_serialize(const pp_index *ix, const char *path);
+int pp_index_deserialize(const char *path, pp_index **out);
+/* Index.Count, Index.ChunkMaxBytes, Index[i] — Common/Index.cs:9,20,21 */
+int32_t pp_index_count(const pp_index *ix);
+int32_t pp_index_chunk_max_bytes(const pp_index *ix);
+int pp_index_point(const pp_index *ix, int32_t i, pp_point *out);
+void pp_index_free(pp_index *ix);
+
+/* ----------------------------------------------------------------- Device */
+
+/* Open CUDA device `device`.  Fails with PP_E_NO_DEVICE when there is no GPU. */
+int pp_open(int32_t device, pp_ctx **out);
+void pp_close(pp_ctx *ctx);
+/* Pinned host memory for the compressed file (cudaHostAlloc / cudaHostRegister). */
+int pp_host_alloc(size_t bytes, void **out);
+void pp_host_free(void *p);
+int pp_host_register(void *p, size_t bytes);
+void pp_host_unregister(void *p);
+
+/* -------------------------------------------------- Decompress(checkpoint) */
+
+/*
+ * Core.ExtractDeflateIndex(fileBuffer, from, to, buf) — Decompressor/Core.cs:133-192.
+ * `fileBuffer` is the byte range LazyFileReader hands over: file bytes
+ * [from.Input-1, to.Input) (Decompressor/LazyFileReader.cs:63-69) where
+ * from = index[from_point], to = index[from_point+1].  Inflates into `buf`
+ * (capacity >= to.Output-from.Output).  Returns bytes produced, or a negative code.
+ */
+int64_t pp_extract(pp_ctx *ctx, const uint8_t *fileBuffer, int64_t fileBufferLen, const pp_index *ix,
+                   int32_t from_point, uint8_t *buf, int64_t buf_len);
+
+/* ------------------------------------------------------------ Parsing.Parse */
+
+/*
+ * Parsing.Parse(new CombinedMemory(prepend, rest)) — Decompressor/Parsing.cs:11-117.
+ * `rest` is the data proper; the reference's zero tail (the rented array is
+ * pow-2 sized, BatchedFASTQ.cs:65-68) is implied: parsing stops at the first
+ * NUL or at the end of `rest`, and a trailing partial record is dropped.
+ * For each record r < cap writes line_starts[4r..4r+3]: combined-memory index
+ * of the first byte of the id line ('@'), sequence line, '+' line and quality
+ * line; *parse_end receives the index just past the last record.  In the
+ * reference's terms: start=idnFrom=l0+1, idnLen=l1-l0-2, seqFrom=l1,
+ * seqLen=l2-l1-1, plsFrom=l2+1, plsLen=l3-l2-2, qltFrom=l3, qltLen=next_l0-l3-1.
+ * Returns the record count (may exceed cap) or a negative code.
+ */
+int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const uint8_t *rest, int64_t rest_len,
+                 uint32_t *line_starts, int64_t cap, uint32_t *parse_end);
+
+/* ------------------------------------------------------------ DecompressAll */
+
+/* flags for pp_job_create */
+#define PP_JOB_STRICT 1u      /* extension: drop the duplicate record of quirk H1 */
+#define PP_JOB_ZEROCOPY 2u    /* kernels pull compressed bytes/windows straight from pinned host memory */
+
+typedef struct pp_job_info {
+    int32_t first_chunk, n_chunks;
+    int64_t total_records;   /* records over all chunks (canonical order: chunk, then in-chunk) */
+    int64_t total_bytes;     /* inflated bytes over all chunks                                    */
+    int64_t scanned_bytes;   /* sum over chunks of |offset_k| + inflated_k (bytes the parser reads) */
+    int64_t compressed_bytes;/* compressed bytes consumed                                          */
+    int64_t h2d_bytes;       /* bytes copied host->device by pp_job_upload                         */
+    int64_t d2h_bytes;       /* bytes copied device->host by pp_job_download                       */
+    int32_t status;          /* first non-zero chunk status, else 0                                */
+    int32_t exact_chunks;    /* chunks that went through the exact (quirk-exact) parser            */
+    float upload_ms, inflate_ms, scan_ms, parse_ms, download_ms; /* CUDA-event times of the last run */
+    int32_t launches;        /* kernels launched by the last pp_job_execute                        */
+} pp_job_info;
+
+typedef struct pp_chunk_info {
+    int32_t status;        /* 0 or negative ZResult of this chunk's inflate                      */
+    int32_t prefix_len;    /* |from.offset|                                                      */
+    int64_t inflated;      /* bytes produced (Core.ExtractDeflateIndex return value)             */
+    int64_t records;       /* records Parsing.Parse yields for the chunk                         */
+    int64_t record_base;   /* index of the chunk's first record in the line_start arrays         */
+    uint32_t parse_end;    /* combined-memory index just past the chunk's last record            */
+    uint32_t flags;        /* bit0: went through the exact parser                                */
+} pp_chunk_info;
+
+/*
+ * DecompressAll — the BatchedFASTQ enumeration (Decompressor/BatchedFASTQ.cs:54-98)
+ * over chunks [first_chunk, first_chunk+n_chunks) of the index (chunk k =
+ * (index[k], index[k+1]), LazyFileReader.cs:53-61), split into phases so a
+ * caller can keep the plan and inputs resident:
+ *   create  : plan device layout, allocate device + pinned staging (no timing relevance)
+ *   upload  : H2D of the compressed byte range and the checkpoint windows
+ *   execute : inflate kernel -> record-base scan -> parse kernel (all device resident)
+ *   download: D2H of the per-chunk results (status, counts)
+ * `gz` is the whole .gz file in host memory (pinned for full H2D speed).
+ * n_chunks < 0 means "to the last chunk".
+ */
+int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_chunk, int32_t n_chunks,
+                  uint32_t flags, pp_job **out);
+int pp_job_upload(pp_job *job, const uint8_t *gz);
+int pp_job_execute(pp_job *job);
+int pp_job_download(pp_job *job);
+int pp_job_info_get(const pp_job *job, pp_job_info *out);
+int pp_job_chunk_info(const pp_job *job, int32_t chunk /* relative to first_chunk */, pp_chunk_info *out);
+/* Copy results to host memory.  line_starts: four arrays of total_records u32 each. */
+int pp_job_fetch_line_starts(pp_job *job, uint32_t *l0, uint32_t *l1, uint32_t *l2, uint32_t *l3);
+/* Inflated bytes of one chunk (dst capacity >= inflated). */
+int pp_job_fetch_chunk(pp_job *job, int32_t chunk, uint8_t *dst, int64_t cap);
+/* Inflated bytes of all chunks, concatenated (dst capacity >= total_bytes). */
+int pp_job_fetch_bytes(pp_job *job, uint8_t *dst, int64_t cap);
+/* Device pointers for on-device consumers (valid until the job is freed). */
+int pp_job_device_ptrs(const pp_job *job, const uint8_t **slots, const uint64_t **chunk_data_off,
+                       const uint32_t **l0, const uint32_t **l1, const uint32_t **l2, const uint32_t **l3);
+void pp_job_free(pp_job *job);
+
+/* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */
+int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t gz_len, int32_t first_chunk,
+                      int32_t n_chunks, uint32_t flags, pp_job **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPB200_H */
