@@ -84,6 +84,9 @@ int pp_index_new(pp_index **out);
 /* Index.AddPoint(bits, input, output, left, window, offset) — Common/Index.cs:24-48 */
 int pp_index_add_point(pp_index *ix, int32_t bits, int64_t input, int64_t output, uint32_t left,
                        const uint8_t *window, const uint8_t *offset, int32_t offset_len);
+/* Index.Add(Point) — Common/Index.cs:22: append a finished point unchanged (ChunkMaxBytes untouched) */
+int pp_index_add(pp_index *ix, int32_t bits, int64_t input, int64_t output, const uint8_t *window,
+                 const uint8_t *offset, int32_t offset_len);
 /* IndexIO.Serialize / Deserialize — Common/IndexIO.cs:7-27 / :29-53 (same bytes on disk) */
 int pp_index_serialize(const pp_index *ix, const char *path);
 int pp_index_deserialize(const char *path, pp_index **out);

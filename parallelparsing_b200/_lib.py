@@ -1,0 +1,109 @@
+"""ctypes binding of libppb200.so (include/ppb200.h).  No fallback: if the CUDA
+library is missing or there is no sm_100 device the calls raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libppb200.so")
+
+WINSIZE = 32768
+
+PP_OK = 0
+PP_E_CUDA, PP_E_NO_DEVICE, PP_E_ARG, PP_E_IO, PP_E_RECORD_TOO_LONG, PP_E_FORMAT = -100, -101, -102, -103, -104, -105
+PP_INDEX_LIFT_RECORD_CAP = 1
+PP_JOB_STRICT, PP_JOB_ZEROCOPY = 1, 2
+
+
+class PPPoint(C.Structure):
+    _fields_ = [("output", C.c_int64), ("input", C.c_int64), ("bits", C.c_int32), ("offset_len", C.c_int32),
+                ("window", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint8))]
+
+
+class PPJobInfo(C.Structure):
+    _fields_ = [("first_chunk", C.c_int32), ("n_chunks", C.c_int32), ("total_records", C.c_int64),
+                ("total_bytes", C.c_int64), ("scanned_bytes", C.c_int64), ("compressed_bytes", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("status", C.c_int32),
+                ("exact_chunks", C.c_int32), ("upload_ms", C.c_float), ("inflate_ms", C.c_float),
+                ("scan_ms", C.c_float), ("parse_ms", C.c_float), ("download_ms", C.c_float),
+                ("launches", C.c_int32)]
+
+
+class PPChunkInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("prefix_len", C.c_int32), ("inflated", C.c_int64), ("records", C.c_int64),
+                ("record_base", C.c_int64), ("parse_end", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class ZException(Exception):
+    """Interop/Conventions.cs:33-41 — carries the ZResult-compatible code."""
+
+    def __init__(self, code, what=""):
+        self.Code = code
+        msg = lib().pp_strerror(code).decode() if _lib is not None else str(code)
+        super().__init__(f"{what}: {msg} ({code})" if what else f"{msg} ({code})")
+
+
+_lib = None
+
+# every symbol include/ppb200.h declares: (name, restype, argtypes)
+_p, _i32, _i64, _u32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
+_PP = C.POINTER(_p)
+SYMBOLS = [
+    ("pp_abi_version", C.c_int, []),
+    ("pp_strerror", C.c_char_p, [C.c_int]),
+    ("pp_index_create", C.c_int, [_p, _sz, _u32, _u32, _PP]),
+    ("pp_index_create_file", C.c_int, [C.c_char_p, _u32, _u32, _PP]),
+    ("pp_index_new", C.c_int, [_PP]),
+    ("pp_index_add_point", C.c_int, [_p, _i32, _i64, _i64, _u32, _p, _p, _i32]),
+    ("pp_index_add", C.c_int, [_p, _i32, _i64, _i64, _p, _p, _i32]),
+    ("pp_index_serialize", C.c_int, [_p, C.c_char_p]),
+    ("pp_index_deserialize", C.c_int, [C.c_char_p, _PP]),
+    ("pp_index_count", _i32, [_p]),
+    ("pp_index_chunk_max_bytes", _i32, [_p]),
+    ("pp_index_point", C.c_int, [_p, _i32, C.POINTER(PPPoint)]),
+    ("pp_index_free", None, [_p]),
+    ("pp_open", C.c_int, [_i32, _PP]),
+    ("pp_close", None, [_p]),
+    ("pp_host_alloc", C.c_int, [_sz, _PP]),
+    ("pp_host_free", None, [_p]),
+    ("pp_host_register", C.c_int, [_p, _sz]),
+    ("pp_host_unregister", None, [_p]),
+    ("pp_extract", _i64, [_p, _p, _i64, _p, _i32, _p, _i64]),
+    ("pp_parse", _i64, [_p, _p, _i64, _p, _i64, _p, _i64, C.POINTER(_u32)]),
+    ("pp_job_create", C.c_int, [_p, _p, _sz, _i32, _i32, _u32, _PP]),
+    ("pp_job_upload", C.c_int, [_p, _p]),
+    ("pp_job_execute", C.c_int, [_p]),
+    ("pp_job_download", C.c_int, [_p]),
+    ("pp_job_info_get", C.c_int, [_p, C.POINTER(PPJobInfo)]),
+    ("pp_job_chunk_info", C.c_int, [_p, _i32, C.POINTER(PPChunkInfo)]),
+    ("pp_job_fetch_line_starts", C.c_int, [_p, _p, _p, _p, _p]),
+    ("pp_job_fetch_chunk", C.c_int, [_p, _i32, _p, _i64]),
+    ("pp_job_fetch_bytes", C.c_int, [_p, _p, _i64]),
+    ("pp_job_device_ptrs", C.c_int, [_p, _PP, _PP, _PP, _PP, _PP, _PP]),
+    ("pp_job_free", None, [_p]),
+    ("pp_decompress_all", C.c_int, [_p, _p, _p, _sz, _i32, _i32, _u32, _PP]),
+]
+
+
+def lib():
+    """Load libppb200.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m parallelparsing_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, rt, at in SYMBOLS:
+            f = getattr(L, name)
+            f.restype = rt
+            f.argtypes = at
+        if L.pp_abi_version() != 1:
+            raise RuntimeError("libppb200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc < 0:
+        raise ZException(rc, what)
+    return rc

@@ -119,6 +119,20 @@ int pp_index_add_point(pp_index *ix, int32_t bits, int64_t input, int64_t output
     return PP_OK;
 }
 
+int pp_index_add(pp_index *ix, int32_t bits, int64_t input, int64_t output, const uint8_t *window,
+                 const uint8_t *offset, int32_t offset_len)
+{
+    if (!ix || (offset_len > 0 && !offset)) return PP_E_ARG;
+    const int32_t keep = ix->chunk_max_bytes;
+    try {
+        add_point(ix, bits, input, output, 0, window, offset, offset_len);
+    } catch (...) {
+        return PP_MEM_ERROR;
+    }
+    ix->chunk_max_bytes = keep;
+    return PP_OK;
+}
+
 int32_t pp_index_count(const pp_index *ix) { return ix ? ix->count() : 0; }
 int32_t pp_index_chunk_max_bytes(const pp_index *ix) { return ix ? ix->chunk_max_bytes : 0; }
 

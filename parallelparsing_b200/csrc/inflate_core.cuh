@@ -94,10 +94,10 @@ struct ChunkResult {
     uint64_t end_bit;   // bit position after the last consumed bit
 };
 
-struct Smem {
+struct alignas(128) Smem {
+    uint32_t ring[kRingWords];  // first: TMA destinations must be 16 B aligned
     uint32_t lit[kLitCap];
     uint32_t dist[kDistCap];
-    uint32_t ring[kRingWords];
     uint16_t count[16];
     uint16_t next[16];
     uint8_t lens[320];
@@ -156,19 +156,24 @@ PP_DEV void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-PP_DEV void mbar_wait(unsigned long long *bar, uint32_t parity)
+// Bounded wait: a transfer that never lands (bad pointer, driver fault) must not hang the GPU.
+PP_DEV bool mbar_wait(unsigned long long *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > 4000000000LL) return false;  // ~2 s
+    }
 }
 PP_DEV void tma_load_tile(void *dst_smem, const void *src_gmem, unsigned long long *bar)
 {
@@ -207,12 +212,12 @@ PP_DEV void rd_issue(Reader &r, Smem &sm)
 PP_DEV void rd_wait(Reader &r, Smem &sm, uint32_t seq)
 {
 #ifndef PP_HOST_EMU
-    mbar_wait(&sm.bar[seq % kStages], (seq / kStages) & 1u);
+    if (!mbar_wait(&sm.bar[seq % kStages], (seq / kStages) & 1u)) r.exhausted = 2;
 #else
     (void)sm; (void)seq;
 #endif
     const int64_t tile = r.tile_bias + (int64_t)seq;
-    if (tile < 0 || (uint64_t)tile >= r.comp_tiles) r.exhausted = 1;
+    if (tile < 0 || (uint64_t)tile >= r.comp_tiles) r.exhausted |= 1;
 }
 
 // Position the reader at absolute bit `bit` of the compressed buffer.
@@ -226,7 +231,7 @@ PP_DEV void rd_seek(Reader &r, Smem &sm, uint64_t bit, bool first)
     const uint64_t tile = word / kTileWords;
     r.tile_bias = (int64_t)tile - (int64_t)r.s_issued;
     r.s_cur = r.s_issued;
-    r.exhausted = 0;
+    r.exhausted &= 2;  // a timed-out transfer stays fatal
     for (int i = 0; i < kStages; i++) rd_issue(r, sm);
     rd_wait(r, sm, r.s_cur);
     r.wnext = word;
@@ -693,6 +698,7 @@ PP_DEV void inflate_chunk(const ChunkDesc &d, const uint8_t *comp, uint64_t comp
     r.s_cur = 0;
     r.s_issued = 0;
     r.tile_bias = 0;
+    r.exhausted = 0;
     // 2. bit cursor: 8*Input - Bits (Core.cs:151-157 inflatePrime semantics)
     rd_seek(r, sm, d.in_bit, true);
 

@@ -1,0 +1,55 @@
+// Device-side interfaces shared by inflate.cu, parse.cu and runtime.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "inflate_core.cuh"
+
+namespace pp {
+
+using ppinf::ChunkDesc;
+using ppinf::ChunkResult;
+
+// Per-chunk input of the parse stage (written by the record-base scan kernel).
+struct ParseDesc {
+    uint64_t data_off;   // byte offset of the chunk's combined memory (from.offset ++ inflated) in the slots buffer
+    int64_t rec_base;    // index of the chunk's first record in the line-start arrays
+    uint32_t total;      // |from.offset| + bytes inflated
+    uint32_t rec_count;  // records the chunk yields
+    uint32_t skip;       // leading records dropped (PP_JOB_STRICT, quirk H1)
+    uint32_t exact;      // 1: route through the exact (sequential, quirk-exact) parser
+};
+
+// Per-chunk output of the parse stage.
+struct ParseOut {
+    uint32_t parse_end;  // combined-memory index just past the last record
+    uint32_t flags;      // bit0: anomaly found by the fast parser (needs the exact parser)
+    uint32_t newlines;   // '\n' seen by the fast parser (cross-check against the inflate count)
+    uint32_t records;    // records emitted
+};
+
+struct ScanTotals {
+    int64_t total_records;
+    int64_t total_bytes;
+    int64_t scanned_bytes;
+    int32_t overflow;   // total_records > capacity: nothing was parsed
+    int32_t first_status;
+    int32_t exact_chunks;
+    int32_t pad;
+};
+
+// kernel launchers (each returns the cudaGetLastError() of its launch)
+cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
+                           const uint8_t *lead, ChunkResult *results, cudaStream_t st);
+cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
+                               cudaStream_t st);
+cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,
+                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ScanTotals *totals, cudaStream_t st);
+cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines, int64_t line_stride,
+                         ParseOut *pout, const ScanTotals *totals, cudaStream_t st);
+cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
+                               const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st);
+cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,
+                              int64_t line_stride, ParseOut *pout, const ScanTotals *totals, cudaStream_t st);
+
+}  // namespace pp

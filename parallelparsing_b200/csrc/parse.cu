@@ -1,0 +1,391 @@
+// Kernel 2 — FASTQ parse, plus the small kernels around it.
+//
+// Replaces Parsing.Parse / ParseLine / CombinedMemory (Decompressor/Parsing.cs:11-117).
+// The reference walks the bytes of `from.offset ++ inflated ++ zeros` one at a
+// time; for well-formed input that is "every '\n' ends a line, every 4 lines are a
+// record, stop at the first NUL".  The fast kernel computes exactly that in one
+// streaming pass and proves, per chunk, that the input is in the regime where the
+// two definitions agree; a chunk that is not (a NUL inside the data, or an empty
+// id/'+' line, whose first byte Parsing.cs:19,30 would skip unchecked) is flagged
+// and re-parsed by the exact kernel below, which restates Parsing.cs literally.
+//
+// Layout: the combined memory of chunk k is CONTIGUOUS in the slots buffer: the
+// inflate kernel puts the checkpoint window right before the output and
+// from.offset is by construction the tail of that window (Core.cs:86-94,107), so
+// no concatenation or copy is needed.  Output is structure-of-arrays: four u32
+// arrays (one per FASTQ line) holding, for every record, the combined-memory index
+// of the first byte of that line.
+#include "kernels.cuh"
+
+namespace pp {
+
+constexpr int kParseThreads = 256;
+constexpr int kParseWarps = kParseThreads / 32;
+constexpr int kRows = 4;                                   // 16-byte vectors per lane per iteration
+constexpr int kWarpBytes = 32 * 16 * kRows;                // 2 KB per warp per iteration
+constexpr int kIterBytes = kWarpBytes * kParseWarps;       // 16 KB per CTA per iteration
+
+// 0x80 in every byte of w that equals '\n'
+__device__ __forceinline__ uint32_t nl_bytes(uint32_t w)
+{
+    const uint32_t x = w ^ 0x0a0a0a0au;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+// gather bits 7,15,23,31 into a nibble
+__device__ __forceinline__ uint32_t nibble(uint32_t t) { return ((t >> 7) * 0x01020408u) >> 24 & 15u; }
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// One CTA per chunk streams the chunk's combined memory in 16 KB steps.
+// lines: four arrays of `stride` u32 each (line 0..3), record r of the chunk at rec_base + r.
+__global__ void __launch_bounds__(kParseThreads) pp_parse_kernel(const uint8_t *__restrict__ slots,
+                                                                 const ParseDesc *__restrict__ pdesc, int n,
+                                                                 uint32_t *__restrict__ lines, int64_t stride,
+                                                                 ParseOut *__restrict__ pout,
+                                                                 const ScanTotals *__restrict__ totals)
+{
+    __shared__ uint32_t warp_tot[2][kParseWarps];
+    __shared__ uint32_t s_flags;
+    const int k = (int)blockIdx.x;
+    if (k >= n || totals->overflow) return;
+    const ParseDesc d = pdesc[k];
+    if (d.exact) return;  // handled by pp_exact_emit_kernel
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    if (threadIdx.x == 0) s_flags = 0;
+
+    const uint8_t *data = slots + d.data_off;
+    const uint32_t total = d.total;
+    const uint32_t head = (uint32_t)((uintptr_t)data & 15u);  // bytes before `data` in its first vector
+    const uint4 *vec0 = reinterpret_cast<const uint4 *>(data - head);
+    const uint32_t span = head + total;                       // bytes from vec0 to the end
+    const uint32_t rec_total = d.rec_count + d.skip;          // records in the chunk before skipping
+    uint32_t *const l_base = lines + d.rec_base;
+
+    if (threadIdx.x == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
+    uint32_t run = 0;      // newlines before this iteration
+    uint32_t flags = 0;
+    uint32_t end_pos = 0;  // written by the thread that sees newline 4R-1
+
+    for (uint32_t it0 = 0; it0 < span; it0 += kIterBytes) {
+        const uint32_t wbase = it0 + (uint32_t)warp * kWarpBytes;  // byte offset (from vec0) of this warp's block
+        uint32_t m[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            const uint32_t off = wbase + (uint32_t)r * 512u + (uint32_t)lane * 16u;
+            uint32_t mask = 0;
+            if (off < span) {
+                const uint4 v = ld_stream(vec0 + (off >> 4));
+                mask = nibble(nl_bytes(v.x)) | (nibble(nl_bytes(v.y)) << 4) | (nibble(nl_bytes(v.z)) << 8) |
+                       (nibble(nl_bytes(v.w)) << 12);
+                // bytes outside [head, span) are not part of the chunk
+                if (off < head) mask &= 0xffffu << (head - off);
+                if (off + 16u > span) mask &= 0xffffu >> (off + 16u - span);
+            }
+            m[r] = mask;
+        }
+        // successor bit of every vector: is the byte right after it a newline?
+        uint32_t fb = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; r++) fb |= (m[r] & 1u) << r;
+        uint32_t nfb = __shfl_down_sync(0xffffffffu, fb, 1);
+        const uint32_t fb0 = __shfl_sync(0xffffffffu, fb, 0);
+        if (lane == 31) {
+            nfb = fb0 >> 1;  // rows 0..2 continue at lane 0 of the next row
+            const uint32_t nxt = wbase + (uint32_t)kWarpBytes;  // first byte after this warp's block
+            if (nxt >= head && nxt < span && data[nxt - head] == '\n') nfb |= 1u << (kRows - 1);
+        }
+        // per-row counts, packed two per register, inclusive warp scan
+        uint32_t c01 = __popc(m[0]) | (__popc(m[1]) << 16), c23 = __popc(m[2]) | (__popc(m[3]) << 16);
+        uint32_t s01 = c01, s23 = c23;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, s01, sft), b = __shfl_up_sync(0xffffffffu, s23, sft);
+            if (lane >= sft) { s01 += a; s23 += b; }
+        }
+        const uint32_t t01 = __shfl_sync(0xffffffffu, s01, 31), t23 = __shfl_sync(0xffffffffu, s23, 31);
+        const uint32_t tot0 = t01 & 0xffffu, tot1 = t01 >> 16, tot2 = t23 & 0xffffu, tot3 = t23 >> 16;
+        const uint32_t wtot = tot0 + tot1 + tot2 + tot3;
+        const int buf = (int)((it0 / kIterBytes) & 1u);
+        if (lane == 0) warp_tot[buf][warp] = wtot;
+        __syncthreads();
+        uint32_t before = run, all = 0;
+#pragma unroll
+        for (int w = 0; w < kParseWarps; w++) {
+            const uint32_t t = warp_tot[buf][w];
+            if (w < warp) before += t;
+            all += t;
+        }
+        run += all;
+        // exclusive newline ordinal of each of this lane's vectors
+        uint32_t ex[kRows];
+        ex[0] = before + (s01 & 0xffffu) - (c01 & 0xffffu);
+        ex[1] = before + tot0 + (s01 >> 16) - (c01 >> 16);
+        ex[2] = before + tot0 + tot1 + (s23 & 0xffffu) - (c23 & 0xffffu);
+        ex[3] = before + tot0 + tot1 + tot2 + (s23 >> 16) - (c23 >> 16);
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            uint32_t mask = m[r];
+            if (mask == 0) continue;
+            const uint32_t off = wbase + (uint32_t)r * 512u + (uint32_t)lane * 16u;
+            // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
+            const uint32_t pairs = (mask | (((nfb >> r) & 1u) << 16)) & ((mask | (((nfb >> r) & 1u) << 16)) >> 1) & 0xffffu;
+            uint32_t ord = ex[r];
+            while (mask) {
+                const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                const uint32_t pos = off + b - head;  // combined-memory index of this '\n'
+                const uint32_t L = ord + 1u;          // the line that starts at pos + 1
+                const uint32_t rec = L >> 2, f = L & 3u;
+                if (((pairs >> b) & 1u) && (L & 1u) == 0u && rec < rec_total) flags |= 1u;
+                if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
+                if (rec >= d.skip) {
+                    if (rec < rec_total) l_base[(int64_t)f * stride + (rec - d.skip)] = pos + 1u;
+                    else if (L == rec_total * 4u) end_pos = pos + 1u;
+                }
+                ord++;
+            }
+        }
+    }
+    if (end_pos) pout[k].parse_end = end_pos;
+    if (flags) atomicOr(&s_flags, flags);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (rec_total == 0) pout[k].parse_end = 0;
+        pout[k].flags = s_flags;
+        pout[k].newlines = run;
+        pout[k].records = d.rec_count;
+    }
+}
+
+// ---- exact parser: Parsing.cs:11-69 literally, one thread per chunk -------------
+struct ExactCursor {
+    const uint8_t *d;
+    uint32_t total;
+    __device__ uint32_t at(uint32_t i) const { return i < total ? d[i] : 0u; }  // zero tail (H3)
+};
+// ParseLine (Parsing.cs:54-69): returns false when it meets NUL before '\n'
+__device__ bool exact_line(const ExactCursor &c, uint32_t &pos)
+{
+    for (;;) {
+        const uint32_t b = c.at(pos);
+        if (b == '\n') break;
+        if (b == 0u) return false;
+        pos++;
+    }
+    pos++;
+    return true;
+}
+// emit != nullptr: writes line starts; returns the record count
+__device__ uint32_t exact_parse(const ExactCursor &c, uint32_t skip, uint32_t *l_base, int64_t stride, bool emit,
+                                uint32_t *parse_end)
+{
+    uint32_t i = 0, n = 0, end = 0;
+    while (i < c.total) {
+        if (c.at(i) == 0u) break;  // :16
+        const uint32_t l0 = i;
+        i++;                       // :19 skip '@' unchecked
+        if (!exact_line(c, i)) break;
+        const uint32_t l1 = i;
+        if (!exact_line(c, i)) break;
+        const uint32_t l2 = i;
+        i++;                       // :30 skip '+' unchecked
+        if (!exact_line(c, i)) break;
+        const uint32_t l3 = i;
+        if (!exact_line(c, i)) break;
+        if (emit && n >= skip) {
+            const uint32_t r = n - skip;
+            l_base[r] = l0;
+            l_base[stride + r] = l1;
+            l_base[2 * stride + r] = l2;
+            l_base[3 * stride + r] = l3;
+        }
+        end = i;
+        n++;
+    }
+    if (parse_end) *parse_end = end;
+    return n;
+}
+
+__global__ void pp_exact_count_kernel(const uint8_t *__restrict__ slots, const ChunkDesc *__restrict__ descs,
+                                      const ChunkResult *__restrict__ results, const ParseOut *__restrict__ pout,
+                                      int n, int64_t *__restrict__ exact_counts)
+{
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= n) return;
+    const bool need = exact_counts[k] >= 0 || results[k].min_byte == 0u || (pout && (pout[k].flags & 1u));
+    if (!need || results[k].status != 0) return;
+    const ChunkDesc d = descs[k];
+    ExactCursor c{slots + d.slot_off + d.lead_len - d.prefix_len, d.prefix_len + results[k].produced};
+    exact_counts[k] = (int64_t)exact_parse(c, 0, nullptr, 0, false, nullptr);
+}
+
+__global__ void pp_exact_emit_kernel(const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc, int n,
+                                     uint32_t *__restrict__ lines, int64_t stride, ParseOut *__restrict__ pout,
+                                     const ScanTotals *__restrict__ totals)
+{
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= n || totals->overflow) return;
+    const ParseDesc d = pdesc[k];
+    if (!d.exact) return;
+    ExactCursor c{slots + d.data_off, d.total};
+    uint32_t end = 0;
+    const uint32_t cnt = exact_parse(c, d.skip, lines + d.rec_base, stride, true, &end);
+    pout[k].parse_end = end;
+    pout[k].flags = 2u;
+    pout[k].newlines = 0;
+    pout[k].records = cnt - (d.skip < cnt ? d.skip : cnt);
+}
+
+// ---- byte statistics for buffers that did not come out of the inflate kernel ------
+// (pp_parse on caller-provided bytes): '\n' count and minimum byte up to the first NUL.
+__global__ void __launch_bounds__(256) pp_bytes_stats_kernel(const uint8_t *__restrict__ slots,
+                                                             const ChunkDesc *__restrict__ descs,
+                                                             ChunkResult *__restrict__ results, int n)
+{
+    __shared__ uint32_t s_nl, s_min;
+    const int k = (int)blockIdx.x;
+    if (k >= n) return;
+    if (threadIdx.x == 0) { s_nl = 0; s_min = 255u; }
+    __syncthreads();
+    const ChunkDesc d = descs[k];
+    const uint8_t *p = slots + d.slot_off + d.lead_len;
+    uint32_t nl = 0, mn = 255u;
+    for (uint32_t i = threadIdx.x; i < d.out_len; i += blockDim.x) {
+        const uint32_t b = p[i];
+        nl += (b == 10u);
+        mn = b < mn ? b : mn;
+    }
+    atomicAdd(&s_nl, nl);
+    atomicMin(&s_min, mn);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        results[k].status = 0;
+        results[k].produced = d.out_len;
+        results[k].newlines = s_nl;
+        results[k].min_byte = s_min;
+        results[k].end_bit = 0;
+    }
+}
+
+// ---- record-base scan ---------------------------------------------------------------
+// One CTA: per-chunk record counts -> exclusive prefix sum -> ParseDesc.  Replaces the
+// host-side bookkeeping BatchedFASTQ does with its ConcurrentQueue (BatchedFASTQ.cs:69).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) pp_scan_kernel(const ChunkDesc *__restrict__ descs,
+                                                               const ChunkResult *__restrict__ results,
+                                                               const int64_t *__restrict__ exact_counts, int n,
+                                                               uint32_t strict, int64_t capacity,
+                                                               ParseDesc *__restrict__ pdesc,
+                                                               ScanTotals *__restrict__ totals)
+{
+    __shared__ int64_t s_part[kScanThreads];
+    __shared__ int64_t s_bytes[kScanThreads];
+    __shared__ int64_t s_scanned[kScanThreads];
+    __shared__ int s_first_k, s_status, s_exact;
+    const int t = (int)threadIdx.x;
+    if (t == 0) { s_first_k = n; s_status = 0; s_exact = 0; }
+    __syncthreads();
+    const int per = (n + kScanThreads - 1) / kScanThreads;
+    const int lo = min(n, t * per), hi = min(n, lo + per);
+    int64_t sum = 0, bytes = 0, scanned = 0;
+    int first_status = 0, first_k = n, nexact = 0;
+    for (int k = lo; k < hi; k++) {
+        const ChunkDesc d = descs[k];
+        const ChunkResult r = results[k];
+        uint32_t cnt = 0, skip = 0, exact = 0;
+        if (r.status == 0) {
+            cnt = (d.prefix_nl + r.newlines) >> 2;
+            if (exact_counts && exact_counts[k] >= 0) { cnt = (uint32_t)exact_counts[k]; exact = 1; }
+            if (strict && d.prefix_nl >= 4u) skip = min(cnt, d.prefix_nl >> 2);
+        } else if (first_status == 0) {
+            first_status = r.status;
+            first_k = k;
+        }
+        ParseDesc p;
+        p.data_off = d.slot_off + d.lead_len - d.prefix_len;
+        p.total = r.status == 0 ? d.prefix_len + r.produced : 0u;
+        p.rec_count = cnt - skip;
+        p.skip = skip;
+        p.exact = exact;
+        p.rec_base = sum;  // local to this thread's range; rebased below
+        pdesc[k] = p;
+        sum += cnt - skip;
+        bytes += r.produced;
+        scanned += p.total;
+        nexact += (int)exact;
+    }
+    s_part[t] = sum;
+    s_bytes[t] = bytes;
+    s_scanned[t] = scanned;
+    if (first_status) atomicMin(&s_first_k, first_k);
+    if (nexact) atomicAdd(&s_exact, nexact);
+    __syncthreads();
+    if (first_status && s_first_k == first_k) s_status = first_status;
+    if (t == 0) {
+        // n <= a few 100k chunks: a serial pass over 1024 partials is negligible
+        int64_t acc = 0, b = 0, sc = 0;
+        for (int i = 0; i < kScanThreads; i++) {
+            const int64_t v = s_part[i];
+            s_part[i] = acc;
+            acc += v;
+            b += s_bytes[i];
+            sc += s_scanned[i];
+        }
+        totals->total_records = acc;
+        totals->total_bytes = b;
+        totals->scanned_bytes = sc;
+        totals->overflow = acc > capacity ? 1 : 0;
+    }
+    __syncthreads();
+    const int64_t base = s_part[t];
+    for (int k = lo; k < hi; k++) pdesc[k].rec_base += base;
+    if (t == 0) {
+        totals->first_status = s_status;
+        totals->exact_chunks = s_exact;
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------
+cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
+                               cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pp_bytes_stats_kernel<<<n, 256, 0, st>>>(slots, descs, results, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,
+                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ScanTotals *totals, cudaStream_t st)
+{
+    pp_scan_kernel<<<1, kScanThreads, 0, st>>>(descs, results, exact_counts, n, strict, capacity, pdesc, totals);
+    return cudaGetLastError();
+}
+cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines, int64_t line_stride,
+                         ParseOut *pout, const ScanTotals *totals, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pp_parse_kernel<<<n, kParseThreads, 0, st>>>(slots, pdesc, n, lines, line_stride, pout, totals);
+    return cudaGetLastError();
+}
+cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
+                               const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pp_exact_count_kernel<<<(n + 31) / 32, 32, 0, st>>>(slots, descs, results, pout, n, exact_counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,
+                              int64_t line_stride, ParseOut *pout, const ScanTotals *totals, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pp_exact_emit_kernel<<<(n + 31) / 32, 32, 0, st>>>(slots, pdesc, n, lines, line_stride, pout, totals);
+    return cudaGetLastError();
+}
+
+}  // namespace pp

@@ -1,0 +1,741 @@
+// Host runtime behind the C ABI: device context, DecompressAll jobs,
+// Decompress(checkpoint) and Parse on caller buffers.
+//
+// DecompressAll (BatchedFASTQ, Decompressor/BatchedFASTQ.cs:54-98) becomes a
+// plan ("job") over a contiguous chunk range:
+//   upload   one H2D copy of the compressed byte range [Input_first-1, Input_last)
+//            (LazyFileReader.cs:63-69 reads the same bytes chunk by chunk) and one of
+//            the checkpoint windows, both from pinned host memory;
+//   execute  inflate kernel (one CTA per chunk) -> exact-count kernel (only chunks that
+//            need the quirk-exact parser do work) -> record-base scan -> parse kernel;
+//   download per-chunk results.
+// Chunks are independent: a multi-GPU run gives every rank its own
+// pp_ctx and a disjoint chunk range; there is no cross-GPU exchange.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "index.hpp"
+#include "kernels.cuh"
+#include "ppb200.h"
+
+using namespace pp;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "ppb200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PP_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+// Small RAII helper for the single-call entry points.
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    template <class T> T *as() { return (T *)p; }
+};
+
+struct pp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int sm_count = 0;
+};
+
+static constexpr uint64_t kTile = ppinf::kTileBytes;
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct pp_job {
+    pp_ctx *ctx = nullptr;
+    const pp_index *ix = nullptr;
+    int32_t first = 0, n = 0;
+    uint32_t flags = 0;
+    // host plan
+    std::vector<ChunkDesc> descs;
+    uint64_t comp_file_lo = 0;   // file offset of device compressed byte 0 (16 B aligned)
+    uint64_t comp_copy = 0;      // bytes copied from the file
+    uint64_t comp_alloc = 0;     // device bytes (tile multiple, + one spare tile)
+    uint64_t slots_bytes = 0;
+    uint64_t lead_bytes = 0;
+    bool lead_direct = true;     // leads are exactly the index windows (one contiguous copy)
+    uint8_t *h_lead = nullptr;   // pinned staging when !lead_direct
+    int64_t rec_cap = 0;
+    // device
+    uint8_t *d_comp = nullptr, *d_lead = nullptr, *d_slots = nullptr;
+    ChunkDesc *d_descs = nullptr;
+    ChunkResult *d_results = nullptr;
+    ParseDesc *d_pdesc = nullptr;
+    ParseOut *d_pout = nullptr;
+    ScanTotals *d_totals = nullptr;
+    int64_t *d_exact = nullptr;
+    uint32_t *d_lines = nullptr;
+    // pinned host mirrors
+    ChunkResult *h_results = nullptr;
+    ParseDesc *h_pdesc = nullptr;
+    ParseOut *h_pout = nullptr;
+    ScanTotals *h_totals = nullptr;
+    bool have_results = false;
+    bool zero_copy = false;
+    const uint8_t *zc_comp = nullptr;  // device-visible alias of the caller's pinned gz buffer
+    cudaEvent_t ev[8] = {};
+    pp_job_info info{};
+};
+
+// --------------------------------------------------------------------------- ctx
+
+static int check_device(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PP_E_NO_DEVICE;
+    if (device < 0 || device >= count) return PP_E_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PP_E_CUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "ppb200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major,
+                prop.minor);
+        return PP_E_NO_DEVICE;
+    }
+    return PP_OK;
+}
+
+extern "C" void pp_internal_unpin_index(const pp_index *ix)
+{
+    if (ix && ix->pinned_base) {
+        cudaHostUnregister(ix->pinned_base);
+        ix->pinned_base = nullptr;
+        ix->pinned_bytes = 0;
+    }
+}
+
+static void pin_index_windows(const pp_index *ix)
+{
+    const size_t bytes = (size_t)ix->count() * PP_WINSIZE;
+    if (!ix->windows || bytes == 0) return;
+    if (ix->pinned_base == ix->windows && ix->pinned_bytes >= bytes) return;
+    pp_internal_unpin_index(ix);
+    // pin the whole allocation so later points added in place stay covered
+    const size_t cap_bytes = ix->win_cap * (size_t)PP_WINSIZE;
+    if (cudaHostRegister(ix->windows, cap_bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        ix->pinned_base = ix->windows;
+        ix->pinned_bytes = cap_bytes;
+    } else {
+        cudaGetLastError();  // stay pageable: copies still work, just slower
+    }
+}
+
+extern "C" {
+
+int pp_open(int32_t device, pp_ctx **out)
+{
+    if (!out) return PP_E_ARG;
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc != PP_OK) return rc;
+    pp_ctx *c = new (std::nothrow) pp_ctx();
+    if (!c) return PP_MEM_ERROR;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return PP_E_CUDA;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return PP_OK;
+}
+
+void pp_close(pp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int pp_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return PP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PP_E_NO_DEVICE;
+    // two spare TMA tiles behind the data: PP_JOB_ZEROCOPY kernels read whole tiles
+    CK(cudaHostAlloc(out, bytes + 4 * kTile, cudaHostAllocPortable));
+    memset((uint8_t *)*out + bytes, 0, 4 * kTile);
+    return PP_OK;
+}
+void pp_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+int pp_host_register(void *p, size_t bytes)
+{
+    if (!p) return PP_E_ARG;
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return PP_OK;
+}
+void pp_host_unregister(void *p)
+{
+    if (p) cudaHostUnregister(p);
+}
+
+// --------------------------------------------------------------------------- job
+
+void pp_job_free(pp_job *j)
+{
+    if (!j) return;
+    if (j->ctx) {
+        std::lock_guard<std::mutex> lk(j->ctx->mu);
+        cudaSetDevice(j->ctx->device);
+        cudaStreamSynchronize(j->ctx->stream);
+    }
+    cudaFree(j->d_comp);
+    cudaFree(j->d_lead);
+    cudaFree(j->d_slots);
+    cudaFree(j->d_descs);
+    cudaFree(j->d_results);
+    cudaFree(j->d_pdesc);
+    cudaFree(j->d_pout);
+    cudaFree(j->d_totals);
+    cudaFree(j->d_exact);
+    cudaFree(j->d_lines);
+    cudaFreeHost(j->h_lead);
+    cudaFreeHost(j->h_results);
+    cudaFreeHost(j->h_pdesc);
+    cudaFreeHost(j->h_pout);
+    cudaFreeHost(j->h_totals);
+    for (auto &e : j->ev)
+        if (e) cudaEventDestroy(e);
+    delete j;
+}
+
+static int job_alloc_lines(pp_job *j, int64_t cap)
+{
+    if (j->d_lines) cudaFree(j->d_lines);
+    j->d_lines = nullptr;
+    j->rec_cap = std::max<int64_t>(cap, 16);
+    CK(cudaMalloc(&j->d_lines, (size_t)j->rec_cap * 4 * sizeof(uint32_t)));
+    return PP_OK;
+}
+
+// Lay out one chunk: where its compressed bits start, where its slot lives, what goes in
+// front of its output.  `lead_len` bytes of history precede the output; normally that is
+// the 32 KB checkpoint window, of which from.offset is the tail (Core.cs:86-94,107).
+static void count_prefix(const uint8_t *p, int32_t n, uint32_t *nl, bool *has_nul)
+{
+    uint32_t c = 0;
+    bool z = false;
+    for (int32_t i = 0; i < n; i++) {
+        c += (p[i] == '\n');
+        z |= (p[i] == 0);
+    }
+    *nl = c;
+    *has_nul = z;
+}
+
+}  // extern "C"
+
+static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_chunk, int n)
+{
+    auto fail = [&](int rc) { return rc; };
+    try {
+        j->descs.resize((size_t)std::max(n, 1));
+        std::vector<uint8_t> forced_exact((size_t)std::max(n, 1), 0);
+        // compressed range: one byte before Input_first (the Bits live there) .. Input_last
+        uint64_t lo = 0, hi = 0;
+        if (n > 0) {
+            const int64_t in0 = ix->input[(size_t)first_chunk];
+            lo = in0 > 0 ? (uint64_t)(in0 - 1) : 0;
+            lo &= ~(uint64_t)127;  // keep file offsets and device offsets congruent mod 128
+            hi = std::min<uint64_t>((uint64_t)ix->input[(size_t)(first_chunk + n)], gz_len);
+            if (hi < lo) hi = lo;
+        }
+        j->comp_file_lo = lo;
+        j->comp_copy = hi - lo;
+        j->comp_alloc = align_up(j->comp_copy, kTile) + 2 * kTile;
+        uint64_t slot_off = 0, lead_off = 0;
+        int64_t scanned = 0;
+        for (int k = 0; k < n; k++) {
+            const int c = first_chunk + k;
+            ChunkDesc &d = j->descs[(size_t)k];
+            const int64_t in = ix->input[(size_t)c], out_lo = ix->output[(size_t)c], out_hi = ix->output[(size_t)c + 1];
+            const int32_t bits = ix->bits[(size_t)c];
+            const int64_t len = out_hi - out_lo;
+            if (len < 0 || len > 0x7fffffffLL || (uint64_t)in < lo) return fail(PP_E_ARG);
+            d.in_bit = ((uint64_t)in - lo) * 8u - (uint64_t)bits;
+            d.in_limit = std::min<uint64_t>((uint64_t)ix->input[(size_t)c + 1], gz_len) - lo;
+            d.out_len = (uint32_t)len;
+            const int32_t ol = ix->off_len[(size_t)c];
+            d.prefix_len = (uint32_t)ol;
+            bool nul = false;
+            count_prefix(ix->offset(c), ol, &d.prefix_nl, &nul);
+            // from.offset must be the tail of the history placed before the output
+            bool tail_ok = true;
+            if (ol <= PP_WINSIZE) {
+                tail_ok = ol == 0 || memcmp(ix->window(c) + PP_WINSIZE - ol, ix->offset(c), (size_t)ol) == 0;
+                d.lead_len = PP_WINSIZE;
+            } else {
+                tail_ok = memcmp(ix->offset(c) + ol - PP_WINSIZE, ix->window(c), PP_WINSIZE) == 0;
+                d.lead_len = (uint32_t)align_up((uint64_t)ol, 16);
+                j->lead_direct = false;
+            }
+            if (!tail_ok) return fail(PP_E_ARG);  // index whose offset is not the stream tail: not produced by CreateIndex
+            if (nul) forced_exact[(size_t)k] = 1;
+            d.lead_src = lead_off;
+            lead_off += d.lead_len;
+            d.slot_off = slot_off;
+            slot_off += align_up((uint64_t)d.lead_len + d.out_len + 1, 128);
+            scanned += (int64_t)d.prefix_len + d.out_len;
+        }
+        j->slots_bytes = std::max<uint64_t>(slot_off, 128);
+        j->lead_bytes = std::max<uint64_t>(lead_off, 16);
+
+        CK(cudaMalloc(&j->d_slots, j->slots_bytes));
+        CK(cudaMalloc(&j->d_descs, sizeof(ChunkDesc) * (size_t)std::max(n, 1)));
+        CK(cudaMalloc(&j->d_results, sizeof(ChunkResult) * (size_t)std::max(n, 1)));
+        CK(cudaMalloc(&j->d_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1)));
+        CK(cudaMalloc(&j->d_pout, sizeof(ParseOut) * (size_t)std::max(n, 1)));
+        CK(cudaMalloc(&j->d_totals, sizeof(ScanTotals)));
+        CK(cudaMalloc(&j->d_exact, sizeof(int64_t) * (size_t)std::max(n, 1)));
+        CK(cudaHostAlloc(&j->h_results, sizeof(ChunkResult) * (size_t)std::max(n, 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_pout, sizeof(ParseOut) * (size_t)std::max(n, 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&j->h_totals, sizeof(ScanTotals), cudaHostAllocDefault));
+        if (!j->zero_copy) {
+            CK(cudaMalloc(&j->d_comp, j->comp_alloc));
+            CK(cudaMemsetAsync(j->d_comp, 0, j->comp_alloc, ctx->stream));
+            CK(cudaMalloc(&j->d_lead, j->lead_bytes));
+        }
+        if (j->lead_direct) {
+            pin_index_windows(ix);
+        } else {
+            CK(cudaHostAlloc(&j->h_lead, j->lead_bytes, cudaHostAllocDefault));
+            for (int k = 0; k < n; k++) {
+                const int c = first_chunk + k;
+                const ChunkDesc &d = j->descs[(size_t)k];
+                uint8_t *dst = j->h_lead + d.lead_src;
+                const int32_t ol = ix->off_len[(size_t)c];
+                if (ol <= PP_WINSIZE) {
+                    memcpy(dst, ix->window(c), PP_WINSIZE);
+                } else {
+                    const uint32_t padn = d.lead_len - (uint32_t)ol;
+                    memset(dst, 0, padn);
+                    memcpy(dst + padn, ix->offset(c), (size_t)ol);
+                }
+            }
+        }
+        // records: start from >= 32 bytes per record; execute() grows the arrays if a corpus
+        // has shorter records (the scan kernel reports the exact need)
+        int rc = job_alloc_lines(j, scanned / 32 + n + 16);
+        if (rc != PP_OK) return fail(rc);
+        // exact-count overrides: -1 = none; 0 = forced through the exact parser
+        std::vector<int64_t> ex((size_t)std::max(n, 1), -1);
+        for (int k = 0; k < n; k++)
+            if (forced_exact[(size_t)k]) ex[(size_t)k] = 0;
+        CK(cudaMemcpyAsync(j->d_exact, ex.data(), sizeof(int64_t) * (size_t)std::max(n, 1), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CK(cudaMemcpyAsync(j->d_descs, j->descs.data(), sizeof(ChunkDesc) * (size_t)std::max(n, 1),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(j->d_pout, 0, sizeof(ParseOut) * (size_t)std::max(n, 1), ctx->stream));
+        CK(cudaMemsetAsync(j->d_results, 0, sizeof(ChunkResult) * (size_t)std::max(n, 1), ctx->stream));
+        for (auto &e : j->ev) CK(cudaEventCreate(&e));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        return fail(PP_MEM_ERROR);
+    }
+    return PP_OK;
+}
+
+extern "C" {
+
+int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_chunk, int32_t n_chunks,
+                  uint32_t flags, pp_job **out)
+{
+    if (!ctx || !ix || !out) return PP_E_ARG;
+    *out = nullptr;
+    const int32_t nchunks_total = ix->count() - 1;
+    if (n_chunks < 0) n_chunks = nchunks_total - first_chunk;
+    if (first_chunk < 0 || n_chunks < 0 || first_chunk + n_chunks > nchunks_total) return PP_E_ARG;
+    pp_job *j = nullptr;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        j = new (std::nothrow) pp_job();
+        if (!j) return PP_MEM_ERROR;
+        j->ctx = nullptr;  // set on success; pp_job_free must not lock the mutex we hold
+        j->ix = ix;
+        j->first = first_chunk;
+        j->n = n_chunks;
+        j->flags = flags;
+        j->zero_copy = (flags & PP_JOB_ZEROCOPY) != 0;
+        rc = job_create_inner(j, ctx, ix, gz_len, first_chunk, n_chunks);
+    }
+    if (rc != PP_OK) {
+        pp_job_free(j);
+        return rc;
+    }
+    j->info.first_chunk = first_chunk;
+    j->info.n_chunks = n_chunks;
+    j->ctx = ctx;
+    *out = j;
+    return PP_OK;
+}
+
+int pp_job_upload(pp_job *j, const uint8_t *gz)
+{
+    if (!j || !j->ctx || (!gz && j->comp_copy)) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    cudaStream_t st = j->ctx->stream;
+    CK(cudaEventRecord(j->ev[0], st));
+    int64_t h2d = 0;
+    if (j->zero_copy) {
+        // kernels read the caller's pinned buffer through its device alias: nothing to copy
+        void *dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(gz), 0));
+        j->zc_comp = (const uint8_t *)dp + j->comp_file_lo;
+    } else if (j->n > 0) {
+        CK(cudaMemcpyAsync(j->d_comp, gz + j->comp_file_lo, j->comp_copy, cudaMemcpyHostToDevice, st));
+        h2d += (int64_t)j->comp_copy;
+        const uint8_t *src = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
+        CK(cudaMemcpyAsync(j->d_lead, src, j->lead_bytes, cudaMemcpyHostToDevice, st));
+        h2d += (int64_t)j->lead_bytes;
+    }
+    CK(cudaEventRecord(j->ev[1], st));
+    j->info.h2d_bytes = h2d;
+    return PP_OK;
+}
+
+static int job_parse_stage(pp_job *j, cudaStream_t st, bool with_pout_flags, int *launches)
+{
+    const int n = j->n;
+    if (launch_exact_count(j->d_slots, j->d_descs, j->d_results, with_pout_flags ? j->d_pout : nullptr, n, j->d_exact,
+                           st) != cudaSuccess)
+        return PP_E_CUDA;
+    if (launch_scan(j->d_descs, j->d_results, j->d_exact, n, (j->flags & PP_JOB_STRICT) ? 1u : 0u, j->rec_cap,
+                    j->d_pdesc, j->d_totals, st) != cudaSuccess)
+        return PP_E_CUDA;
+    CK(cudaEventRecord(j->ev[4], st));
+    if (launch_parse(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st) != cudaSuccess)
+        return PP_E_CUDA;
+    CK(cudaEventRecord(j->ev[5], st));
+    if (launch_exact_emit(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st) != cudaSuccess)
+        return PP_E_CUDA;
+    *launches += n > 0 ? 4 : 1;
+    return PP_OK;
+}
+
+int pp_job_execute(pp_job *j)
+{
+    if (!j || !j->ctx) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    cudaStream_t st = j->ctx->stream;
+    int launches = 0;
+    CK(cudaEventRecord(j->ev[2], st));
+    const uint8_t *comp = j->zero_copy ? j->zc_comp : j->d_comp;
+    const uint8_t *lead = j->d_lead;
+    uint64_t comp_bytes = j->comp_alloc;
+    if (j->zero_copy) {
+        if (!comp) return PP_E_ARG;
+        void *dp = nullptr;
+        const uint8_t *hl = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
+        CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(hl), 0));
+        lead = (const uint8_t *)dp;
+        comp_bytes = align_up(j->comp_copy, kTile) + kTile;  // pp_host_alloc keeps spare tiles behind the data
+    }
+    if (launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, st) != cudaSuccess)
+        return PP_E_CUDA;
+    launches += j->n > 0 ? 1 : 0;
+    CK(cudaEventRecord(j->ev[3], st));
+    int rc = job_parse_stage(j, st, false, &launches);
+    if (rc != PP_OK) return rc;
+    j->info.launches = launches;
+    j->have_results = false;
+    return PP_OK;
+}
+
+int pp_job_download(pp_job *j)
+{
+    if (!j || !j->ctx) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    cudaStream_t st = j->ctx->stream;
+    const size_t n = (size_t)std::max(j->n, 1);
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaEventRecord(j->ev[6], st));
+        CK(cudaMemcpyAsync(j->h_results, j->d_results, sizeof(ChunkResult) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(j->h_pdesc, j->d_pdesc, sizeof(ParseDesc) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(j->h_pout, j->d_pout, sizeof(ParseOut) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(j->h_totals, j->d_totals, sizeof(ScanTotals), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(j->ev[7], st));
+        CK(cudaStreamSynchronize(st));
+        bool redo = false;
+        if (j->h_totals->overflow) {
+            // more records than the arrays hold: grow to the exact need and parse again
+            int rc = job_alloc_lines(j, j->h_totals->total_records + 16);
+            if (rc != PP_OK) return rc;
+            redo = true;
+        } else {
+            for (int k = 0; k < j->n; k++)
+                if ((j->h_pout[k].flags & 1u) && !j->h_pdesc[k].exact) { redo = true; break; }
+        }
+        if (!redo) break;
+        int launches = 0;
+        int rc = job_parse_stage(j, st, true, &launches);
+        if (rc != PP_OK) return rc;
+        j->info.launches += launches;
+    }
+    pp_job_info &I = j->info;
+    I.total_records = j->h_totals->total_records;
+    I.total_bytes = j->h_totals->total_bytes;
+    I.scanned_bytes = j->h_totals->scanned_bytes;
+    I.status = j->h_totals->first_status;
+    I.exact_chunks = j->h_totals->exact_chunks;
+    I.compressed_bytes = (int64_t)j->comp_copy;
+    I.d2h_bytes = (int64_t)((sizeof(ChunkResult) + sizeof(ParseDesc) + sizeof(ParseOut)) * n + sizeof(ScanTotals));
+    auto ms = [&](float *dst, int a, int b) {
+        if (cudaEventElapsedTime(dst, j->ev[a], j->ev[b]) != cudaSuccess) {
+            *dst = 0.f;  // an event not recorded yet (e.g. no upload) is not an error of the job
+            cudaGetLastError();
+        }
+    };
+    ms(&I.upload_ms, 0, 1);
+    ms(&I.inflate_ms, 2, 3);
+    ms(&I.scan_ms, 3, 4);
+    ms(&I.parse_ms, 4, 5);
+    ms(&I.download_ms, 6, 7);
+    j->have_results = true;
+    return PP_OK;
+}
+
+int pp_job_info_get(const pp_job *j, pp_job_info *out)
+{
+    if (!j || !out) return PP_E_ARG;
+    *out = j->info;
+    return PP_OK;
+}
+
+int pp_job_chunk_info(const pp_job *j, int32_t k, pp_chunk_info *out)
+{
+    if (!j || !out || k < 0 || k >= j->n || !j->have_results) return PP_E_ARG;
+    const ChunkResult &r = j->h_results[k];
+    const ParseDesc &p = j->h_pdesc[k];
+    const ParseOut &o = j->h_pout[k];
+    out->status = r.status;
+    out->prefix_len = (int32_t)j->descs[(size_t)k].prefix_len;
+    out->inflated = r.produced;
+    out->records = p.rec_count;
+    out->record_base = p.rec_base;
+    out->parse_end = o.parse_end;
+    out->flags = p.exact ? 1u : 0u;
+    return PP_OK;
+}
+
+int pp_job_fetch_line_starts(pp_job *j, uint32_t *l0, uint32_t *l1, uint32_t *l2, uint32_t *l3)
+{
+    if (!j || !j->ctx || !j->have_results) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    const size_t bytes = (size_t)j->info.total_records * sizeof(uint32_t);
+    uint32_t *dst[4] = {l0, l1, l2, l3};
+    for (int f = 0; f < 4; f++)
+        if (dst[f] && bytes)
+            CK(cudaMemcpyAsync(dst[f], j->d_lines + (size_t)f * (size_t)j->rec_cap, bytes, cudaMemcpyDeviceToHost,
+                               j->ctx->stream));
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
+int pp_job_fetch_chunk(pp_job *j, int32_t k, uint8_t *dst, int64_t cap)
+{
+    if (!j || !j->ctx || !j->have_results || k < 0 || k >= j->n || !dst) return PP_E_ARG;
+    const int64_t nbytes = j->h_results[k].produced;
+    if (cap < nbytes) return PP_BUF_ERROR;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    const ChunkDesc &d = j->descs[(size_t)k];
+    if (nbytes) CK(cudaMemcpyAsync(dst, j->d_slots + d.slot_off + d.lead_len, (size_t)nbytes, cudaMemcpyDeviceToHost, j->ctx->stream));
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
+int pp_job_fetch_bytes(pp_job *j, uint8_t *dst, int64_t cap)
+{
+    if (!j || !j->ctx || !j->have_results || !dst) return PP_E_ARG;
+    if (cap < j->info.total_bytes) return PP_BUF_ERROR;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    int64_t pos = 0;
+    for (int k = 0; k < j->n; k++) {
+        const ChunkDesc &d = j->descs[(size_t)k];
+        const int64_t nbytes = j->h_results[k].produced;
+        if (nbytes) CK(cudaMemcpyAsync(dst + pos, j->d_slots + d.slot_off + d.lead_len, (size_t)nbytes, cudaMemcpyDeviceToHost, j->ctx->stream));
+        pos += nbytes;
+    }
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
+int pp_job_device_ptrs(const pp_job *j, const uint8_t **slots, const uint64_t **chunk_data_off, const uint32_t **l0,
+                       const uint32_t **l1, const uint32_t **l2, const uint32_t **l3)
+{
+    if (!j) return PP_E_ARG;
+    if (slots) *slots = j->d_slots;
+    // ParseDesc is {u64 data_off, ...} with a 32-byte stride; the first field is the offset
+    if (chunk_data_off) *chunk_data_off = reinterpret_cast<const uint64_t *>(j->d_pdesc);
+    const uint32_t *b = j->d_lines;
+    if (l0) *l0 = b;
+    if (l1) *l1 = b + (size_t)j->rec_cap;
+    if (l2) *l2 = b + 2 * (size_t)j->rec_cap;
+    if (l3) *l3 = b + 3 * (size_t)j->rec_cap;
+    return PP_OK;
+}
+
+int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t gz_len, int32_t first_chunk,
+                      int32_t n_chunks, uint32_t flags, pp_job **out)
+{
+    if (!out) return PP_E_ARG;
+    pp_job *j = nullptr;
+    int rc = pp_job_create(ctx, ix, gz_len, first_chunk, n_chunks, flags, &j);
+    if (rc != PP_OK) return rc;
+    rc = pp_job_upload(j, gz);
+    if (rc == PP_OK) rc = pp_job_execute(j);
+    if (rc == PP_OK) rc = pp_job_download(j);
+    if (rc != PP_OK) {
+        pp_job_free(j);
+        return rc;
+    }
+    *out = j;
+    return j->info.status;
+}
+
+// ------------------------------------------------------------ single-call entry points
+
+
+int64_t pp_extract(pp_ctx *ctx, const uint8_t *fileBuffer, int64_t fileBufferLen, const pp_index *ix,
+                   int32_t from_point, uint8_t *buf, int64_t buf_len)
+{
+    if (!ctx || !fileBuffer || !ix || !buf || fileBufferLen < 0) return PP_E_ARG;
+    if (from_point < 0 || from_point + 1 >= ix->count()) return PP_E_ARG;
+    const int64_t len64 = ix->output[(size_t)from_point + 1] - ix->output[(size_t)from_point];
+    if ((int32_t)len64 < 0) return 0;  // Core.cs:145
+    if (len64 > buf_len || len64 > 0x7fffffffLL) return PP_BUF_ERROR;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int32_t bits = ix->bits[(size_t)from_point];
+    // fileBuffer[0] is file byte from.Input-1 (LazyFileReader.cs:68): the stream starts
+    // `bits` bits before fileBuffer[1] (Core.cs:151-157)
+    ChunkDesc d{};
+    d.in_bit = 8u - (uint64_t)bits;
+    d.in_limit = (uint64_t)fileBufferLen;
+    d.slot_off = 0;
+    d.lead_src = 0;
+    d.lead_len = PP_WINSIZE;
+    d.out_len = (uint32_t)len64;
+    const uint64_t comp_alloc = align_up((uint64_t)fileBufferLen, kTile) + 2 * kTile;
+    const uint64_t slot_bytes = align_up((uint64_t)PP_WINSIZE + d.out_len + 1, 128);
+    DevBuf comp, lead, slot, desc, res;
+    CK(comp.alloc(comp_alloc));
+    CK(lead.alloc(PP_WINSIZE));
+    CK(slot.alloc(slot_bytes));
+    CK(desc.alloc(sizeof d));
+    CK(res.alloc(sizeof(ChunkResult)));
+    CK(cudaMemsetAsync(comp.p, 0, comp_alloc, st));
+    CK(cudaMemcpyAsync(comp.p, fileBuffer, (size_t)fileBufferLen, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(lead.p, ix->window(from_point), PP_WINSIZE, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(desc.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
+    if (launch_inflate(desc.as<ChunkDesc>(), 1, comp.as<uint8_t>(), comp_alloc, slot.as<uint8_t>(), lead.as<uint8_t>(),
+                       res.as<ChunkResult>(), st) != cudaSuccess)
+        return PP_E_CUDA;
+    ChunkResult r{};
+    CK(cudaMemcpyAsync(&r, res.p, sizeof r, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (r.status < 0) return r.status;  // the reference throws ZException(code), Core.cs:178-179
+    if (r.produced) CK(cudaMemcpyAsync(buf, slot.as<uint8_t>() + PP_WINSIZE, r.produced, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (int64_t)r.produced;
+}
+
+int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const uint8_t *rest, int64_t rest_len,
+                 uint32_t *line_starts, int64_t cap, uint32_t *parse_end)
+{
+    if (!ctx || prepend_len < 0 || rest_len < 0 || (prepend_len && !prepend) || (rest_len && !rest)) return PP_E_ARG;
+    if (prepend_len + rest_len > 0x7fffffffLL) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ChunkDesc d{};
+    d.lead_len = (uint32_t)align_up((uint64_t)prepend_len, 16);
+    d.out_len = (uint32_t)rest_len;
+    d.prefix_len = (uint32_t)prepend_len;
+    bool nul = false;
+    count_prefix(prepend, (int32_t)prepend_len, &d.prefix_nl, &nul);
+    const uint64_t slot_bytes = align_up((uint64_t)d.lead_len + d.out_len + 1, 128);
+    const int64_t rec_cap = (prepend_len + rest_len) / 4 + 16;
+    DevBuf slot, desc, res, pdesc, pout, totals, exact, lines;
+    CK(slot.alloc(slot_bytes));
+    CK(desc.alloc(sizeof d));
+    CK(res.alloc(sizeof(ChunkResult)));
+    CK(pdesc.alloc(sizeof(ParseDesc)));
+    CK(pout.alloc(sizeof(ParseOut)));
+    CK(totals.alloc(sizeof(ScanTotals)));
+    CK(exact.alloc(sizeof(int64_t)));
+    CK(lines.alloc((size_t)rec_cap * 4 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(slot.p, 0, slot_bytes, st));
+    CK(cudaMemsetAsync(pout.p, 0, sizeof(ParseOut), st));
+    if (prepend_len)
+        CK(cudaMemcpyAsync(slot.as<uint8_t>() + d.lead_len - prepend_len, prepend, (size_t)prepend_len,
+                           cudaMemcpyHostToDevice, st));
+    if (rest_len) CK(cudaMemcpyAsync(slot.as<uint8_t>() + d.lead_len, rest, (size_t)rest_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(desc.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
+    const int64_t ex0 = nul ? 0 : -1;
+    CK(cudaMemcpyAsync(exact.p, &ex0, sizeof ex0, cudaMemcpyHostToDevice, st));
+    if (launch_bytes_stats(slot.as<uint8_t>(), desc.as<ChunkDesc>(), res.as<ChunkResult>(), 1, st) != cudaSuccess)
+        return PP_E_CUDA;
+    ParseOut o{};
+    ParseDesc p{};
+    for (int pass = 0; pass < 2; pass++) {
+        if (launch_exact_count(slot.as<uint8_t>(), desc.as<ChunkDesc>(), res.as<ChunkResult>(),
+                               pass ? pout.as<ParseOut>() : nullptr, 1, exact.as<int64_t>(), st) != cudaSuccess ||
+            launch_scan(desc.as<ChunkDesc>(), res.as<ChunkResult>(), exact.as<int64_t>(), 1, 0, rec_cap,
+                        pdesc.as<ParseDesc>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
+            launch_parse(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, lines.as<uint32_t>(), rec_cap,
+                         pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
+            launch_exact_emit(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, lines.as<uint32_t>(), rec_cap,
+                              pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess)
+            return PP_E_CUDA;
+        CK(cudaMemcpyAsync(&o, pout.p, sizeof o, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&p, pdesc.p, sizeof p, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!((o.flags & 1u) && !p.exact)) break;
+    }
+    const int64_t nrec = p.rec_count;
+    if (parse_end) *parse_end = o.parse_end;
+    if (line_starts && cap > 0 && nrec > 0) {
+        // interleave the four arrays into line_starts[4r + f] on the host side of the copy
+        const int64_t m = std::min(nrec, cap);
+        std::vector<uint32_t> tmp((size_t)m * 4);
+        for (int f = 0; f < 4; f++)
+            CK(cudaMemcpyAsync(tmp.data() + (size_t)f * (size_t)m, lines.as<uint32_t>() + (size_t)f * (size_t)rec_cap,
+                               (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int64_t r = 0; r < m; r++)
+            for (int f = 0; f < 4; f++) line_starts[4 * r + f] = tmp[(size_t)f * (size_t)m + (size_t)r];
+    }
+    return nrec;
+}
+
+}  // extern "C"
