@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — DecompressAll throughput (uncompressed GB/s, reads/s) of the B200 path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--reads R] [--chunk C]
+
+A "step" is one DecompressAll pass over the whole indexed gzip FASTQ (BASELINE.json
+configs[1]: Generator seed 0, 10 M reads x 150 bp, gzip level 6, chunk 10,000).
+  value   : uncompressed GB/s with the compressed bytes and checkpoint windows already in
+            HBM (pp_job_execute only: inflate kernel -> scan -> parse kernel)
+  e2e     : same metric through the C ABI with HOST buffers: H2D of the compressed range
+            and windows from pinned memory + kernels + D2H of the per-chunk results, every step
+  roofline: the parse kernel against the measured HBM copy bandwidth (BASELINE.md §4:
+            (U' + 16 R) / t_parse); the inflate kernel is branch/latency bound and is
+            reported as decompressed GB/s in "inflate"
+  cpu_baseline: the oracle's thread-pool DecompressAll (C restatement of the reference on the
+            same zlib) on all host cores, same file, same run
+Multi GPU (torchrun, one rank per GPU): chunks are independent, there is no collective on
+the data path; every rank decodes its own full copy of the workload ("weak" scaling).
+--impl reference times the host restatement only (the C# reference cannot run here).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CACHE = os.environ.get("PPB200_CACHE", "/tmp/ppb200_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def ensure_built():
+    for d in ("tools", "oracle", os.path.join("parallelparsing_b200", "csrc")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, d)])
+
+
+def corpus_paths(reads, fixed, seed, chunk):
+    key = f"gen_s{seed}_r{reads}_L{fixed}_gz6"
+    d = os.path.join(CACHE, key)
+    return d, os.path.join(d, "reads.fastq.gz"), os.path.join(d, f"chunk{chunk}.gzi"), os.path.join(d, "meta.json")
+
+
+def make_corpus(reads, fixed, seed, chunk):
+    """Generator-exact FASTQ -> one gzip member (level 6) -> IndexIO file.  Cached under /tmp."""
+    import parallelparsing_b200 as pp
+    d, gz_path, idx_path, meta_path = corpus_paths(reads, fixed, seed, chunk)
+    os.makedirs(d, exist_ok=True)
+    if not os.path.exists(gz_path):
+        t = time.time()
+        tmp = gz_path + f".tmp{os.getpid()}"
+        gen = [os.path.join(ROOT, "tools", "_build", "ppgen"), str(reads), "--seed", str(seed)]
+        if fixed:
+            gen += ["--fixed", str(fixed)]
+        p1 = subprocess.Popen(gen, stdout=subprocess.PIPE)
+        p2 = subprocess.Popen([os.path.join(ROOT, "tools", "_build", "ppgzip"), "-l", "6", "-", tmp], stdin=p1.stdout)
+        p1.stdout.close()
+        if p2.wait() != 0 or p1.wait() != 0:
+            raise RuntimeError("corpus generation failed")
+        os.replace(tmp, gz_path)
+        log(f"[bench] corpus {reads} reads -> {os.path.getsize(gz_path)/1e6:.1f} MB gz in {time.time()-t:.1f}s")
+    if not os.path.exists(idx_path):
+        t = time.time()
+        ix = pp.Core.BuildDeflateIndex(gz_path, chunk)
+        tmp = idx_path + f".tmp{os.getpid()}"
+        pp.IndexIO.Serialize(ix, tmp)
+        os.replace(tmp, idx_path)
+        log(f"[bench] CreateIndex chunk={chunk}: {ix.Count} points in {time.time()-t:.1f}s")
+    return gz_path, idx_path
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for i, nm in enumerate(names):
+                    if s[3 + i].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference(gz, idx_path, threads, steps, warmup):
+    """The host restatement of the reference's parallel DecompressAll, all cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    ox = O.OracleIndex.deserialize(idx_path)
+    times, recs, nbytes = [], 0, 0
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        recs, nbytes = O.decompress_all_mt(gz, ox, threads=threads)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    if recs < 0:
+        raise RuntimeError(f"oracle failed rc={recs}")
+    return float(np.mean(times)), recs, nbytes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--chunk", type=int, default=10_000)
+    ap.add_argument("--fixed-len", type=int, default=150)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--zero-copy", action="store_true", help="kernels read pinned host memory directly")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = (f"Generator seed {args.seed}, {args.reads} reads x {args.fixed_len}bp single-end, gzip -6 "
+                f"(one member), chunk {args.chunk}")
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ensure_built()
+        gz_path, idx_path = make_corpus(args.reads, args.fixed_len, args.seed, args.chunk)
+        gz = np.fromfile(gz_path, np.uint8)
+        dt, recs, nbytes = cpu_reference(gz, idx_path, cores, max(args.steps, 1), min(args.warmup, 1))
+        val = nbytes / dt / 1e9
+        line = {
+            "impl": "reference", "metric": "DecompressAll uncompressed GB/s", "value": val, "unit": "GB/s",
+            "reads_per_s": recs / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "records": recs, "uncompressed_bytes": nbytes,
+                       "note": "C restatement of the reference's thread-pool DecompressAll on the same system zlib; "
+                               "the C# reference cannot run in this image (no dotnet)"},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
+                             "sample": "whole workload, every step"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if local_rank == 0:
+        ensure_built()
+        make_corpus(args.reads, args.fixed_len, args.seed, args.chunk)
+    barrier()
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200 import _lib
+    L = pp.lib()
+    gz_path, idx_path = corpus_paths(args.reads, args.fixed_len, args.seed, args.chunk)[1:3]
+    gz_np = np.fromfile(gz_path, np.uint8)
+    gz, gz_ptr = pp.pinned_copy(gz_np)           # pinned host memory: the e2e source buffer
+    ix = pp.IndexIO.Deserialize(idx_path)
+    dev = pp.Device(local_rank)
+    job = pp.Job(dev, ix, gz.size, 0, -1, zero_copy=args.zero_copy)
+
+    def sync():
+        torch.cuda.synchronize()
+
+    # correctness gate before timing: one full pass, byte total and record count must be sane
+    info = job.run(gz)
+    if info.status != 0:
+        raise SystemExit(f"bench.py: DecompressAll failed status={info.status}")
+    U, R, Us = info.total_bytes, info.total_records, info.scanned_bytes
+    n_chunks = info.n_chunks
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # --- kernel-only: inputs resident in HBM ------------------------------------------------
+    job.upload(gz_ptr)
+    sync()
+    for _ in range(args.warmup):
+        job.execute()
+    sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        job.execute()
+    sync()
+    t_dev = (time.perf_counter() - t0) / args.steps
+    job.download()
+    info = job.info()
+    t_inflate, t_parse, t_scan = info.inflate_ms * 1e-3, info.parse_ms * 1e-3, info.scan_ms * 1e-3
+    launches_per_step = info.launches
+
+    # --- end to end through the C ABI: H2D + kernels + D2H every step --------------------------
+    for _ in range(2):
+        job.upload(gz_ptr); job.execute(); job.download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        job.upload(gz_ptr)
+        job.execute()
+        job.download()     # synchronises: per-chunk status, counts, record bases on the host
+    sync()
+    t_e2e = (time.perf_counter() - t0) / args.steps
+    info2 = job.info()
+    barrier()
+    clocks = sampler.finish()
+
+    # --- optional: also bring every record's line offsets to the host ---------------------------
+    t0 = time.perf_counter()
+    job.upload(gz_ptr); job.execute(); job.download()
+    ls = job.line_starts()
+    t_e2e_offsets = time.perf_counter() - t0
+    del ls
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets = [float(x) for x in tt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        b_parse = Us + 16 * R                      # bytes scanned + four u32 line starts / record
+        b_inflate = info2.compressed_bytes + 32768 * n_chunks + U
+        line = {
+            "metric": "DecompressAll uncompressed GB/s", "value": world * U / t_dev / 1e9, "unit": "GB/s",
+            "reads_per_s": world * R / t_dev,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "chunks": n_chunks, "records": R, "uncompressed_bytes": U,
+                       "compressed_bytes": info2.compressed_bytes, "per_gpu": "full workload per rank",
+                       "l2": "inputs larger than L2 (0.9 GB compressed, 3.8 GB inflated per step)",
+                       "zero_copy": bool(args.zero_copy)},
+            "e2e": {"value": world * U / t_e2e / 1e9, "unit": "GB/s", "reads_per_s": world * R / t_e2e,
+                    "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": info2.h2d_bytes,
+                    "d2h_bytes_per_step": info2.d2h_bytes,
+                    "with_line_offsets_to_host": {"value": world * U / t_e2e_offsets / 1e9, "unit": "GB/s",
+                                                  "d2h_bytes_per_step": info2.d2h_bytes + 16 * R}},
+            "roofline": {"kernel": "pp_parse_kernel", "bound": "hbm", "achieved": b_parse / t_parse / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": b_parse / t_parse / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes": b_parse, "ms": t_parse * 1e3, "peak_source": peak_src},
+            "inflate": {"kernel": "pp_inflate_kernel", "bound": "latency/branch (serial Huffman decode per chunk)",
+                        "decompressed_gbs": U / t_inflate / 1e9, "ms": t_inflate * 1e3,
+                        "bytes_moved": b_inflate, "hbm_frac": b_inflate / t_inflate / 1e9 / peak,
+                        "share_of_step": t_inflate / t_dev},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            dt, recs, nbytes = cpu_reference(gz_np, idx_path, cores, 2, 1)
+            assert recs == R and nbytes == U, (recs, R, nbytes, U)
+            line["cpu_baseline"] = {"value": nbytes / dt / 1e9, "unit": "GB/s", "reads_per_s": recs / dt,
+                                    "cores": cores, "kind": "port", "sample": "whole workload (2 timed passes)"}
+        print(json.dumps(line), flush=True)
+    job.free()
+    L.pp_host_free(gz_ptr)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

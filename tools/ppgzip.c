@@ -1,9 +1,9 @@
 /*
- * ppgzip — parallel single-member gzip writer for the big benchmark corpora.
+ * ppgzip — parallel, streaming, single-member gzip writer for the big benchmark corpora.
  *
  * Not part of the reference (which is fed by system `gzip`); it exists because
  * `gzip -6` compresses Generator data at ~5 MB/s here and the
- * 10 M / 100 M-read configs must be produced inside a gpurun call.
+ * 10 M / 100 M-read configs must be produced inside a benchmark run.
  *
  * pigz-style: the input is cut into segments; each segment is raw-deflated
  * independently (level 6, memLevel 9 so that blocks close every 32 K symbols as
@@ -13,7 +13,11 @@
  * reference cannot extract chunks that span members.  The
  * sync-flush joins also exercise the decoder's stored-block path.
  *
- * usage: ppgzip [-l level] [-t threads] [-s segment_bytes] in out.gz
+ * Streaming: the main thread reads segments (file or stdin, so `ppgen | ppgzip -`
+ * overlaps generation with compression), workers compress, results are written
+ * in order; at most 3*threads segments are in flight.
+ *
+ * usage: ppgzip [-l level] [-t threads] [-s segment_bytes] in|- out.gz
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -23,89 +27,167 @@
 #include <unistd.h>
 #include <zlib.h>
 
-typedef struct {
-    const uint8_t *in;
+typedef struct seg {
+    uint8_t *in;
     size_t in_len;
-    size_t seg;
-    size_t nseg;
+    uint8_t dict[32768];
+    size_t dict_len;
+    int last;
+    uint8_t *out;
+    size_t out_len;
+    uLong crc;
+    int done;
+    struct seg *next_todo;
+} seg_t;
+
+typedef struct {
     int level;
-    uint8_t **out;
-    size_t *out_len;
-    uLong *crc;
-    size_t next;
     pthread_mutex_t mu;
-    int err;
-} job_t;
+    pthread_cond_t cv_todo, cv_done;
+    seg_t *todo_head, *todo_tail;
+    int closing, err;
+} pool_t;
 
 static void *worker(void *arg)
 {
-    job_t *j = (job_t *)arg;
+    pool_t *p = (pool_t *)arg;
     for (;;) {
-        pthread_mutex_lock(&j->mu);
-        size_t s = j->next < j->nseg ? j->next++ : (size_t)-1;
-        pthread_mutex_unlock(&j->mu);
-        if (s == (size_t)-1) break;
-        size_t off = s * j->seg;
-        size_t len = j->in_len - off < j->seg ? j->in_len - off : j->seg;
-        int last = (s + 1 == j->nseg);
+        pthread_mutex_lock(&p->mu);
+        while (!p->todo_head && !p->closing) pthread_cond_wait(&p->cv_todo, &p->mu);
+        seg_t *s = p->todo_head;
+        if (s) {
+            p->todo_head = s->next_todo;
+            if (!p->todo_head) p->todo_tail = NULL;
+        }
+        pthread_mutex_unlock(&p->mu);
+        if (!s) break;
         z_stream z;
         memset(&z, 0, sizeof z);
-        if (deflateInit2(&z, j->level, Z_DEFLATED, -15, 9, Z_DEFAULT_STRATEGY) != Z_OK) { j->err = 1; break; }
-        if (off > 0) {
-            size_t d = off < 32768 ? off : 32768;
-            deflateSetDictionary(&z, j->in + off - d, (uInt)d);
+        int bad = deflateInit2(&z, p->level, Z_DEFLATED, -15, 9, Z_DEFAULT_STRATEGY) != Z_OK;
+        if (!bad) {
+            if (s->dict_len) deflateSetDictionary(&z, s->dict, (uInt)s->dict_len);
+            size_t cap = deflateBound(&z, (uLong)s->in_len) + 64;
+            s->out = (uint8_t *)malloc(cap);
+            z.next_in = s->in;
+            z.avail_in = (uInt)s->in_len;
+            z.next_out = s->out;
+            z.avail_out = (uInt)cap;
+            int rc = deflate(&z, s->last ? Z_FINISH : Z_SYNC_FLUSH);
+            if ((s->last && rc != Z_STREAM_END) || (!s->last && rc != Z_OK) || z.avail_in != 0) bad = 1;
+            s->out_len = cap - z.avail_out;
+            s->crc = crc32(crc32(0L, Z_NULL, 0), s->in, (uInt)s->in_len);
+            deflateEnd(&z);
         }
-        size_t cap = deflateBound(&z, (uLong)len) + 64;
-        uint8_t *o = (uint8_t *)malloc(cap);
-        z.next_in = (Bytef *)(j->in + off);
-        z.avail_in = (uInt)len;
-        z.next_out = o;
-        z.avail_out = (uInt)cap;
-        int rc = deflate(&z, last ? Z_FINISH : Z_SYNC_FLUSH);
-        if ((last && rc != Z_STREAM_END) || (!last && rc != Z_OK) || z.avail_in != 0) { j->err = 2; free(o); deflateEnd(&z); break; }
-        j->out[s] = o;
-        j->out_len[s] = cap - z.avail_out;
-        j->crc[s] = crc32(crc32(0L, Z_NULL, 0), j->in + off, (uInt)len);
-        deflateEnd(&z);
+        free(s->in);
+        s->in = NULL;
+        pthread_mutex_lock(&p->mu);
+        if (bad) p->err = 1;
+        s->done = 1;
+        pthread_cond_broadcast(&p->cv_done);
+        pthread_mutex_unlock(&p->mu);
     }
     return NULL;
 }
 
-int ppgzip_buffer(const uint8_t *in, size_t in_len, int level, int threads, size_t seg, FILE *f)
+static size_t read_full(FILE *f, uint8_t *buf, size_t n)
 {
-    job_t j;
-    memset(&j, 0, sizeof j);
-    if (seg < 65536) seg = 65536;
-    j.in = in; j.in_len = in_len; j.seg = seg; j.level = level;
-    j.nseg = in_len ? (in_len + seg - 1) / seg : 1;
-    j.out = (uint8_t **)calloc(j.nseg, sizeof(*j.out));
-    j.out_len = (size_t *)calloc(j.nseg, sizeof(*j.out_len));
-    j.crc = (uLong *)calloc(j.nseg, sizeof(*j.crc));
-    pthread_mutex_init(&j.mu, NULL);
+    size_t got = 0;
+    while (got < n) {
+        size_t r = fread(buf + got, 1, n - got, f);
+        if (r == 0) break;
+        got += r;
+    }
+    return got;
+}
+
+int ppgzip_stream(FILE *fi, FILE *fo, int level, int threads, size_t seg_bytes)
+{
+    if (seg_bytes < 65536) seg_bytes = 65536;
     if (threads < 1) threads = 1;
-    if ((size_t)threads > j.nseg) threads = (int)j.nseg;
+    pool_t p;
+    memset(&p, 0, sizeof p);
+    p.level = level;
+    pthread_mutex_init(&p.mu, NULL);
+    pthread_cond_init(&p.cv_todo, NULL);
+    pthread_cond_init(&p.cv_done, NULL);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
-    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &j);
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &p);
+
+    const int window = 3 * threads;  /* segments in flight */
+    seg_t **ring = (seg_t **)calloc((size_t)window, sizeof(seg_t *));
+    size_t n_read = 0, n_written = 0;
+    static const uint8_t hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
+    fwrite(hdr, 1, 10, fo);
+    uLong crc = crc32(0L, Z_NULL, 0);
+    uint64_t total = 0;
+    uint8_t tail[32768];
+    size_t tail_len = 0;
+    /* one segment of read-ahead so that we know which one is last */
+    uint8_t *cur = (uint8_t *)malloc(seg_bytes);
+    size_t cur_len = read_full(fi, cur, seg_bytes);
+    int eof = 0, rc = 0;
+    while (!eof || n_written < n_read) {
+        /* write finished segments in order; block when the window is full or input is over */
+        while (n_written < n_read) {
+            seg_t *s = ring[n_written % (size_t)window];
+            pthread_mutex_lock(&p.mu);
+            int must_wait = eof || (n_read - n_written) >= (size_t)window;
+            while (!s->done && must_wait) pthread_cond_wait(&p.cv_done, &p.mu);
+            int done = s->done;
+            pthread_mutex_unlock(&p.mu);
+            if (!done) break;
+            if (s->out) fwrite(s->out, 1, s->out_len, fo);
+            crc = crc32_combine(crc, s->crc, (z_off_t)s->in_len);
+            total += s->in_len;
+            free(s->out);
+            free(s);
+            n_written++;
+        }
+        if (eof) continue;
+        uint8_t *nxt = (uint8_t *)malloc(seg_bytes);
+        size_t nxt_len = cur_len == seg_bytes ? read_full(fi, nxt, seg_bytes) : 0;
+        seg_t *s = (seg_t *)calloc(1, sizeof(seg_t));
+        s->in = cur;
+        s->in_len = cur_len;
+        memcpy(s->dict, tail, tail_len);
+        s->dict_len = tail_len;
+        s->last = nxt_len == 0;
+        /* remember this segment's last 32 KB as the next one's dictionary */
+        if (cur_len >= 32768) {
+            memcpy(tail, cur + cur_len - 32768, 32768);
+            tail_len = 32768;
+        } else {
+            size_t keep = 32768 - cur_len < tail_len ? 32768 - cur_len : tail_len;
+            memmove(tail, tail + tail_len - keep, keep);
+            memcpy(tail + keep, cur, cur_len);
+            tail_len = keep + cur_len;
+        }
+        ring[n_read % (size_t)window] = s;
+        n_read++;
+        pthread_mutex_lock(&p.mu);
+        if (p.todo_tail) p.todo_tail->next_todo = s; else p.todo_head = s;
+        p.todo_tail = s;
+        pthread_cond_signal(&p.cv_todo);
+        pthread_mutex_unlock(&p.mu);
+        if (s->last) { eof = 1; free(nxt); }
+        else { cur = nxt; cur_len = nxt_len; }
+    }
+    pthread_mutex_lock(&p.mu);
+    p.closing = 1;
+    pthread_cond_broadcast(&p.cv_todo);
+    pthread_mutex_unlock(&p.mu);
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     free(th);
-    if (j.err) return -1;
-    static const uint8_t hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
-    fwrite(hdr, 1, 10, f);
-    uLong crc = crc32(0L, Z_NULL, 0);
-    for (size_t s = 0; s < j.nseg; s++) {
-        size_t off = s * seg;
-        size_t len = in_len - off < seg ? in_len - off : seg;
-        fwrite(j.out[s], 1, j.out_len[s], f);
-        crc = crc32_combine(crc, j.crc[s], (z_off_t)len);
-        free(j.out[s]);
-    }
+    free(ring);
+    if (p.err) rc = -1;
     uint8_t tr[8];
-    uint32_t c = (uint32_t)crc, n = (uint32_t)in_len;
+    uint32_t c = (uint32_t)crc, n = (uint32_t)total;
     for (int i = 0; i < 4; i++) { tr[i] = (uint8_t)(c >> (8 * i)); tr[4 + i] = (uint8_t)(n >> (8 * i)); }
-    fwrite(tr, 1, 8, f);
-    free(j.out); free(j.out_len); free(j.crc);
-    pthread_mutex_destroy(&j.mu);
-    return 0;
+    fwrite(tr, 1, 8, fo);
+    pthread_mutex_destroy(&p.mu);
+    pthread_cond_destroy(&p.cv_todo);
+    pthread_cond_destroy(&p.cv_done);
+    return rc;
 }
 
 #ifndef PPGZIP_NO_MAIN
@@ -120,20 +202,15 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seg = strtoull(argv[++i], NULL, 10);
         else break;
     }
-    if (argc - i != 2) { fprintf(stderr, "usage: ppgzip [-l level] [-t threads] [-s segment_bytes] in out.gz\n"); return 2; }
-    FILE *fi = fopen(argv[i], "rb");
+    if (argc - i != 2) { fprintf(stderr, "usage: ppgzip [-l level] [-t threads] [-s segment_bytes] in|- out.gz\n"); return 2; }
+    FILE *fi = strcmp(argv[i], "-") ? fopen(argv[i], "rb") : stdin;
     if (!fi) { perror("ppgzip: in"); return 1; }
-    fseek(fi, 0, SEEK_END);
-    size_t n = (size_t)ftell(fi);
-    fseek(fi, 0, SEEK_SET);
-    uint8_t *in = (uint8_t *)malloc(n ? n : 1);
-    if (fread(in, 1, n, fi) != n) { perror("ppgzip: read"); return 1; }
-    fclose(fi);
     FILE *fo = fopen(argv[i + 1], "wb");
     if (!fo) { perror("ppgzip: out"); return 1; }
-    int rc = ppgzip_buffer(in, n, level, threads, seg, fo);
-    fclose(fo);
-    free(in);
+    setvbuf(fo, NULL, _IOFBF, 1 << 22);
+    int rc = ppgzip_stream(fi, fo, level, threads, seg);
+    if (fclose(fo) != 0) rc = -1;
+    if (fi != stdin) fclose(fi);
     return rc ? 1 : 0;
 }
 #endif
