@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(32) pp_inflate_kernel(const ChunkDesc *__restr
                                                         uint8_t *slots, const uint8_t *__restrict__ lead,
                                                         ChunkResult *__restrict__ results)
 {
-    __shared__ ppinf::Smem sm;
+    ppinf::Smem &sm = ppinf::g_sm;
     const int k = (int)blockIdx.x;
     if (k >= n) return;
     if (threadIdx.x == 0) {
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(32) pp_inflate_kernel(const ChunkDesc *__restr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    ppinf::inflate_chunk(descs[k], comp, comp_bytes, slots, lead, sm, results[k]);
+    ppinf::inflate_chunk(descs[k], comp, comp_bytes, slots, lead, results[k]);
 }
 
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,

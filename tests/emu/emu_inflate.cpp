@@ -14,12 +14,11 @@ extern "C" {
 int emu_inflate_chunk(const uint8_t *comp, uint64_t comp_bytes, uint64_t in_bit, uint64_t in_limit,
                       uint8_t *slot, const uint8_t *lead, uint32_t lead_len, uint32_t out_len, uint64_t *res)
 {
-    static ppinf::Smem sm;
     ppinf::ChunkDesc d;
     d.in_bit = in_bit; d.in_limit = in_limit; d.slot_off = 0; d.lead_src = 0;
     d.lead_len = lead_len; d.out_len = out_len; d.prefix_len = 0; d.prefix_nl = 0;
     ppinf::ChunkResult r;
-    ppinf::inflate_chunk(d, comp, comp_bytes, slot, lead, sm, r);
+    ppinf::inflate_chunk(d, comp, comp_bytes, slot, lead, r);
     res[0] = r.produced; res[1] = r.newlines; res[2] = r.min_byte; res[3] = r.end_bit;
     return r.status;
 }
