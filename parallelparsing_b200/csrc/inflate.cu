@@ -1,31 +1,64 @@
-// Kernel 1 — checkpoint inflate.  One CTA (one warp) per index chunk; the decoder
-// itself lives in inflate_core.cuh.  Replaces Core.ExtractDeflateIndex + zlib
-// inflate (Decompressor/Core.cs:133-192, Interop/PlatformInterop.cs:9-34).
+// Kernel 1 — checkpoint inflate.  One CTA per index chunk at a time (CTAs pull chunk
+// numbers from a global counter), all threads of the CTA decoding sub-sequences of the
+// same deflate block; the decoder itself lives in inflate_core.cuh.  Replaces
+// Core.ExtractDeflateIndex + zlib inflate (Decompressor/Core.cs:133-192,
+// Interop/PlatformInterop.cs:9-34).
 #include "kernels.cuh"
 
 namespace pp {
 
-__global__ void __launch_bounds__(32) pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n,
-                                                        const uint8_t *__restrict__ comp, uint64_t comp_bytes,
-                                                        uint8_t *slots, const uint8_t *__restrict__ lead,
-                                                        ChunkResult *__restrict__ results)
+__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
+    pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
+                      uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
+                      uint16_t *map_scratch, uint32_t map_cap, int *next_chunk)
 {
-    ppinf::Smem &sm = ppinf::g_sm;
-    const int k = (int)blockIdx.x;
-    if (k >= n) return;
+    extern __shared__ __align__(128) uint8_t pp_smem_raw[];
+    ppinf::Sm sm;
+    ppinf::sm_carve(sm, pp_smem_raw, (int)blockDim.x);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ppinf::kStages; s++) ppinf::mbar_init(&sm.bar[s], 1);
+        ppinf::mbar_init(sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    ppinf::inflate_chunk(descs[k], comp, comp_bytes, slots, lead, results[k]);
+    __syncthreads();
+    uint16_t *map = map_scratch + (size_t)blockIdx.x * map_cap;
+    uint32_t stage_phase = 0;
+    for (;;) {
+        if (threadIdx.x == 0) sm.u[16] = (uint32_t)atomicAdd(next_chunk, 1);
+        __syncthreads();
+        const int k = (int)sm.u[16];
+        __syncthreads();
+        if (k >= n) break;
+        ppinf::inflate_chunk(sm, descs[k], comp, comp_bytes, slots, lead, map, results[k], stage_phase);
+    }
+}
+
+int inflate_max_ctas_per_sm(int threads)
+{
+    int nb = 0;
+    const size_t smem = ppinf::sm_bytes_for(threads);
+    if (cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pp_inflate_kernel, threads, smem) != cudaSuccess) return 0;
+    return nb;
+}
+
+size_t inflate_scratch_bytes(int threads, int grid)
+{
+    return (size_t)grid * ppinf::map_cap_for(threads) * sizeof(uint16_t);
 }
 
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                           const uint8_t *lead, ChunkResult *results, cudaStream_t st)
+                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    pp_inflate_kernel<<<n, 32, 0, st>>>(descs, n, comp, comp_bytes, slots, lead, results);
+    cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const size_t smem = ppinf::sm_bytes_for(cfg.threads);
+    e = cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = n < cfg.grid ? n : cfg.grid;
+    pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
+                                                        ppinf::map_cap_for(cfg.threads), cfg.counter);
     return cudaGetLastError();
 }
 

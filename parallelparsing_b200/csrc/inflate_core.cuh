@@ -2,78 +2,100 @@
 // inflate() on the Decompress(checkpoint) path (Core.ExtractDeflateIndex,
 // Decompressor/Core.cs:133-192; zlib reached through Interop/PlatformInterop.cs:9-34).
 //
-// Execution model: ONE WARP decodes ONE index chunk, alternating two phases.
+// Execution model: ONE CTA decodes ONE index chunk, and the threads of the CTA share
+// the work INSIDE every deflate block.  A serial Huffman decoder is a dependent chain
+// of table lookups (hundreds of cycles per symbol on a GPU); instead the block's bit
+// stream is cut into fixed-size sub-sequences, one per thread:
 //
-//  DECODE  All 32 lanes run the serial Huffman decode redundantly on identical
-//          registers (table lookups are shared-memory broadcasts), so every lane
-//          knows every token without a queue, shuffle or barrier.  Nothing touches
-//          global memory here: each token is written into a shared-memory SOURCE MAP
-//          — one u16 per output byte saying "literal v" or "copy from d bytes back" —
-//          with lane j writing byte j of the token.  The decoder also records where
-//          a token reads bytes produced since the last such point ("rounds").
-//  COPY    About 1 KB of output at a time is resolved with all lanes busy:
-//          (1) every byte whose source lies before the batch is gathered from the
-//              history in global memory — all loads independent and in flight together,
-//              so the L2 latency is paid once per batch, not once per match;
-//          (2) bytes whose source lies inside the batch are resolved from shared memory,
-//              round by round;
-//          (3) the finished bytes leave with aligned 16-byte vector stores, and the same
-//              pass counts '\n' and looks for NUL bytes for the parse stage.
+//  STAGE    the compressed window (T sub-sequences) is brought into shared memory with
+//           TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//  HEADER   block header; dynamic code lengths; both lookup tables are built by all
+//           threads (canonical-code search per table slot, no serial fill);
+//  GUESS    every thread decodes from the first bit of its sub-sequence.  Only thread 0
+//           starts on a real symbol boundary, but a Huffman decoder that starts at a
+//           wrong bit falls back onto true boundaries after a few symbols
+//           (self-synchronisation), so most threads END on a true boundary;
+//  SYNC     every thread restarts where its predecessor ended, until nothing moves.
+//           Thread 0 is right by construction, so after k rounds threads 0..k are
+//           exact; with self-synchronisation two or three rounds settle all of them;
+//  SCAN     block-wide prefix sum of the bytes each sub-sequence produces;
+//  EMIT     every thread decodes its (now exact) sub-sequence once more and writes a
+//           SOURCE MAP: one u16 per output byte, "literal v" or "copy from d+1 back";
+//  RESOLVE  the CTA walks the window's output in tiles of 16 bytes per thread: sources
+//           in front of the tile are gathered from global memory (all loads in flight
+//           together), sources inside the tile are settled in shared memory by pointer
+//           jumping, and the tile leaves with 16-byte stores ('\n' / NUL counted on the
+//           way for the parse stage).
 //
 // History is addressed directly in global memory: the chunk's output slot is laid out
-// as [window (>= 32 KB)][output], so a back-reference is out[pos-dist] with no wrap test.
-// Compressed bytes stream through a shared-memory ring filled by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx), kStages tiles ahead of the bit reader.
+// as [window (>= 32 KB)][output], so a back-reference is out[pos-dist] with no wrap.
 //
 // The same source compiles in two modes:
 //   * device (default): used by inflate.cu, the only mode shipped in libppb200.so;
-//   * PP_HOST_EMU: lanes are run one after another by a plain loop.  Compiled ONLY by
-//     tests/emu/ to check the decoder logic against zlib on machines without a GPU.
-//     It is test scaffolding, not a fallback: nothing in the product links it.
-// Lane-parallel sections never read a byte written in the same section, which is what
-// makes the sequential emulation equivalent to lockstep execution.
+//   * PP_HOST_EMU: threads are run one after another by plain loops, phase by phase.
+//     Compiled ONLY by tests/emu/ to check the decoder logic against zlib on machines
+//     without a GPU.  It is test scaffolding, not a fallback: nothing in the product
+//     links it.  Phases never read what another thread writes in the same phase
+//     (except the monotone pointer-jumping of RESOLVE, which is order-independent),
+//     which is what makes the sequential emulation equivalent.
 #pragma once
 #include <stdint.h>
 
 #ifdef PP_HOST_EMU
 #include <string.h>
+namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: windows, sync rounds, max rounds, blocks
 #define PP_DEV static inline
-#define PP_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
-#define PP_LANES_END }
-#define PP_LANES_END_NOSYNC }
-#define PP_WARP_SYNC()
-#define PP_LANE0_BEGIN {
-#define PP_LANE0_END }
-#define PP_LV(T, name) T name[32]
-#define PP_L(name) name[lane]
+#define PP_HD static inline
+#define PP_NT (ppinf::g_T)
+#define PP_FOR_T(t) for (int t = 0; t < PP_NT; ++t) {
+#define PP_END_T }
+#define PP_SYNC()
+#define PP_SYNC_OR(v) (v)
+#define PP_T0_BEGIN {
+#define PP_T0_END }
 #define PP_CONST static const
+#define PP_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PP_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
 #else
 #define PP_DEV __device__ __forceinline__
-#define PP_LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u);
-#define PP_LANES_END } __syncwarp();
-#define PP_LANES_END_NOSYNC }
-#define PP_WARP_SYNC() __syncwarp()
-#define PP_LANE0_BEGIN if ((threadIdx.x & 31u) == 0) {
-#define PP_LANE0_END } __syncwarp();
-#define PP_LV(T, name) T name
-#define PP_L(name) name
+#define PP_HD __host__ __device__ __forceinline__
+#define PP_NT ((int)blockDim.x)
+#define PP_FOR_T(t) { const int t = (int)threadIdx.x;
+#define PP_END_T }
+#define PP_SYNC() __syncthreads()
+#define PP_SYNC_OR(v) __syncthreads_or(v)
+#define PP_T0_BEGIN if (threadIdx.x == 0) {
+#define PP_T0_END }
 #define PP_CONST __device__ const
+#define PP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define PP_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #endif
 
 namespace ppinf {
 
 // ---- geometry -------------------------------------------------------------
-constexpr int kRootL = 9;              // primary bits, literal/length table
-constexpr int kRootD = 9;              // primary bits, distance table
-constexpr int kLitCap = 852 + 4;       // zlib's proven bound for (286 syms, root 9, max 15)
-constexpr int kDistCap = 512 + 288;    // 30 syms: every 2^k sub-table holds >= k+1 symbols
-constexpr int kTileBytes = 2048;       // one TMA bulk copy
-constexpr int kTileWords = kTileBytes / 4;
-constexpr int kStages = 4;             // ring depth
-constexpr int kRingWords = kTileWords * kStages;
-constexpr int kBatch = 1024;           // output bytes resolved per copy phase (multiple of 16)
-constexpr int kMaxMatch = 258;
-constexpr int kMaxRounds = 192;
+constexpr int kRootL = 10;              // primary bits, literal/length table
+constexpr int kRootD = 8;               // primary bits, distance table
+constexpr int kLitCap = 1024 + 512;     // zlib `enough 288 10 15` = 1334
+constexpr int kDistCap = 256 + 256;     // zlib `enough 32 8 15` = 402
+#ifndef PP_SUBW
+#define PP_SUBW 31                      // words per sub-sequence; odd => the threads' word reads spread over all banks
+#endif
+constexpr int kSubW = PP_SUBW;
+constexpr int kSubBits = kSubW * 32;
+constexpr int kHdrWords = 160;          // a dynamic block header is < 4600 bits
+constexpr int kSlackWords = 16;         // last symbol overrun (<= 48 bits) + reader look-ahead
+constexpr int kMaxThreads = 1024;
+constexpr int kTileB = 16;              // output bytes per thread per resolve tile
+constexpr uint32_t kMinMapCap = 160u * 1024u;  // one sub-sequence can emit kSubBits/2*258 < 128 Ki bytes
+
+PP_HD uint32_t cw_words_for(int T) { return (uint32_t)(T * kSubW + kHdrWords + kSlackWords + 3) & ~3u; }
+// source-map entries one window may produce before the window is cut short
+PP_HD uint32_t map_cap_for(int T)
+{
+    const uint32_t c = (uint32_t)T * (uint32_t)kSubW * 4u * 8u;  // 8x expansion of a full window
+    return c > kMinMapCap ? c : kMinMapCap;
+}
 
 // ---- table entry ------------------------------------------------------------
 // [4:0] bits to consume (code + extra)  [7:5] kind  [12:8] code length
@@ -89,6 +111,8 @@ PP_DEV uint32_t e_tot(uint32_t e) { return e & 31u; }
 PP_DEV uint32_t e_cl(uint32_t e) { return (e >> 8) & 31u; }
 PP_DEV uint32_t e_sub(uint32_t e) { return (e >> 13) & 7u; }
 PP_DEV uint32_t e_val(uint32_t e) { return e >> 16; }
+
+enum : uint32_t { F_NONE = 0, F_EOB = 1, F_BAD = 2 };
 
 // ---- per-chunk descriptor / result (shared with the host runtime) -----------
 struct ChunkDesc {
@@ -109,26 +133,72 @@ struct ChunkResult {
     uint64_t end_bit;   // bit position after the last consumed bit
 };
 
-struct alignas(128) Smem {
-    uint32_t ring[kRingWords];        // first: TMA destinations must be 16 B aligned
-    uint32_t lit[kLitCap];
-    uint32_t dist[kDistCap];
-    alignas(16) uint8_t obuf[kBatch + kMaxMatch + 32];   // resolved output bytes of the batch
-    uint16_t map[kBatch + kMaxMatch + 32];                // source map of the batch
-    uint16_t rounds[kMaxRounds + 2];                      // batch-relative start of every round
-    uint16_t count[16];
-    uint16_t next[16];
-    uint8_t lens[320];
+// Shared-memory carve-up (pointers into dynamic shared memory / emulation arrays).
+struct Sm {
+    uint32_t *cw;       // staged compressed words                         [cw_words_for(T)]
+    uint32_t *lit;      // literal/length lookup table                     [kLitCap]
+    uint32_t *dist;     // distance lookup table                           [kDistCap]
+    uint32_t *start;    // per thread: first bit of its segment (window relative)   [T]
+    uint32_t *end;      // per thread: bit after its last symbol                    [T]
+    uint32_t *outc;     // per thread: bytes its segment produces; then exclusive sums [T]
+    uint32_t *flag;     // per thread: F_*                                          [T]
+    uint32_t *nl;       // per thread: '\n' bytes stored                            [T]
+    uint32_t *nul;      // per thread: non-zero when a NUL byte was stored          [T]
+    uint32_t *ns;       // per thread: its predecessor's end, latched for a SYNC round [T]
+    uint16_t *res;      // resolve tile: 0x8000|byte or tile-relative source index  [kTileB*T]
+    uint16_t *sorted;   // symbols in canonical order                               [320]
+    uint16_t *codes;    // canonical code of every symbol                           [320]
+    uint8_t *lens;      // code lengths: lit/len at 0, distance at 288              [320]
+    uint32_t *count;    // [16] symbols per code length
+    uint32_t *first;    // [16] first code of each length (MSB-first value)
+    uint32_t *offs;     // [16] index of each length's first symbol in `sorted`
+    uint32_t *u;        // [32] block-uniform scratch (broadcast slots)
+    uint32_t *wsum;     // [32] per-warp partial sums
 #ifndef PP_HOST_EMU
-    unsigned long long bar[kStages];
+    unsigned long long *bar;  // one mbarrier for the staging copies
 #endif
 };
 
-#ifdef PP_HOST_EMU
-static Smem g_sm;
-#else
-__shared__ Smem g_sm;
+PP_HD uint32_t sm_bytes_for(int T)
+{
+    uint32_t b = 0;
+    b += cw_words_for(T) * 4u;
+    b += (kLitCap + kDistCap) * 4u;
+    b += (uint32_t)T * 4u * 7u;
+    b += (uint32_t)T * kTileB * 2u;
+    b += 320u * 2u * 2u + 320u;
+    b += (16u * 3u + 32u * 2u) * 4u;
+    b += 16u;  // mbarrier
+    return (b + 127u) & ~127u;
+}
+// `raw` must be 128-byte aligned (TMA destinations need 16)
+PP_DEV void sm_carve(Sm &s, uint8_t *raw, int T)
+{
+    uint8_t *p = raw;
+    s.cw = (uint32_t *)p; p += cw_words_for(T) * 4u;
+    s.lit = (uint32_t *)p; p += kLitCap * 4u;
+    s.dist = (uint32_t *)p; p += kDistCap * 4u;
+    s.start = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.end = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.outc = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.flag = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.nl = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.nul = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.ns = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.res = (uint16_t *)p; p += (uint32_t)T * kTileB * 2u;
+    s.count = (uint32_t *)p; p += 16u * 4u;
+    s.first = (uint32_t *)p; p += 16u * 4u;
+    s.offs = (uint32_t *)p; p += 16u * 4u;
+    s.u = (uint32_t *)p; p += 32u * 4u;
+    s.wsum = (uint32_t *)p; p += 32u * 4u;
+#ifndef PP_HOST_EMU
+    s.bar = (unsigned long long *)p;
 #endif
+    p += 16u;
+    s.sorted = (uint16_t *)p; p += 320u * 2u;
+    s.codes = (uint16_t *)p; p += 320u * 2u;
+    s.lens = p;
+}
 
 // RFC 1951 3.2.5 length / distance bases and extra-bit counts
 PP_CONST uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -144,45 +214,30 @@ PP_DEV uint32_t bitrev(uint32_t v, int n)
     for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i);
     return r;
 #else
-    return __brev(v) >> (32 - n);
+    return n ? __brev(v) >> (32 - n) : 0u;
 #endif
 }
-PP_DEV uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t n)  // low 32 bits of (hi:lo) >> (n & 31)
+PP_DEV uint32_t popc32(uint32_t v)
 {
 #ifdef PP_HOST_EMU
-    n &= 31u;
-    return n ? (lo >> n) | (hi << (32u - n)) : lo;
+    return (uint32_t)__builtin_popcount(v);
 #else
-    return __funnelshift_r(lo, hi, n);
+    return (uint32_t)__popc(v);
 #endif
 }
-PP_DEV uint32_t fsl_hi(uint32_t lo, uint32_t n)  // high 32 bits of (0:lo) << (n & 31)
+// 0x80 in every byte of w that equals the byte replicated in c4
+PP_DEV uint32_t eq_bytes(uint32_t w, uint32_t c4)
 {
-#ifdef PP_HOST_EMU
-    n &= 31u;
-    return n ? lo >> (32u - n) : 0u;
-#else
-    return __funnelshift_l(lo, 0u, n);
-#endif
+    const uint32_t x = w ^ c4;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
 }
-
-// ---- compressed-input reader ------------------------------------------------
-// (hi:lo) holds the next `bitcnt` bits of the stream, lo always fully valid
-// (bitcnt >= 32 between tokens); words come from the ring one at a time and the
-// word after the current one is always preloaded in `nw`.
-struct Reader {
-    const uint8_t *comp;   // compressed buffer (global, 16 B aligned)
-    uint64_t comp_tiles;   // tiles available in the buffer
-    uint32_t lo, hi;
-    int bitcnt;            // valid bits in hi:lo
-    uint64_t wnext;        // word index (from comp) of the word held in nw
-    uint32_t nw;           // preloaded word
-    uint32_t rpos;         // ring position of wnext
-    uint32_t s_cur;        // sequence number of the tile holding wnext
-    uint32_t s_issued;     // tiles issued so far
-    int64_t tile_bias;     // tile index = tile_bias + sequence number
-    int exhausted;         // 1: ran past the buffer, 2: a transfer never landed
-};
+// n bits (n <= 25) at window-relative bit position pos
+PP_DEV uint32_t peek_bits(const uint32_t *cw, uint32_t pos, uint32_t n)
+{
+    const uint32_t w = pos >> 5, s = pos & 31u;
+    const uint64_t v = (uint64_t)cw[w] | ((uint64_t)cw[w + 1] << 32);
+    return (uint32_t)(v >> s) & ((1u << n) - 1u);
+}
 
 #ifndef PP_HOST_EMU
 PP_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,659 +268,767 @@ PP_DEV bool mbar_wait(unsigned long long *bar, uint32_t parity)
         if (clock64() - t0 > 4000000000LL) return false;  // ~2 s
     }
 }
-PP_DEV void tma_load_tile(void *dst_smem, const void *src_gmem, unsigned long long *bar)
+PP_DEV void tma_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"((uint32_t)kTileBytes), "r"(smem_u32(bar))
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 #endif
 
-PP_DEV void rd_issue(Reader &r)
+// ---- STAGE -------------------------------------------------------------------
+// Bring compressed bytes [byte_off, byte_off + 4*words) into sm.cw (zero filled past the
+// end of the buffer).  byte_off is a multiple of 16.  Returns false when a transfer never
+// landed.  `phase` counts the uses of the mbarrier.
+PP_DEV bool stage_window(const Sm &sm, const uint8_t *comp, uint64_t comp_bytes, uint64_t byte_off, uint32_t words,
+                         uint32_t &phase)
 {
-    // issue the tile with sequence number s_issued (if the buffer still has it)
-    const int64_t tile = r.tile_bias + (int64_t)r.s_issued;
-    const uint32_t stage = r.s_issued % kStages;
-    if (tile >= 0 && (uint64_t)tile < r.comp_tiles) {
+    uint64_t avail = byte_off < comp_bytes ? comp_bytes - byte_off : 0;
+    avail &= ~(uint64_t)15;
+    const uint32_t want = words * 4u;
+    const uint32_t nbytes = avail < want ? (uint32_t)avail : want;
+    PP_SYNC();  // every thread is done with the previous contents of cw
 #ifdef PP_HOST_EMU
-        memcpy(&g_sm.ring[stage * kTileWords], r.comp + (uint64_t)tile * kTileBytes, kTileBytes);
+    if (nbytes) memcpy(sm.cw, comp + byte_off, nbytes);
+    memset((uint8_t *)sm.cw + nbytes, 0, want - nbytes);
+    (void)phase;
+    return true;
 #else
-        __syncwarp();  // every lane is done reading the stage being overwritten
-        if ((threadIdx.x & 31u) == 0) {
-            mbar_expect_tx(&g_sm.bar[stage], kTileBytes);
-            tma_load_tile(&g_sm.ring[stage * kTileWords], r.comp + (uint64_t)tile * kTileBytes, &g_sm.bar[stage]);
+    if (threadIdx.x == 0 && nbytes) {
+        mbar_expect_tx(sm.bar, nbytes);
+        for (uint32_t o = 0; o < nbytes; o += 32768u) {
+            const uint32_t n = nbytes - o < 32768u ? nbytes - o : 32768u;
+            tma_load((uint8_t *)sm.cw + o, comp + byte_off + o, n, sm.bar);
         }
+    }
+    for (uint32_t i = nbytes / 4u + threadIdx.x; i < words; i += blockDim.x) sm.cw[i] = 0;
+    bool ok = true;
+    if (nbytes) {
+        ok = mbar_wait(sm.bar, phase & 1u);
+        phase++;
+    }
+    return __syncthreads_and(ok ? 1 : 0) != 0;
 #endif
-    } else {
-#ifndef PP_HOST_EMU
-        // nothing to load: complete the phase by hand so waiters do not hang
-        if ((threadIdx.x & 31u) == 0)
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&g_sm.bar[stage])) : "memory");
+}
+
+// ---- block-wide exclusive prefix sum over a[0..T) (in place); returns the total ----
+PP_DEV uint32_t block_excl_scan(const Sm &sm, uint32_t *a)
+{
+#ifdef PP_HOST_EMU
+    uint32_t acc = 0;
+    for (int t = 0; t < PP_NT; t++) {
+        const uint32_t v = a[t];
+        a[t] = acc;
+        acc += v;
+    }
+    return acc;
+#else
+    const int t = (int)threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t v = a[t];
+    uint32_t s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += x;
+    }
+    if (lane == 31) sm.wsum[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = ((int)blockDim.x + 31) >> 5;
+        const uint32_t w = lane < nw ? sm.wsum[lane] : 0u;
+        uint32_t ws = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, ws, d);
+            if (lane >= d) ws += x;
+        }
+        sm.wsum[lane] = ws - w;          // exclusive warp offsets
+        if (lane == 31) sm.u[31] = ws;   // total
+    }
+    __syncthreads();
+    a[t] = sm.wsum[warp] + s - v;
+    const uint32_t total = sm.u[31];
+    __syncthreads();
+    return total;
 #endif
+}
+
+// ---- HEADER: Huffman table construction -----------------------------------------
+// Canonical codes (RFC 1951 3.2.2) into a two-level lookup table: `root` primary bits,
+// sub-tables sized by the longest code under each primary prefix.  Validity rules follow
+// zlib's inflate_table: over-subscribed sets are rejected, incomplete sets are rejected
+// unless the set is a single 1-bit code (or, for distances, empty).
+// mode 0: literal/length alphabet, 1: distance alphabet.  Returns 0 or -3 (Z_DATA_ERROR).
+PP_DEV uint32_t sym_entry(int mode, uint32_t s, uint32_t l)
+{
+    if (mode == 0) {
+        if (s < 256u) return mk_entry(K_LIT, l, l, 0x8000u | s);
+        if (s == 256u) return mk_entry(K_EOB, l, l, 0);
+        if (s < 286u) return mk_entry(K_BASE, l + kLenExtra[s - 257u], l, kLenBase[s - 257u]);
+        return mk_entry(K_BAD, l, l, 0);
     }
-    r.s_issued++;
+    if (s < 30u) return mk_entry(K_BASE, l + kDistExtra[s], l, kDistBase[s]);
+    return mk_entry(K_BAD, l, l, 0);
 }
 
-PP_DEV void rd_wait(Reader &r, uint32_t seq)
+PP_DEV int build_table(const Sm &sm, uint32_t *tbl, int root, int cap, int nsym, int lens_off, int mode)
 {
-#ifndef PP_HOST_EMU
-    if (!mbar_wait(&g_sm.bar[seq % kStages], (seq / kStages) & 1u)) r.exhausted = 2;
-#endif
-    const int64_t tile = r.tile_bias + (int64_t)seq;
-    if (tile < 0 || (uint64_t)tile >= r.comp_tiles) r.exhausted |= 1;
-}
-
-// move the preloaded word one further (the tile crossing is the rare, out-of-line part)
-PP_DEV void rd_cross_tile(Reader &r)
-{
-    if (r.rpos == kRingWords) r.rpos = 0;
-    r.s_cur++;
-    rd_wait(r, r.s_cur);   // the stage we enter must have landed
-    rd_issue(r);           // the stage we leave is free again
-}
-PP_DEV void rd_advance(Reader &r)
-{
-    r.wnext++;
-    r.rpos++;
-    if ((r.rpos & (kTileWords - 1)) == 0) rd_cross_tile(r);
-    r.nw = g_sm.ring[r.rpos];
-}
-
-// Position the reader at absolute bit `bit` of the compressed buffer.
-PP_DEV void rd_seek(Reader &r, uint64_t bit, bool first)
-{
-    if (!first) {
-        // drain tiles still in flight so the ring can be re-targeted
-        for (uint32_t s = r.s_cur + 1; s < r.s_issued; s++) rd_wait(r, s);
-    }
-    const uint64_t word = bit >> 5;
-    const uint64_t tile = word / kTileWords;
-    r.tile_bias = (int64_t)tile - (int64_t)r.s_issued;
-    r.s_cur = r.s_issued;
-    r.exhausted &= 2;  // a timed-out transfer stays fatal
-    for (int i = 0; i < kStages; i++) rd_issue(r);
-    rd_wait(r, r.s_cur);
-    r.wnext = word;
-    r.rpos = (r.s_cur % kStages) * kTileWords + (uint32_t)(word % kTileWords);
-    r.nw = g_sm.ring[r.rpos];
-    // first word, minus the bits in front of `bit`; then top up to >= 32 valid bits
-    const uint32_t sh = (uint32_t)(bit & 31ull);
-    r.lo = r.nw >> sh;
-    r.hi = 0;
-    r.bitcnt = 32 - (int)sh;
-    rd_advance(r);
-    if (r.bitcnt < 32) {
-        r.lo |= r.nw << r.bitcnt;
-        r.hi = fsl_hi(r.nw, (uint32_t)r.bitcnt);
-        r.bitcnt += 32;
-        rd_advance(r);
-    }
-}
-
-// restore the invariant bitcnt >= 32 (lo fully valid)
-PP_DEV void rd_refill(Reader &r)
-{
-    if (r.bitcnt < 32) {
-        r.lo |= r.nw << r.bitcnt;
-        r.hi = fsl_hi(r.nw, (uint32_t)r.bitcnt);
-        r.bitcnt += 32;
-        rd_advance(r);
-    }
-}
-PP_DEV void rd_consume(Reader &r, uint32_t n)  // n < 32
-{
-    r.lo = fsr(r.lo, r.hi, n);
-    r.hi >>= n;
-    r.bitcnt -= (int)n;
-}
-PP_DEV uint32_t rd_bits(Reader &r, uint32_t n)  // n <= 16
-{
-    const uint32_t v = r.lo & ((1u << n) - 1u);
-    rd_consume(r, n);
-    rd_refill(r);
-    return v;
-}
-PP_DEV uint64_t rd_bitpos(const Reader &r) { return r.wnext * 32ull - (uint64_t)r.bitcnt; }
-
-// ---- Huffman table construction ---------------------------------------------
-// Canonical codes (RFC 1951 3.2.2) into a two-level lookup table: `root` primary
-// bits, sub-tables sized by the longest code under each primary prefix.
-// Validity rules follow zlib's inflate_table: over-subscribed sets are rejected,
-// incomplete sets are rejected unless the set is a single 1-bit code (or, for
-// distances, empty).  Returns 0 or -3 (Z_DATA_ERROR).
-// mode 0: literal/length alphabet, 1: distance alphabet, 2: code-length alphabet.
-PP_DEV int build_table(uint32_t *tbl, int root, int cap, int nsym, int lens_off, int mode)
-{
-    Smem &sm = g_sm;
     const uint8_t *lens = sm.lens + lens_off;
+    const int T = PP_NT;
     // 1. histogram of code lengths
-    PP_LANE0_BEGIN
-    for (int i = 0; i < 16; i++) sm.count[i] = 0;
-    for (int s = 0; s < nsym; s++) sm.count[lens[s]]++;
-    PP_LANE0_END
-    int maxlen = 0;
-    for (int l = 15; l >= 1; l--)
-        if (sm.count[l]) { maxlen = l; break; }
-    // 2. validity + first code of each length
-    int left = 1;
-    for (int l = 1; l <= 15; l++) {
-        left <<= 1;
-        left -= (int)sm.count[l];
-        if (left < 0) return -3;  // over-subscribed
-    }
-    if (left > 0 && maxlen != 1 && !(mode == 1 && maxlen == 0)) return -3;  // incomplete set
-    if (left > 0 && mode == 2) return -3;                                   // zlib: CODES must be complete
-    PP_LANE0_BEGIN
+    PP_FOR_T(t)
+    if (t < 16) sm.count[t] = 0;
+    PP_END_T
+    PP_SYNC();
+    PP_FOR_T(t)
+    for (int s = t; s < nsym; s += T) PP_ATOMIC_ADD(&sm.count[lens[s]], 1u);
+    PP_END_T
+    PP_SYNC();
+    // 2. validity, first code and first sorted slot of each length (thread 0)
+    PP_T0_BEGIN
     {
-        uint32_t code = 0;
-        sm.next[0] = 0;
+        int maxlen = 0, left = 1, err = 0;
         for (int l = 1; l <= 15; l++) {
-            code = (code + (l > 1 ? (uint32_t)sm.count[l - 1] : 0u)) << 1;
-            sm.next[l] = (uint16_t)code;
+            if (sm.count[l]) maxlen = l;
+            left <<= 1;
+            left -= (int)sm.count[l];
+            if (left < 0) err = 1;  // over-subscribed
         }
+        if (left > 0 && maxlen != 1 && !(mode == 1 && maxlen == 0)) err = 1;  // incomplete set
+        uint32_t code = 0, off = 0;
+        sm.first[0] = 0;
+        sm.offs[0] = 0;
+        for (int l = 1; l <= 15; l++) {
+            code = (code + (l > 1 ? sm.count[l - 1] : 0u)) << 1;
+            sm.first[l] = code;
+            sm.offs[l] = off;
+            off += sm.count[l];
+        }
+        sm.u[0] = (uint32_t)err;
+        sm.u[1] = (uint32_t)maxlen;
     }
-    PP_LANE0_END
-    // 3. primary table: start from "invalid code" everywhere (incomplete sets leave holes)
+    PP_T0_END
+    PP_SYNC();
+    if (sm.u[0]) { PP_SYNC(); return -3; }
+    const int maxlen = (int)sm.u[1];
+    // 3. canonical code of every symbol: first[len] + (symbols of the same length before it)
+    PP_FOR_T(t)
+    for (int s = t; s < nsym; s += T) {
+        const uint32_t l = lens[s];
+        if (l == 0) continue;
+        uint32_t rank = 0;
+        const uint32_t l4 = l * 0x01010101u;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(lens);  // lens_off is a multiple of 4
+        const int full = s >> 2;
+        for (int i = 0; i < full; i++) rank += popc32(eq_bytes(w[i], l4));
+        for (int i = full * 4; i < s; i++) rank += (lens[i] == l);
+        sm.codes[lens_off + s] = (uint16_t)(sm.first[l] + rank);
+        sm.sorted[sm.offs[l] + rank] = (uint16_t)s;
+    }
+    PP_END_T
+    PP_SYNC();
+    // 4. primary table: every slot finds its own code by canonical search
     const int nprim = 1 << root;
-    PP_LANES_BEGIN
-    for (int i = lane; i < nprim; i += 32) tbl[i] = mk_entry(K_BAD, 1, 1, 0);
-    PP_LANES_END
-    // 4. sub-table geometry for prefixes that own codes longer than `root`.
-    // Prefix p (root bits, MSB-first code order) owns the length-l codes in
-    // [p << (l-root), (p+1) << (l-root)); it needs a sub-table when that range meets
-    // [first[l], first[l]+count[l]) for some l > root.  Long codes sit at the top of the
-    // code space, so only prefixes from the first long code's prefix upward are visited,
-    // in code order (sub-tables come out in canonical order).
-    int used = nprim;
-    if (maxlen > root) {
+    PP_FOR_T(t)
+    for (int i = t; i < nprim; i += T) {
+        const uint32_t c = bitrev((uint32_t)i, root);  // the slot's bits as an MSB-first code prefix
+        uint32_t ent = mk_entry(K_BAD, 1, 1, 0);
+        const int lim = maxlen < root ? maxlen : root;
+        for (int l = 1; l <= lim; l++) {
+            const uint32_t cc = (c >> (root - l)) - sm.first[l];
+            if (cc < sm.count[l]) {
+                ent = sym_entry(mode, sm.sorted[sm.offs[l] + cc], (uint32_t)l);
+                break;
+            }
+        }
+        tbl[i] = ent;
+    }
+    PP_END_T
+    PP_SYNC();
+    if (maxlen <= root) return 0;
+    // 5. sub-table geometry (thread 0): prefix p owns the length-l codes in
+    //    [p << (l-root), (p+1) << (l-root)); long codes sit at the top of the code space.
+    PP_T0_BEGIN
+    {
+        int used = nprim, err = 0;
         int pmin = nprim;
         for (int l = root + 1; l <= maxlen; l++)
-            if (sm.count[l]) { pmin = (int)(sm.next[l] >> (l - root)); break; }
+            if (sm.count[l]) { pmin = (int)(sm.first[l] >> (l - root)); break; }
         for (int p = pmin; p < nprim; p++) {
             int sub = 0;
             for (int l = maxlen; l > root; l--) {
                 const uint32_t lo = (uint32_t)p << (l - root), hi = ((uint32_t)p + 1u) << (l - root);
-                const uint32_t f = sm.next[l], e = f + sm.count[l];
+                const uint32_t f = sm.first[l], e = f + sm.count[l];
                 if (sm.count[l] && lo < e && hi > f) { sub = l - root; break; }
             }
             if (sub) {
-                if (used + (1 << sub) > cap) return -3;  // cannot happen for valid sets (see kLitCap/kDistCap)
-                const uint32_t idx = bitrev((uint32_t)p, root);
-                PP_LANE0_BEGIN
-                tbl[idx] = mk_entry(K_SUB, (uint32_t)root, (uint32_t)root, (uint32_t)used) | ((uint32_t)sub << 13);
-                PP_LANE0_END
-                PP_LANES_BEGIN
-                for (int i = lane; i < (1 << sub); i += 32) tbl[used + i] = mk_entry(K_BAD, 1, 1, 0);
-                PP_LANES_END
+                if (used + (1 << sub) > cap) { err = 1; break; }
+                tbl[bitrev((uint32_t)p, root)] =
+                    mk_entry(K_SUB, (uint32_t)root, (uint32_t)root, (uint32_t)used) | ((uint32_t)sub << 13);
                 used += 1 << sub;
             }
         }
+        sm.u[0] = (uint32_t)err;
+        sm.u[2] = (uint32_t)used;
     }
-    // 5. assign codes in symbol order and replicate entries
-    for (int s = 0; s < nsym; s++) {
+    PP_T0_END
+    PP_SYNC();
+    if (sm.u[0]) { PP_SYNC(); return -3; }
+    const int used = (int)sm.u[2];
+    PP_FOR_T(t)
+    for (int i = nprim + t; i < used; i += T) tbl[i] = mk_entry(K_BAD, 1, 1, 0);
+    PP_END_T
+    PP_SYNC();
+    // 6. long codes into their sub-tables (one symbol per thread)
+    PP_FOR_T(t)
+    for (int s = t; s < nsym; s += T) {
         const int l = lens[s];
-        if (l == 0) continue;
-        const uint32_t code = sm.next[l];
-        PP_LANE0_BEGIN
-        sm.next[l] = (uint16_t)(code + 1);
-        PP_LANE0_END
-        uint32_t kind, tot, val;
-        if (mode == 0) {
-            if (s < 256) { kind = K_LIT; tot = (uint32_t)l; val = 0x8000u | (uint32_t)s; }
-            else if (s == 256) { kind = K_EOB; tot = (uint32_t)l; val = 0; }
-            else if (s < 286) { kind = K_BASE; tot = (uint32_t)l + kLenExtra[s - 257]; val = kLenBase[s - 257]; }
-            else { kind = K_BAD; tot = (uint32_t)l; val = 0; }
-        } else if (mode == 1) {
-            if (s < 30) { kind = K_BASE; tot = (uint32_t)l + kDistExtra[s]; val = kDistBase[s]; }
-            else { kind = K_BAD; tot = (uint32_t)l; val = 0; }
-        } else {
-            kind = K_LIT; tot = (uint32_t)l; val = (uint32_t)s;
-        }
-        const uint32_t ent = mk_entry(kind, tot, (uint32_t)l, val);
-        if (l <= root) {
-            const uint32_t base = bitrev(code, l);
-            const int reps = 1 << (root - l);
-            PP_LANES_BEGIN
-            for (int j = lane; j < reps; j += 32) tbl[base | ((uint32_t)j << l)] = ent;
-            PP_LANES_END
-        } else {
-            const uint32_t p = code >> (l - root);
-            const uint32_t pe = tbl[bitrev(p, root)];
-            const int sub = (int)e_sub(pe);
-            const uint32_t start = e_val(pe);
-            const int sl = l - root;  // bits of this code inside the sub-table
-            const uint32_t base = bitrev(code & ((1u << sl) - 1u), sl);
-            const int reps = 1 << (sub - sl);
-            PP_LANES_BEGIN
-            for (int j = lane; j < reps; j += 32) tbl[start + (base | ((uint32_t)j << sl))] = ent;
-            PP_LANES_END
-        }
+        if (l <= root) continue;
+        const uint32_t code = sm.codes[lens_off + s];
+        const uint32_t pe = tbl[bitrev(code >> (l - root), root)];
+        const int sub = (int)e_sub(pe);
+        const uint32_t st = e_val(pe);
+        const int sl = l - root;  // bits of this code inside the sub-table
+        const uint32_t base = bitrev(code & ((1u << sl) - 1u), sl);
+        const uint32_t ent = sym_entry(mode, (uint32_t)s, (uint32_t)l);
+        for (int j = 0; j < (1 << (sub - sl)); j++) tbl[st + (base | ((uint32_t)j << sl))] = ent;
     }
+    PP_END_T
+    PP_SYNC();
     return 0;
 }
 
-// ---- output side --------------------------------------------------------------
-// A batch covers output bytes [abase, abase + bpos): abase is 16-byte aligned, the first
-// `carry` bytes are already resolved (the unaligned tail of the previous batch).
-struct Out {
-    uint8_t *base;       // &slot[lead_len]: output byte 0; history is at negative offsets
-    uint32_t len;        // bytes wanted
-    uint32_t abase;      // output offset of batch byte 0 (multiple of 16)
-    uint32_t bpos;       // bytes of the batch described so far (carry + decoded)
-    uint32_t carry;      // resolved bytes at the front of the batch
-    uint32_t rstart;     // batch offset where the current round began
-    uint32_t nrounds;
-    PP_LV(uint32_t, nl);   // '\n' bytes flushed by this lane
-    PP_LV(uint32_t, nul);  // non-zero when this lane flushed a NUL byte
-};
-
-PP_DEV uint32_t out_pos(const Out &o) { return o.abase + o.bpos; }
-
-// 0x80 in every byte of w that equals c (c replicated in all four bytes of c4)
-PP_DEV uint32_t eq_bytes(uint32_t w, uint32_t c4)
+PP_DEV int fixed_tables(const Sm &sm)
 {
-    const uint32_t x = w ^ c4;
-    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
-}
-PP_DEV uint32_t popc32(uint32_t v)
-{
-#ifdef PP_HOST_EMU
-    return (uint32_t)__builtin_popcount(v);
-#else
-    return (uint32_t)__popc(v);
-#endif
+    PP_FOR_T(t)
+    for (int s = t; s < 320; s += PP_NT)
+        sm.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5);
+    PP_END_T
+    PP_SYNC();
+    int rc = build_table(sm, sm.lit, kRootL, kLitCap, 288, 0, 0);
+    if (rc) return rc;
+    // zlib's fixed distance table is the 5-bit complete code over 32 symbols (30/31 invalid)
+    return build_table(sm, sm.dist, kRootD, kDistCap, 32, 288, 1);
 }
 
-// COPY phase: resolve the batch and move its whole 16-byte vectors to global memory.
-// final: also write the unaligned tail (end of chunk / before a stored block).
-PP_DEV void out_resolve(Out &o, bool final)
+// Dynamic block header at window-relative bit `pos` (just past the 3 block-type bits):
+// HLIT/HDIST/HCLEN, the code-length code and the run-length coded lengths (thread 0),
+// then both tables (all threads).  On success *pos_out is the first symbol's bit.
+PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 {
-    Smem &sm = g_sm;
-    const uint32_t n = o.bpos;
-    const int32_t carry = (int32_t)o.carry;
-    PP_WARP_SYNC();  // the source map written during DECODE is read by other lanes now
-    // (1) literals and bytes whose source is already resolved (before the batch, or in the
-    //     carried head): independent gathers
+    PP_T0_BEGIN
     {
-        const uint8_t *hist = o.base + o.abase;  // batch byte i lives at hist[i]
-        for (uint32_t b = o.carry; b < n; b += 128u) {
-            PP_LANES_BEGIN
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = b + (uint32_t)u * 32u + (uint32_t)lane;
-                if (i < n) {
-                    const uint32_t e = sm.map[i];
-                    const int32_t sidx = (int32_t)i - (int32_t)e - 1;  // batch offset of the source
-                    if (e & 0x8000u) sm.obuf[i] = (uint8_t)e;
-                    else if (sidx < 0) sm.obuf[i] = hist[sidx];
-                    else if (sidx < carry) sm.obuf[i] = sm.obuf[sidx];
+        int err = 0;
+        const uint32_t nlen = peek_bits(sm.cw, pos, 5) + 257u;
+        const uint32_t ndist = peek_bits(sm.cw, pos + 5, 5) + 1u;
+        const uint32_t ncode = peek_bits(sm.cw, pos + 10, 4) + 4u;
+        uint32_t p = pos + 14;
+        if (nlen > 286u || ndist > 30u) err = 1;  // too many length or distance symbols
+        // code-length code: 19 symbols with 3-bit lengths.  7-bit direct lookup table kept in
+        // sm.dist (free at this point): entry = sym | len << 8, 0 = invalid
+        uint8_t cl[19];
+        for (int i = 0; i < 19; i++) cl[i] = 0;
+        for (uint32_t i = 0; i < ncode; i++) { cl[kClOrder[i]] = (uint8_t)peek_bits(sm.cw, p, 3); p += 3; }
+        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nxt[8];
+        for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+        int left = 1;
+        for (int l = 1; l <= 7; l++) {
+            left <<= 1;
+            left -= (int)cnt[l];
+            if (left < 0) err = 1;
+        }
+        if (left > 0) err = 1;  // zlib: the code-length code must be complete
+        if (!err) {
+            uint32_t code = 0;
+            for (int l = 1; l <= 7; l++) {
+                code = (code + (l > 1 ? cnt[l - 1] : 0u)) << 1;
+                nxt[l] = code;
+            }
+            for (int i = 0; i < 128; i++) sm.dist[i] = 0;
+            for (uint32_t s = 0; s < 19; s++) {
+                const uint32_t l = cl[s];
+                if (!l) continue;
+                const uint32_t base = bitrev(nxt[l]++, (int)l);
+                for (uint32_t j = base; j < 128u; j += 1u << l) sm.dist[j] = s | (l << 8) | 0x8000u;
+            }
+            uint32_t have = 0;
+            const uint32_t total = nlen + ndist;
+            while (have < total && !err) {
+                const uint32_t e = sm.dist[peek_bits(sm.cw, p, 7)];
+                if (!e) { err = 1; break; }
+                p += (e >> 8) & 15u;
+                const uint32_t sym = e & 255u;
+                if (sym < 16u) {
+                    sm.lens[have++] = (uint8_t)sym;
+                } else {
+                    uint32_t rep, val = 0;
+                    if (sym == 16u) {
+                        if (have == 0) { err = 1; break; }  // invalid bit length repeat
+                        val = sm.lens[have - 1];
+                        rep = 3u + peek_bits(sm.cw, p, 2);
+                        p += 2;
+                    } else if (sym == 17u) {
+                        rep = 3u + peek_bits(sm.cw, p, 3);
+                        p += 3;
+                    } else {
+                        rep = 11u + peek_bits(sm.cw, p, 7);
+                        p += 7;
+                    }
+                    if (have + rep > total) { err = 1; break; }  // invalid bit length repeat
+                    for (uint32_t j = 0; j < rep; j++) sm.lens[have + j] = (uint8_t)val;
+                    have += rep;
                 }
             }
-            PP_LANES_END
-        }
-    }
-    // (2) bytes whose source is inside the batch: round by round out of shared memory
-    for (uint32_t r = 0; r < o.nrounds; r++) {
-        const uint32_t rs = sm.rounds[r], re = r + 1 < o.nrounds ? sm.rounds[r + 1] : n;
-        for (uint32_t b = rs; b < re; b += 32u) {
-            PP_LV(uint32_t, val);
-            PP_LV(uint32_t, has);
-            PP_LANES_BEGIN
-            const uint32_t i = b + (uint32_t)lane;
-            PP_L(has) = 0;
-            PP_L(val) = 0;
-            if (i < re) {
-                const uint32_t e = sm.map[i];
-                const int32_t sidx = (int32_t)i - (int32_t)e - 1;
-                if (!(e & 0x8000u) && sidx >= carry) { PP_L(val) = sm.obuf[sidx]; PP_L(has) = 1; }
-            }
-            PP_LANES_END
-            PP_LANES_BEGIN
-            if (PP_L(has)) sm.obuf[b + (uint32_t)lane] = (uint8_t)PP_L(val);
-            PP_LANES_END
-        }
-    }
-    // (3) whole 16-byte vectors leave; '\n' and NUL are counted on the way
-    const uint32_t nvec = n / 16u;
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(o.base + o.abase);
-        const uint4 *src = reinterpret_cast<const uint4 *>(sm.obuf);
-        PP_LANES_BEGIN
-        for (uint32_t i = (uint32_t)lane; i < nvec; i += 32u) {
-            const uint4 w = src[i];
-            dst[i] = w;
-            PP_L(o.nl) += popc32(eq_bytes(w.x, 0x0a0a0a0au)) + popc32(eq_bytes(w.y, 0x0a0a0a0au)) +
-                          popc32(eq_bytes(w.z, 0x0a0a0a0au)) + popc32(eq_bytes(w.w, 0x0a0a0a0au));
-            PP_L(o.nul) |= eq_bytes(w.x, 0u) | eq_bytes(w.y, 0u) | eq_bytes(w.z, 0u) | eq_bytes(w.w, 0u);
-        }
-        PP_LANES_END
-    }
-    const uint32_t done = nvec * 16u, rem = n - done;
-    if (final) {
-        PP_LANES_BEGIN
-        if ((uint32_t)lane < rem) {
-            const uint32_t c = sm.obuf[done + (uint32_t)lane];
-            o.base[o.abase + done + (uint32_t)lane] = (uint8_t)c;
-            PP_L(o.nl) += (c == 10u);
-            PP_L(o.nul) |= (c == 0u);
-        }
-        PP_LANES_END
-        o.abase += n;  // may be unaligned now: only a stored block or the end of the chunk follows
-        o.carry = 0;
-    } else {
-        // the unaligned tail stays in shared memory as the head of the next batch
-        PP_LV(uint32_t, t);
-        PP_LANES_BEGIN
-        PP_L(t) = (uint32_t)lane < rem ? sm.obuf[done + (uint32_t)lane] : 0u;
-        PP_LANES_END
-        PP_LANES_BEGIN
-        if ((uint32_t)lane < rem) sm.obuf[lane] = (uint8_t)PP_L(t);
-        PP_LANES_END
-        o.abase += done;
-        o.carry = rem;
-    }
-    o.bpos = o.carry;
-    o.rstart = o.carry;
-    o.nrounds = 0;
-}
-
-// ---- block decoders -------------------------------------------------------------
-// Stored block: bytes go straight from the compressed buffer to the output.
-PP_DEV int stored_block(Reader &r, Out &o)
-{
-    rd_consume(r, (uint32_t)r.bitcnt & 7u);  // to the byte boundary
-    rd_refill(r);
-    const uint32_t v = r.lo;
-    const uint32_t len = v & 0xffffu, nlen = v >> 16;
-    if ((len ^ 0xffffu) != nlen) return -3;  // invalid stored block lengths
-    const uint64_t byte0 = (rd_bitpos(r) >> 3) + 4u;
-    out_resolve(o, true);
-    uint32_t n = len;
-    if (n > o.len - o.abase) n = o.len - o.abase;
-    if (byte0 + len > r.comp_tiles * (uint64_t)kTileBytes) return -3;  // input exhausted
-    const uint8_t *src = r.comp + byte0;
-    uint8_t *dst = o.base + o.abase;
-    const uint32_t end = o.abase + n;
-    const uint32_t al = end & ~15u;  // the next batch must start on a 16-byte boundary
-    for (uint32_t b = 0; b < n; b += 32u) {
-        PP_LANES_BEGIN
-        const uint32_t j = b + (uint32_t)lane;
-        if (j < n) {
-            const uint32_t c = src[j];
-            dst[j] = (uint8_t)c;
-            // bytes past the last boundary are counted when the next batch flushes them
-            if (o.abase + j < al) {
-                PP_L(o.nl) += (c == 10u);
-                PP_L(o.nul) |= (c == 0u);
+            if (!err && sm.lens[256] == 0) err = 1;  // invalid code -- missing end-of-block
+            if (!err) {
+                // distance lengths follow the literal/length lengths: move them to lens[288..]
+                uint8_t tmp[32];
+                for (uint32_t i = 0; i < ndist; i++) tmp[i] = sm.lens[nlen + i];
+                for (uint32_t i = 0; i < ndist; i++) sm.lens[288 + i] = tmp[i];
+                for (uint32_t i = nlen; i < 288u; i++) sm.lens[i] = 0;
+                for (uint32_t i = 288u + ndist; i < 320u; i++) sm.lens[i] = 0;
             }
         }
-        PP_LANES_END
+        sm.u[0] = (uint32_t)err;
+        sm.u[3] = nlen;
+        sm.u[4] = ndist;
+        sm.u[5] = p;
     }
-    // pull the bytes past the boundary back into shared memory as the resolved head of the
-    // next batch (fewer than 16)
-    {
-        PP_LV(uint32_t, t);
-        PP_LANES_BEGIN
-        PP_L(t) = (uint32_t)lane < end - al ? o.base[al + (uint32_t)lane] : 0u;
-        PP_LANES_END
-        PP_LANES_BEGIN
-        if ((uint32_t)lane < end - al) g_sm.obuf[lane] = (uint8_t)PP_L(t);
-        PP_LANES_END
-    }
-    if (al < o.abase) {
-        // a short block: the boundary lies before it.  Bytes [al, abase) were counted by the
-        // final flush above and will be counted again with the next vector: take them out once.
-        PP_LANES_BEGIN
-        if ((uint32_t)lane < o.abase - al) PP_L(o.nl) -= (g_sm.obuf[lane] == 10u);
-        PP_LANES_END
-    }
-    o.carry = end - al;
-    o.abase = al;
-    o.bpos = o.carry;
-    o.rstart = o.carry;
-    o.nrounds = 0;
-    rd_seek(r, (byte0 + len) * 8ull, false);
-    return 0;
+    PP_T0_END
+    PP_SYNC();
+    if (sm.u[0]) { PP_SYNC(); return -3; }
+    const int nlen = (int)sm.u[3], ndist = (int)sm.u[4];
+    *pos_out = sm.u[5];
+    PP_SYNC();
+    int rc = build_table(sm, sm.lit, kRootL, kLitCap, nlen, 0, 0);
+    if (rc) return rc;
+    return build_table(sm, sm.dist, kRootD, kDistCap, ndist, 288, 1);
 }
 
-PP_DEV int fixed_tables()
+// ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
+// Decodes the symbols that START in [start, limit) (window-relative bits).  WRITE: also
+// writes the source map, entry i of the segment at map[o + i], never at or past map[oclip].
+struct Seg {
+    uint32_t end, out, flag;
+};
+template <int WRITE>
+PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *map, uint32_t o, uint32_t oclip)
 {
-    Smem &sm = g_sm;
-    PP_LANES_BEGIN
-    for (int s = lane; s < 288; s += 32) sm.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
-    PP_LANES_END
-    int rc = build_table(sm.lit, kRootL, kLitCap, 288, 0, 0);
-    if (rc) return rc;
-    PP_LANES_BEGIN
-    sm.lens[lane] = 5;
-    PP_LANES_END
-    // zlib's fixed distance table is the 5-bit complete code over 32 symbols (30/31 invalid)
-    return build_table(sm.dist, kRootD, kDistCap, 32, 0, 1);
-}
-
-PP_DEV int dynamic_tables(Reader &r)
-{
-    Smem &sm = g_sm;
-    const uint32_t nlen = rd_bits(r, 5) + 257u;
-    const uint32_t ndist = rd_bits(r, 5) + 1u;
-    const uint32_t ncode = rd_bits(r, 4) + 4u;
-    if (nlen > 286u || ndist > 30u) return -3;  // too many length or distance symbols
-    // code-length code: 19 symbols, 3-bit lengths, stored at lens[288..307)
-    PP_LANES_BEGIN
-    if (lane < 19) sm.lens[288 + lane] = 0;
-    PP_LANES_END
-    for (uint32_t i = 0; i < ncode; i++) {
-        const uint32_t l = rd_bits(r, 3);
-        PP_LANE0_BEGIN
-        sm.lens[288 + kClOrder[i]] = (uint8_t)l;
-        PP_LANE0_END
-    }
-    // zlib builds this table with root 7 and rejects incomplete sets outright (type CODES);
-    // the distance table's storage is free at this point
-    int rc = build_table(sm.dist, 7, kDistCap, 19, 288, 2);
-    if (rc) return rc;
-    uint32_t have = 0;
-    const uint32_t total = nlen + ndist;
-    while (have < total) {
-        const uint32_t e = sm.dist[r.lo & 127u];
-        if (e_kind(e) != K_LIT) return -3;
-        rd_consume(r, e_tot(e));
-        rd_refill(r);
-        const uint32_t sym = e_val(e);
-        if (sym < 16u) {
-            PP_LANE0_BEGIN
-            sm.lens[have] = (uint8_t)sym;
-            PP_LANE0_END
-            have++;
-        } else {
-            uint32_t rep, val = 0;
-            if (sym == 16u) {
-                if (have == 0) return -3;  // invalid bit length repeat
-                val = sm.lens[have - 1];
-                rep = 3u + rd_bits(r, 2);
-            } else if (sym == 17u) {
-                rep = 3u + rd_bits(r, 3);
-            } else {
-                rep = 11u + rd_bits(r, 7);
-            }
-            if (have + rep > total) return -3;  // invalid bit length repeat
-            PP_LANES_BEGIN
-            for (uint32_t j = (uint32_t)lane; j < rep; j += 32u) sm.lens[have + j] = (uint8_t)val;
-            PP_LANES_END
-            have += rep;
-        }
-    }
-    if (sm.lens[256] == 0) return -3;  // invalid code -- missing end-of-block
-    // distance lengths follow the literal/length lengths: move them out of the way first
-    {
-        PP_LV(uint8_t, t);
-        PP_LANES_BEGIN
-        PP_L(t) = (uint32_t)lane < ndist ? sm.lens[nlen + lane] : (uint8_t)0;
-        PP_LANES_END
-        PP_LANES_BEGIN
-        if ((uint32_t)lane < ndist) sm.lens[288 + lane] = PP_L(t);
-        PP_LANES_END
-    }
-    rc = build_table(sm.lit, kRootL, kLitCap, (int)nlen, 0, 0);
-    if (rc) return rc;
-    return build_table(sm.dist, kRootD, kDistCap, (int)ndist, 288, 1);
-}
-
-// DECODE phase for one Huffman block: symbols -> source map, until end-of-block (returns 1),
-// the output is complete (returns 0) or an error (-3).  Runs the copy phase whenever a
-// batch fills up.
-PP_DEV int huffman_block(Reader &r, Out &o)
-{
-    Smem &sm = g_sm;
+    const uint32_t *cw = sm.cw;
+    uint32_t wp = start >> 5;
+    const uint32_t sh = start & 31u;
+    uint64_t buf = ((uint64_t)cw[wp] | ((uint64_t)cw[wp + 1] << 32)) >> sh;
+    uint32_t cnt = 64u - sh;
+    wp += 2;
+    uint32_t out = 0, flag = F_NONE;
     for (;;) {
-        if (o.bpos >= (uint32_t)kBatch || o.nrounds >= (uint32_t)kMaxRounds) out_resolve(o, false);
-        if (out_pos(o) >= o.len) return 0;
-        if (r.exhausted) return -3;
-        uint32_t lo = r.lo;
+        if (wp * 32u - cnt >= limit) break;
+        if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+        uint32_t lo = (uint32_t)buf;
         uint32_t e = sm.lit[lo & ((1u << kRootL) - 1u)];
         if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
-        const uint32_t kind = e_kind(e);
-        const uint32_t tot = e_tot(e);
+        const uint32_t kind = e_kind(e), tot = e_tot(e);
         if (kind == K_LIT) {
-            rd_consume(r, tot);
-            rd_refill(r);
-            sm.map[o.bpos] = (uint16_t)e_val(e);  // every lane stores the same value: no branch, no sync
-            o.bpos++;
+            if (WRITE) { if (o + out < oclip) map[o + out] = (uint16_t)e_val(e); }
+            out++;
+            buf >>= tot;
+            cnt -= tot;
             continue;
         }
         if (kind == K_BASE) {
-            uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
-            rd_consume(r, tot);
-            rd_refill(r);
-            lo = r.lo;
+            const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
+            buf >>= tot;
+            cnt -= tot;
+            if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+            lo = (uint32_t)buf;
             uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
             if (e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
-            if (e_kind(d) != K_BASE) return -3;  // invalid distance code
+            if (e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
             const uint32_t dtot = e_tot(d);
             const uint32_t dist = e_val(d) + ((lo & ~(0xffffffffu << dtot)) >> e_cl(d));
-            rd_consume(r, dtot);
-            rd_refill(r);
+            buf >>= dtot;
+            cnt -= dtot;
             // dist <= 32768 <= lead_len always, so "distance too far back" cannot occur:
             // the reference primes a full 32 KB dictionary (Core.cs:158)
-            const uint32_t room = o.len - out_pos(o);
-            if (len > room) len = room;
-            // does the match read bytes produced since the current round began?
-            const uint32_t span = len < dist ? len : dist;
-            if ((int32_t)(o.bpos - dist + span) > (int32_t)o.rstart) {
-                sm.rounds[o.nrounds] = (uint16_t)o.bpos;  // uniform store
-                o.nrounds++;
-                o.rstart = o.bpos;
+            if (WRITE) {
+                const uint32_t p0 = o + out;
+                uint32_t n = p0 < oclip ? oclip - p0 : 0u;
+                if (n > len) n = len;
+                if (dist >= len) {
+                    const uint16_t v = (uint16_t)(dist - 1u);
+                    for (uint32_t j = 0; j < n; j++) map[p0 + j] = v;
+                } else {
+                    // overlapping run: byte j repeats the `dist` bytes before the match, so its
+                    // source is dist*(j/dist+1) back — always in front of the match itself
+                    for (uint32_t j = 0; j < n; j++) map[p0 + j] = (uint16_t)(dist * (j / dist + 1u) - 1u);
+                }
             }
-            if (dist >= len) {
-                PP_LANES_BEGIN
-                for (uint32_t j = (uint32_t)lane; j < len; j += 32u) sm.map[o.bpos + j] = (uint16_t)(dist - 1u);
-                PP_LANES_END_NOSYNC
-            } else {
-                // overlapping run: byte j repeats the `dist` bytes before the match, so its
-                // source is dist*(j/dist+1) back — always in front of the match itself
-                PP_LANES_BEGIN
-                for (uint32_t j = (uint32_t)lane; j < len; j += 32u)
-                    sm.map[o.bpos + j] = (uint16_t)(dist * (j / dist + 1u) - 1u);
-                PP_LANES_END_NOSYNC
-            }
-            o.bpos += len;
+            out += len;
             continue;
         }
         if (kind == K_EOB) {
-            rd_consume(r, tot);
-            rd_refill(r);
-            return 1;
+            buf >>= tot;
+            cnt -= tot;
+            flag = F_EOB;
+            break;
         }
-        return -3;  // invalid literal/length code
+        flag = F_BAD;  // invalid literal/length code
+        break;
+    }
+    Seg r;
+    r.end = wp * 32u - cnt;
+    r.out = out;
+    r.flag = flag;
+    return r;
+}
+
+struct WindowOut {
+    uint32_t next_bit;   // window-relative bit after the last symbol used
+    uint32_t produced;   // output bytes (clipped to the room left)
+    uint32_t flag;       // F_EOB: the block ended; F_BAD: invalid data; F_NONE: window or output exhausted
+    uint32_t rounds;     // SYNC rounds (statistics)
+};
+
+// ---- RESOLVE ------------------------------------------------------------------------
+// Source map -> bytes for window output [0, total) that lands at outp[0..total).
+// `a` = misalignment of outp (outp - a is 16-byte aligned); map entry of byte q is map[q + a].
+PP_DEV void resolve_window(const Sm &sm, const uint16_t *map, uint8_t *outp, uint32_t a, uint32_t total)
+{
+    const int T = PP_NT;
+    const uint32_t R = (uint32_t)T * kTileB;
+    const uint32_t vend = a + total;         // virtual index = q + a; valid bytes: a <= v < vend
+    uint8_t *vbase = outp - a;               // 16-byte aligned; vbase[v] is the byte of virtual index v
+    for (uint32_t tb = 0; tb < vend; tb += R) {
+        // (1) literals, and bytes whose source lies before the tile: independent gathers
+        int pend_any = 0;
+        PP_FOR_T(t)
+        {
+            const uint32_t v0 = tb + (uint32_t)t * kTileB;
+            uint16_t ent[kTileB];
+            if (v0 < vend) {
+                const uint4 m0 = *reinterpret_cast<const uint4 *>(map + v0);
+                const uint4 m1 = *reinterpret_cast<const uint4 *>(map + v0 + 8);
+                const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int j = 0; j < kTileB; j++) ent[j] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
+            }
+            uint32_t r[kTileB];
+            int pend = 0;
+#pragma unroll
+            for (int j = 0; j < kTileB; j++) {
+                const uint32_t v = v0 + (uint32_t)j;
+                uint32_t x = 0x8000u;  // bytes outside [a, vend) are never stored
+                if (v >= a && v < vend) {
+                    const uint32_t e = ent[j];
+                    if (e & 0x8000u) {
+                        x = e;
+                    } else {
+                        const int64_t sv = (int64_t)v - (int64_t)e - 1;  // virtual index of the source
+                        if (sv < (int64_t)tb || sv < (int64_t)a) {  // before the tile, or before the window
+                            x = 0x8000u | (uint32_t)vbase[sv];
+                        } else {
+                            x = (uint32_t)(sv - (int64_t)tb);
+                            pend = 1;
+                        }
+                    }
+                }
+                r[j] = x;
+            }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.res + (uint32_t)t * kTileB);
+#pragma unroll
+            for (int j = 0; j < kTileB / 2; j++) dst[j] = r[2 * j] | (r[2 * j + 1] << 16);
+            pend_any |= pend;
+        }
+        PP_END_T
+        pend_any = PP_SYNC_OR(pend_any);
+        // (2) sources inside the tile: pointer jumping (every entry is either the byte or the
+        //     index of an earlier byte with the same value; both stay true under any interleaving)
+        while (pend_any) {
+            pend_any = 0;
+            PP_FOR_T(t)
+            {
+                volatile uint16_t *mine = sm.res + (uint32_t)t * kTileB;
+                int pend = 0;
+#pragma unroll
+                for (int j = 0; j < kTileB; j++) {
+                    const uint32_t x = mine[j];
+                    if (!(x & 0x8000u)) {
+                        const uint32_t y = ((volatile uint16_t *)sm.res)[x];
+                        mine[j] = (uint16_t)y;
+                        if (!(y & 0x8000u)) pend = 1;
+                    }
+                }
+                pend_any |= pend;
+            }
+            PP_END_T
+            pend_any = PP_SYNC_OR(pend_any);
+        }
+        // (3) the tile leaves; '\n' and NUL are counted on the way
+        PP_FOR_T(t)
+        {
+            const uint32_t v0 = tb + (uint32_t)t * kTileB;
+            if (v0 < vend && v0 + kTileB > a) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(sm.res + (uint32_t)t * kTileB);
+                uint32_t b[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t p = src[2 * j], q = src[2 * j + 1];
+                    b[j] = (p & 0xffu) | ((p >> 8) & 0xff00u) | ((q & 0xffu) << 16) | ((q << 8) & 0xff000000u);
+                }
+                if (v0 >= a && v0 + kTileB <= vend) {
+                    uint4 w4;
+                    w4.x = b[0]; w4.y = b[1]; w4.z = b[2]; w4.w = b[3];
+                    *reinterpret_cast<uint4 *>(vbase + v0) = w4;
+                    sm.nl[t] += popc32(eq_bytes(b[0], 0x0a0a0a0au)) + popc32(eq_bytes(b[1], 0x0a0a0a0au)) +
+                                popc32(eq_bytes(b[2], 0x0a0a0a0au)) + popc32(eq_bytes(b[3], 0x0a0a0a0au));
+                    sm.nul[t] |= eq_bytes(b[0], 0u) | eq_bytes(b[1], 0u) | eq_bytes(b[2], 0u) | eq_bytes(b[3], 0u);
+                } else {
+                    for (int j = 0; j < kTileB; j++) {
+                        const uint32_t v = v0 + (uint32_t)j;
+                        if (v >= a && v < vend) {
+                            const uint32_t c = (b[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+                            vbase[v] = (uint8_t)c;
+                            sm.nl[t] += (c == 10u);
+                            sm.nul[t] |= (c == 0u);
+                        }
+                    }
+                }
+            }
+        }
+        PP_END_T
+        PP_SYNC();  // stores visible to the next tile's gathers; res free again
     }
 }
 
-// Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
-PP_DEV void inflate_chunk(const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                          const uint8_t *lead_src, ChunkResult &res)
+// One window of a Huffman block: GUESS, SYNC, SCAN, EMIT, RESOLVE.
+// s0: window-relative bit of the first symbol; room: output bytes still wanted (> 0).
+PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32_t mapcap, uint8_t *outp, uint32_t room)
 {
+    const int T = PP_NT;
+    // GUESS
+    PP_FOR_T(t)
+    {
+        const uint32_t st = s0 + (uint32_t)t * kSubBits;
+        const Seg r = decode_seg<0>(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, nullptr, 0, 0);
+        sm.start[t] = st;
+        sm.end[t] = r.end;
+        sm.outc[t] = r.out;
+        sm.flag[t] = r.flag;
+    }
+    PP_END_T
+    PP_SYNC();
+    // SYNC: u[8] = first thread whose start is not its predecessor's end, u[9] = first flagged thread
+    uint32_t rounds = 0;
+    for (;;) {
+        PP_T0_BEGIN
+        sm.u[8] = (uint32_t)T;
+        sm.u[9] = (uint32_t)T;
+        PP_T0_END
+        PP_SYNC();
+        PP_FOR_T(t)
+        if (t > 0 && sm.start[t] != sm.end[t - 1]) PP_ATOMIC_MIN(&sm.u[8], (uint32_t)t);
+        if (sm.flag[t] != F_NONE) PP_ATOMIC_MIN(&sm.u[9], (uint32_t)t);
+        PP_END_T
+        PP_SYNC();
+        const uint32_t m = sm.u[8], f = sm.u[9];
+        if (m == (uint32_t)T || f < m) break;
+        rounds++;
+        // every thread from the first mismatch on restarts where its predecessor ended
+        PP_FOR_T(t)
+        sm.ns[t] = t ? sm.end[t - 1] : sm.start[0];
+        PP_END_T
+        PP_SYNC();
+        PP_FOR_T(t)
+        {
+            const uint32_t ns = sm.ns[t];
+            if ((uint32_t)t >= m && ns != sm.start[t]) {
+                const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
+                Seg r;
+                if (ns >= lim) { r.end = ns; r.out = 0; r.flag = F_NONE; }
+                else r = decode_seg<0>(sm, ns, lim, nullptr, 0, 0);
+                sm.start[t] = ns;
+                sm.end[t] = r.end;
+                sm.outc[t] = r.out;
+                sm.flag[t] = r.flag;
+            }
+        }
+        PP_END_T
+        PP_SYNC();
+    }
+    const uint32_t f = sm.u[9];
+    PP_SYNC();
+    // SCAN: threads past the first flagged one produce nothing
+    PP_FOR_T(t)
+    if ((uint32_t)t > f) sm.outc[t] = 0;
+    PP_END_T
+    PP_SYNC();
+    // outc -> exclusive sums; keep each thread's own count in nl-free scratch: recomputed from neighbours below
+    uint32_t total = block_excl_scan(sm, sm.outc);
+    // live threads: up to the flagged one, cut where the source map or the output is full
+    const uint32_t a = (uint32_t)((uintptr_t)outp & 15u);
+    const uint32_t capv = mapcap - 16u - a;  // entries usable by this window
+    PP_T0_BEGIN
+    sm.u[10] = f < (uint32_t)T ? f + 1u : (uint32_t)T;  // nlive
+    PP_T0_END
+    PP_SYNC();
+    PP_FOR_T(t)
+    {
+        const uint32_t endsum = (t + 1 < T) ? sm.outc[t + 1] : total;  // inclusive sum of thread t
+        // the first thread whose output crosses the map capacity is cut (never thread 0: kMinMapCap)
+        if (t > 0 && (uint32_t)t <= f && endsum > capv) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t);
+        // the first thread that completes the wanted output is the last live one
+        if ((uint32_t)t <= f && endsum >= room) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t + 1u);
+    }
+    PP_END_T
+    PP_SYNC();
+    const uint32_t nlive = sm.u[10];
+    uint32_t produced = nlive < (uint32_t)T ? sm.outc[nlive] : total;
+    const uint32_t next_bit = sm.end[nlive - 1u];
+    uint32_t flag = (f < (uint32_t)T && nlive == f + 1u) ? sm.flag[f] : (uint32_t)F_NONE;
+    if (produced >= room) {
+        // Core.cs:187: the loop ends as soon as the wanted bytes are there (zlib stops mid-block)
+        produced = room;
+        if (flag == F_BAD) flag = F_NONE;
+    }
+    PP_SYNC();
+    // EMIT
+    PP_FOR_T(t)
+    if ((uint32_t)t < nlive) {
+        const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
+        const uint32_t st = sm.start[t];
+        if (st < lim) decode_seg<1>(sm, st, lim, map, a + sm.outc[t], a + produced);
+    }
+    PP_END_T
+    PP_SYNC();
+    // RESOLVE
+    resolve_window(sm, map, outp, a, produced);
+    WindowOut w;
+    w.next_bit = next_bit;
+    w.produced = produced;
+    w.flag = flag;
+    w.rounds = rounds;
+    return w;
+}
+
+// Stored block body: `n` bytes straight from the compressed buffer to the output.
+PP_DEV void stored_copy(const Sm &sm, const uint8_t *src, uint8_t *dst, uint32_t n)
+{
+    const int T = PP_NT;
+    PP_FOR_T(t)
+    {
+        uint32_t nl = 0, nul = 0;
+        for (uint32_t j = (uint32_t)t; j < n; j += (uint32_t)T) {
+            const uint32_t c = src[j];
+            dst[j] = (uint8_t)c;
+            nl += (c == 10u);
+            nul |= (c == 0u);
+        }
+        sm.nl[t] += nl;
+        sm.nul[t] |= nul;
+    }
+    PP_END_T
+    PP_SYNC();
+}
+
+// Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
+// map: this CTA's source-map scratch (global memory, map_cap_for(T) entries, 16 B aligned).
+PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
+                          const uint8_t *lead_src, uint16_t *map, ChunkResult &res, uint32_t &stage_phase)
+{
+    const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
     // 1. history: copy the checkpoint window (Core.cs:158 inflateSetDictionary) in front of the output
     {
         const uint4 *s4 = reinterpret_cast<const uint4 *>(lead_src + d.lead_src);
         uint4 *d4 = reinterpret_cast<uint4 *>(slot);
         const uint32_t n4 = d.lead_len / 16u;
-        PP_LANES_BEGIN
-        for (uint32_t i = (uint32_t)lane; i < n4; i += 32u) d4[i] = s4[i];
-        PP_LANES_END
+        PP_FOR_T(t)
+        for (uint32_t i = (uint32_t)t; i < n4; i += (uint32_t)T) d4[i] = s4[i];
+        sm.nl[t] = 0;
+        sm.nul[t] = 0;
+        PP_END_T
     }
-    Out o;
-    o.base = slot + d.lead_len;
-    o.len = d.out_len;
-    o.abase = 0;
-    o.bpos = 0;
-    o.carry = 0;
-    o.rstart = 0;
-    o.nrounds = 0;
-    PP_LANES_BEGIN
-    PP_L(o.nl) = 0;
-    PP_L(o.nul) = 0;
-    PP_LANES_END
-
-    Reader r;
-    r.comp = comp;
-    r.comp_tiles = comp_bytes / kTileBytes;
-    r.s_cur = 0;
-    r.s_issued = 0;
-    r.tile_bias = 0;
-    r.exhausted = 0;
+    PP_SYNC();
+    uint8_t *out = slot + d.lead_len;
+    const uint32_t out_len = d.out_len;
+    const uint32_t mapcap = map_cap_for(T);
+    const uint32_t cww = cw_words_for(T);
     // 2. bit cursor: 8*Input - Bits (Core.cs:151-157 inflatePrime semantics)
-    rd_seek(r, d.in_bit, true);
-
+    uint64_t bit = d.in_bit;
+    uint32_t produced = 0;
     int status = 0;
-    while (out_pos(o) < o.len) {
-        if (r.exhausted || (rd_bitpos(r) >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174
-        const uint32_t hdr = r.lo & 7u;
-        rd_consume(r, 3);
-        rd_refill(r);
-        const uint32_t last = hdr & 1u, type = hdr >> 1;
-        int rc;
-        if (type == 0u) {
-            rc = stored_block(r, o);
-        } else if (type == 1u || type == 2u) {
-            rc = type == 1u ? fixed_tables() : dynamic_tables(r);
-            if (rc == 0) rc = huffman_block(r, o);
-            if (rc == 1) rc = 0;
-        } else {
-            rc = -3;  // invalid block type
+    bool need_header = true, last = false;
+    while (produced < out_len) {
+        if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
+        const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
+        if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
+        uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
+        if (need_header) {
+            const uint32_t hdr = peek_bits(sm.cw, s0, 3);
+            s0 += 3;
+            last = (hdr & 1u) != 0;
+            const uint32_t type = hdr >> 1;
+            if (type == 0u) {
+                // stored: skip to the byte boundary, LEN / NLEN, then raw bytes
+                const uint32_t bp = (s0 + 7u) & ~7u;
+                const uint32_t len = peek_bits(sm.cw, bp, 16), nlen = peek_bits(sm.cw, bp + 16u, 16);
+                if ((len ^ 0xffffu) != nlen) { status = -3; break; }  // invalid stored block lengths
+                const uint64_t byte0 = base_byte + (bp >> 3) + 4u;
+                if (byte0 + len > comp_bytes || byte0 + len > d.in_limit) { status = -3; break; }
+                uint32_t n = len;
+                if (n > out_len - produced) n = out_len - produced;
+                PP_SYNC();
+                stored_copy(sm, comp + byte0, out + produced, n);
+                produced += n;
+                bit = (byte0 + len) * 8u;
+                if (last) break;  // Z_STREAM_END (Core.cs:185)
+                continue;
+            }
+            int rc;
+            if (type == 1u) rc = fixed_tables(sm);
+            else if (type == 2u) rc = dynamic_tables(sm, s0, &s0);
+            else rc = -3;  // invalid block type
+            if (rc) { status = rc; break; }
+            need_header = false;
         }
-        if (rc < 0) { status = rc; break; }
-        if (last) break;  // Z_STREAM_END (Core.cs:185)
+        const WindowOut w = huffman_window(sm, s0, map, mapcap, out + produced, out_len - produced);
+        produced += w.produced;
+        bit = base_byte * 8u + w.next_bit;
+#ifdef PP_HOST_EMU
+        g_stat[0]++;
+        g_stat[1] += w.rounds;
+        if (w.rounds > g_stat[2]) g_stat[2] = w.rounds;
+        g_stat[3] += (w.flag == F_EOB);
+#endif
+        if (w.flag == F_BAD) { status = -3; break; }
+        if (w.flag == F_EOB) {
+            need_header = true;
+            if (last) break;  // Z_STREAM_END (Core.cs:185)
+        }
     }
-    out_resolve(o, true);
-    const uint32_t produced = o.abase;
+    PP_SYNC();
     // 3. NUL terminator / clean tail for the parse stage
     {
         const uint32_t to = ((d.lead_len + d.out_len + 1u + 127u) & ~127u) - d.lead_len;
-        PP_LANES_BEGIN
-        for (uint32_t i = produced + (uint32_t)lane; i < to; i += 32u) o.base[i] = 0;
-        PP_LANES_END
+        PP_FOR_T(t)
+        for (uint32_t i = produced + (uint32_t)t; i < to; i += (uint32_t)T) out[i] = 0;
+        PP_END_T
     }
     // 4. results
-    uint32_t nl = 0, nul = 0;
-#ifdef PP_HOST_EMU
-    for (int lane = 0; lane < 32; lane++) { nl += o.nl[lane]; nul |= o.nul[lane]; }
-#else
-    nl = o.nl;
-    nul = o.nul;
-    for (int s = 16; s > 0; s >>= 1) {
-        nl += __shfl_xor_sync(0xffffffffu, nl, s);
-        nul |= __shfl_xor_sync(0xffffffffu, nul, s);
+    PP_SYNC();
+    PP_T0_BEGIN
+    {
+        uint32_t nl = 0, nul = 0;
+        for (int t = 0; t < T; t++) { nl += sm.nl[t]; nul |= sm.nul[t]; }
+        res.status = status;
+        res.produced = produced;
+        res.newlines = nl;
+        res.min_byte = nul ? 0u : 1u;
+        res.end_bit = bit;
     }
-#endif
-    PP_LANE0_BEGIN
-    res.status = status;
-    res.produced = produced;
-    res.newlines = nl;
-    res.min_byte = nul ? 0u : 1u;
-    res.end_bit = rd_bitpos(r);
-    PP_LANE0_END
+    PP_T0_END
+    PP_SYNC();
 }
 
 }  // namespace ppinf

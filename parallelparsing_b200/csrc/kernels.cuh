@@ -39,8 +39,17 @@ struct ScanTotals {
 };
 
 // kernel launchers (each returns the cudaGetLastError() of its launch)
+// Launch geometry + scratch of the inflate kernel (owned by the device context).
+struct InflateLaunch {
+    int threads = 0;         // CTA size (multiple of 32, <= 1024)
+    int grid = 0;            // resident CTAs (SMs x CTAs per SM)
+    uint16_t *map = nullptr; // source-map scratch: grid x map_cap_for(threads) entries
+    int *counter = nullptr;  // chunk counter the CTAs pull work from
+};
+int inflate_max_ctas_per_sm(int threads);
+size_t inflate_scratch_bytes(int threads, int grid);
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                           const uint8_t *lead, ChunkResult *results, cudaStream_t st);
+                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st);
 cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
                                cudaStream_t st);
 cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,

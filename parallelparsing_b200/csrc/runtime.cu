@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -48,9 +49,38 @@ struct pp_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int sm_count = 0;
+    // inflate launch geometries: few chunks -> large CTAs (one per SM), many chunks -> more CTAs per SM
+    InflateLaunch wide, dense;
+    uint16_t *d_map = nullptr;
+    int *d_counter = nullptr;
+    const InflateLaunch &inflate_cfg(int n_chunks) const { return n_chunks <= wide.grid ? wide : dense; }
 };
 
-static constexpr uint64_t kTile = ppinf::kTileBytes;
+static int ctx_setup_inflate(pp_ctx *c)
+{
+    int t_wide = 1024, t_dense = 512;
+    if (const char *e = getenv("PPB200_INFLATE_T")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= 1024 && v % 32 == 0) t_wide = t_dense = v;
+    }
+    const int occ_w = inflate_max_ctas_per_sm(t_wide), occ_d = inflate_max_ctas_per_sm(t_dense);
+    if (occ_w <= 0 || occ_d <= 0) {
+        fprintf(stderr, "ppb200: inflate kernel does not fit an SM (threads %d/%d)\n", t_wide, t_dense);
+        return PP_E_CUDA;
+    }
+    c->wide.threads = t_wide;
+    c->wide.grid = c->sm_count * occ_w;
+    c->dense.threads = t_dense;
+    c->dense.grid = c->sm_count * occ_d;
+    const size_t bytes = std::max(inflate_scratch_bytes(t_wide, c->wide.grid), inflate_scratch_bytes(t_dense, c->dense.grid));
+    CK(cudaMalloc(&c->d_map, bytes));
+    CK(cudaMalloc(&c->d_counter, sizeof(int)));
+    c->wide.map = c->dense.map = c->d_map;
+    c->wide.counter = c->dense.counter = c->d_counter;
+    return PP_OK;
+}
+
+static constexpr uint64_t kTile = 2048;  // padding granule of the compressed buffers
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct pp_job {
@@ -148,6 +178,11 @@ int pp_open(int32_t device, pp_ctx **out)
         return PP_E_CUDA;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    rc = ctx_setup_inflate(c);
+    if (rc != PP_OK) {
+        pp_close(c);
+        return rc;
+    }
     *out = c;
     return PP_OK;
 }
@@ -160,6 +195,8 @@ void pp_close(pp_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    cudaFree(ctx->d_map);
+    cudaFree(ctx->d_counter);
     delete ctx;
 }
 
@@ -455,9 +492,10 @@ int pp_job_execute(pp_job *j)
         lead = (const uint8_t *)dp;
         comp_bytes = align_up(j->comp_copy, kTile) + kTile;  // pp_host_alloc keeps spare tiles behind the data
     }
-    if (launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, st) != cudaSuccess)
+    if (launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
+                       st) != cudaSuccess)
         return PP_E_CUDA;
-    launches += j->n > 0 ? 1 : 0;
+    launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)
     CK(cudaEventRecord(j->ev[3], st));
     int rc = job_parse_stage(j, st, false, &launches);
     if (rc != PP_OK) return rc;
@@ -658,7 +696,7 @@ int64_t pp_extract(pp_ctx *ctx, const uint8_t *fileBuffer, int64_t fileBufferLen
     CK(cudaMemcpyAsync(lead.p, ix->window(from_point), PP_WINSIZE, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(desc.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
     if (launch_inflate(desc.as<ChunkDesc>(), 1, comp.as<uint8_t>(), comp_alloc, slot.as<uint8_t>(), lead.as<uint8_t>(),
-                       res.as<ChunkResult>(), st) != cudaSuccess)
+                       res.as<ChunkResult>(), ctx->inflate_cfg(1), st) != cudaSuccess)
         return PP_E_CUDA;
     ChunkResult r{};
     CK(cudaMemcpyAsync(&r, res.p, sizeof r, cudaMemcpyDeviceToHost, st));

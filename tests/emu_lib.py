@@ -1,0 +1,53 @@
+"""TEST SCAFFOLDING: builds and drives the host emulation of the inflate kernel
+(tests/emu/emu_inflate.cpp compiles parallelparsing_b200/csrc/inflate_core.cuh with
+PP_HOST_EMU).  Used by the CPU tests to check the decoder logic against zlib; never
+used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "emu_inflate.cpp")
+CORE = os.path.join(ROOT, "parallelparsing_b200", "csrc", "inflate_core.cuh")
+OUT = os.path.join(ROOT, "tests", "emu", "_build")
+
+_libs = {}
+
+
+def lib(subw=31):
+    if subw in _libs:
+        return _libs[subw]
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, f"emu_inflate_w{subw}.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-w", f"-DPP_SUBW={subw}", "-o", so, SRC])
+    L = C.CDLL(so)
+    L.emu_inflate_chunk.restype = C.c_int
+    L.emu_inflate_chunk.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.emu_stats.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    _libs[subw] = L
+    return L
+
+
+def inflate_chunk(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window: np.ndarray, out_len: int,
+                  T=64, subw=31):
+    """Emulated Core.ExtractDeflateIndex: the stream starts `bits` bits before byte `in_byte`
+    of gz; returns (status, bytes produced, newlines, min_byte, end_bit)."""
+    L = lib(subw)
+    pad = (-gz.size) % 16
+    comp = np.concatenate([gz, np.zeros(pad + 64, np.uint8)])
+    lead_len = window.size
+    slot = np.zeros(lead_len + out_len + 256, np.uint8)
+    res = (C.c_uint64 * 4)()
+    st = L.emu_inflate_chunk(T, comp.ctypes.data, comp.size - 64 + 0, in_byte * 8 - bits, in_limit,
+                             slot.ctypes.data, window.ctypes.data, lead_len, out_len, res)
+    return st, slot[lead_len: lead_len + int(res[0])], int(res[1]), int(res[2]), int(res[3])
+
+
+def stats(subw=31, reset=True):
+    out = (C.c_uint64 * 8)()
+    lib(subw).emu_stats(out, int(reset))
+    return dict(windows=int(out[0]), rounds=int(out[1]), max_rounds=int(out[2]), blocks=int(out[3]))
