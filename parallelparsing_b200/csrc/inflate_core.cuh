@@ -661,7 +661,11 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *ma
                 } else {
                     // overlapping run: byte j repeats the `dist` bytes before the match, so its
                     // source is dist*(j/dist+1) back — always in front of the match itself
-                    for (uint32_t j = 0; j < n; j++) map[p0 + j] = (uint16_t)(dist * (j / dist + 1u) - 1u);
+                    uint32_t v = dist - 1u, r = 0;
+                    for (uint32_t j = 0; j < n; j++) {
+                        map[p0 + j] = (uint16_t)v;
+                        if (++r == dist) { r = 0; v += dist; }
+                    }
                 }
             }
             out += len;
@@ -693,6 +697,13 @@ struct WindowOut {
 // ---- RESOLVE ------------------------------------------------------------------------
 // Source map -> bytes for window output [0, total) that lands at outp[0..total).
 // `a` = misalignment of outp (outp - a is 16-byte aligned); map entry of byte q is map[q + a].
+// Per tile: (1) every thread classifies its 16 bytes — literal, source in front of the tile
+// (gathered from global memory, all loads independent), or source inside the tile (the
+// tile-relative index of that byte) — and publishes them in shared memory; one barrier;
+// (2) in-tile sources are chased with no further barrier: an entry is always either the byte
+// or the index of an EARLIER byte with the same value, every hop is published, so chains
+// collapse like pointer jumping whatever the interleaving of the warps; (3) the 16 bytes
+// leave with one vector store; one barrier before the next tile gathers from them.
 PP_DEV void resolve_window(const Sm &sm, const uint16_t *map, uint8_t *outp, uint32_t a, uint32_t total)
 {
     const int T = PP_NT;
@@ -700,80 +711,67 @@ PP_DEV void resolve_window(const Sm &sm, const uint16_t *map, uint8_t *outp, uin
     const uint32_t vend = a + total;         // virtual index = q + a; valid bytes: a <= v < vend
     uint8_t *vbase = outp - a;               // 16-byte aligned; vbase[v] is the byte of virtual index v
     for (uint32_t tb = 0; tb < vend; tb += R) {
-        // (1) literals, and bytes whose source lies before the tile: independent gathers
-        int pend_any = 0;
+        const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
         PP_FOR_T(t)
         {
             const uint32_t v0 = tb + (uint32_t)t * kTileB;
-            uint16_t ent[kTileB];
             if (v0 < vend) {
                 const uint4 m0 = *reinterpret_cast<const uint4 *>(map + v0);
                 const uint4 m1 = *reinterpret_cast<const uint4 *>(map + v0 + 8);
                 const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                for (int j = 0; j < kTileB; j++) ent[j] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
-            }
-            uint32_t r[kTileB];
-            int pend = 0;
-#pragma unroll
-            for (int j = 0; j < kTileB; j++) {
-                const uint32_t v = v0 + (uint32_t)j;
-                uint32_t x = 0x8000u;  // bytes outside [a, vend) are never stored
-                if (v >= a && v < vend) {
-                    const uint32_t e = ent[j];
-                    if (e & 0x8000u) {
-                        x = e;
-                    } else {
-                        const int64_t sv = (int64_t)v - (int64_t)e - 1;  // virtual index of the source
-                        if (sv < (int64_t)tb || sv < (int64_t)a) {  // before the tile, or before the window
-                            x = 0x8000u | (uint32_t)vbase[sv];
-                        } else {
-                            x = (uint32_t)(sv - (int64_t)tb);
-                            pend = 1;
-                        }
-                    }
-                }
-                r[j] = x;
-            }
-            uint32_t *dst = reinterpret_cast<uint32_t *>(sm.res + (uint32_t)t * kTileB);
-#pragma unroll
-            for (int j = 0; j < kTileB / 2; j++) dst[j] = r[2 * j] | (r[2 * j + 1] << 16);
-            pend_any |= pend;
-        }
-        PP_END_T
-        pend_any = PP_SYNC_OR(pend_any);
-        // (2) sources inside the tile: pointer jumping (every entry is either the byte or the
-        //     index of an earlier byte with the same value; both stay true under any interleaving)
-        while (pend_any) {
-            pend_any = 0;
-            PP_FOR_T(t)
-            {
-                volatile uint16_t *mine = sm.res + (uint32_t)t * kTileB;
-                int pend = 0;
+                uint32_t r[kTileB];
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
-                    const uint32_t x = mine[j];
-                    if (!(x & 0x8000u)) {
-                        const uint32_t y = ((volatile uint16_t *)sm.res)[x];
-                        mine[j] = (uint16_t)y;
-                        if (!(y & 0x8000u)) pend = 1;
+                    const uint32_t v = v0 + (uint32_t)j;
+                    const uint32_t e = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                    const int32_t sv = (int32_t)v - (int32_t)e - 1;  // virtual index of the source
+                    uint32_t x = e;
+                    if (v - a >= total) x = 0x8000u;  // not part of this window: never stored, never a source
+                    else if (!(e & 0x8000u)) {
+                        if (sv < near_lo) x = 0x8000u | (uint32_t)vbase[sv];
+                        else x = (uint32_t)sv - tb;
                     }
+                    r[j] = x;
                 }
-                pend_any |= pend;
+                uint4 q0, q1;
+                q0.x = r[0] | (r[1] << 16); q0.y = r[2] | (r[3] << 16); q0.z = r[4] | (r[5] << 16); q0.w = r[6] | (r[7] << 16);
+                q1.x = r[8] | (r[9] << 16); q1.y = r[10] | (r[11] << 16); q1.z = r[12] | (r[13] << 16); q1.w = r[14] | (r[15] << 16);
+                uint4 *dst = reinterpret_cast<uint4 *>(sm.res + (uint32_t)t * kTileB);
+                dst[0] = q0;
+                dst[1] = q1;
             }
-            PP_END_T
-            pend_any = PP_SYNC_OR(pend_any);
         }
-        // (3) the tile leaves; '\n' and NUL are counted on the way
+        PP_END_T
+        PP_SYNC();
         PP_FOR_T(t)
         {
             const uint32_t v0 = tb + (uint32_t)t * kTileB;
             if (v0 < vend && v0 + kTileB > a) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(sm.res + (uint32_t)t * kTileB);
+                volatile uint16_t *res = sm.res;
+                const uint4 *own = reinterpret_cast<const uint4 *>(sm.res + (uint32_t)t * kTileB);
+                const uint4 q0 = own[0], q1 = own[1];
+                uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                // (2) chase in-tile sources
+                uint32_t pend = ~(w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) & 0x80008000u;
+                while (pend) {
+                    pend = 0;
+#pragma unroll
+                    for (int j = 0; j < kTileB; j++) {
+                        const uint32_t sh = (uint32_t)(j & 1) * 16u;
+                        const uint32_t x = (w[j >> 1] >> sh) & 0xffffu;
+                        if (!(x & 0x8000u)) {
+                            const uint32_t y = res[x];
+                            res[(uint32_t)t * kTileB + (uint32_t)j] = (uint16_t)y;
+                            w[j >> 1] = (w[j >> 1] & ~(0xffffu << sh)) | (y << sh);
+                            if (!(y & 0x8000u)) pend = 1;
+                        }
+                    }
+                }
+                // (3) the bytes leave; '\n' and NUL are counted on the way
                 uint32_t b[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t p = src[2 * j], q = src[2 * j + 1];
+                    const uint32_t p = w[2 * j], q = w[2 * j + 1];
                     b[j] = (p & 0xffu) | ((p >> 8) & 0xff00u) | ((q & 0xffu) << 16) | ((q << 8) & 0xff000000u);
                 }
                 if (v0 >= a && v0 + kTileB <= vend) {
