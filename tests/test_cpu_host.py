@@ -1,0 +1,200 @@
+"""CPU tests (no GPU) of the product's HOST side: the C ABI exports what include/ppb200.h
+declares, CreateIndex / IndexIO of libppb200.so are byte-compatible with the oracle's
+restatement of the reference, the decode entry points fail loudly without a device (there is
+no CPU fallback), and the multi-GPU chunk partitioning works under torch.distributed/gloo."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import corpus
+import oracle_lib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+G = json.load(open(os.path.join(GOLD, "golden.json")))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_abi_exports_every_declared_symbol():
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ppb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], check=True, stdout=subprocess.PIPE, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = declared - exported
+    assert not missing, f"declared in ppb200.h but not exported: {sorted(missing)}"
+    assert {n for n, _, _ in _lib.SYMBOLS} == declared  # the ctypes binding covers the whole header
+    L = pp.lib()
+    assert L.pp_abi_version() == 1
+    assert b"data error" in L.pp_strerror(-3).lower() or L.pp_strerror(-3)
+
+
+def _assert_same_index(ix, ox):
+    assert ix.Count == ox.count
+    assert ix.ChunkMaxBytes == ox.chunk_max_bytes
+    for i in range(ox.count):
+        a, b = ix[i], ox.point(i)
+        assert (a.Output, a.Input, a.Bits) == (b["output"], b["input"], b["bits"]), i
+        assert np.array_equal(a.Window, b["window"]), i
+        assert np.array_equal(a.offset, b["offset"]), i
+
+
+@pytest.mark.parametrize("kind", ["zlib6", "zlib1", "gzip_native", "ppgzip", "syncflush"])
+def test_create_index_matches_oracle(kind):
+    """Core.BuildDeflateIndex (Core.cs:14-131) of the product library vs the oracle: same points."""
+    import parallelparsing_b200 as pp
+    if kind == "gzip_native":
+        gz, cs = corpus.gz_system(corpus.fastq(5000), 6), 1000
+    elif kind == "ppgzip":
+        gz, cs = corpus.gz_parallel(corpus.fastq(20000, fixed=150), 6, segment=1 << 20), 1000
+    elif kind == "syncflush":
+        gz, cs = corpus.gz_member(corpus.fastq(3000, fixed=150), 6, flush_every=50000), 100
+    else:
+        gz, cs = corpus.gz_member(corpus.fastq(8000, fixed=150), int(kind[-1])), 1000
+    _assert_same_index(pp.Core.BuildDeflateIndex(gz, cs), O.OracleIndex.build(gz, cs))
+
+
+def test_index_io_golden_bytes(tmp_path):
+    """IndexIO.Deserialize/Serialize (Common/IndexIO.cs:7-53) on the golden file."""
+    import parallelparsing_b200 as pp
+    src = os.path.join(GOLD, "gen600.chunk50.gzi")
+    ix = pp.IndexIO.Deserialize(src)
+    assert ix.Count == G["index"]["points"]
+    out = str(tmp_path / "o.gzi")
+    pp.IndexIO.Serialize(ix, out)
+    ref, got = open(src, "rb").read(), open(out, "rb").read()
+    assert got[:4] == ref[:4] and got[8:] == ref[8:]  # ChunkMaxBytes is lost by Deserialize (quirk H7)
+    # a freshly built index serialises to exactly the golden bytes
+    gz = np.fromfile(os.path.join(GOLD, "gen600.fastq.gz"), np.uint8)
+    pp.IndexIO.Serialize(pp.Core.BuildDeflateIndex(gz, G["index"]["chunksize"]), out)
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == G["index"]["gzi_md5"]
+    # and the oracle reads what the product wrote
+    _assert_same_index(pp.IndexIO.Deserialize(out), O.OracleIndex.deserialize(out))
+
+
+def test_index_errors():
+    import parallelparsing_b200 as pp
+    gz = corpus.gz_member(corpus.fastq(12, fixed=20000), 6)
+    with pytest.raises(pp.ZException) as e:
+        pp.Core.BuildDeflateIndex(gz, 2)  # Core.cs:93 IndexOutOfRangeException (quirk H2)
+    assert e.value.Code == -104
+    assert pp.Core.BuildDeflateIndex(gz, 2, lift_record_cap=True).Count >= 2
+    with pytest.raises(pp.ZException) as e:
+        pp.Core.BuildDeflateIndex(np.frombuffer(b"not a gzip file at all, definitely", np.uint8), 100)
+    assert e.value.Code == -3  # Z_DATA_ERROR (Core.cs:74)
+    with pytest.raises(pp.ZException):
+        pp.IndexIO.Deserialize("/nonexistent/index.gzi")
+
+
+def test_add_point_unrotates_window():
+    """Index.AddPoint (Common/Index.cs:24-48): the circular 32 KB window is stored in stream order."""
+    import parallelparsing_b200 as pp
+    w = (np.arange(32768) % 251).astype(np.uint8)
+    ix = pp.Index()
+    left = 1000
+    ix.AddPoint(3, 50, 70000, left, w, np.frombuffer(b"@abc", np.uint8))
+    p = ix[0]
+    assert np.array_equal(p.Window, np.concatenate([w[32768 - left:], w[:32768 - left]]))
+    assert (p.Bits, p.Input, p.Output, bytes(p.offset)) == (3, 50, 70000, b"@abc")
+    assert ix.ChunkMaxBytes == 70000
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-device behaviour")
+def test_decode_fails_loudly_without_a_device():
+    import parallelparsing_b200 as pp
+    with pytest.raises(pp.ZException) as e:
+        pp.Device(0)
+    assert e.value.Code == -101  # PP_E_NO_DEVICE: no CPU fallback
+    gz = np.fromfile(os.path.join(GOLD, "gen600.fastq.gz"), np.uint8)
+    with pytest.raises(pp.ZException):
+        pp.BatchedFASTQ(pp.IndexIO.Deserialize(os.path.join(GOLD, "gen600.chunk50.gzi")), gz).Count()
+
+
+def test_product_never_references_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "parallelparsing_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle_lib" not in txt and "pporacle" not in txt and "ora_" not in txt, f
+
+
+def test_partition_chunks_properties():
+    from parallelparsing_b200.shard import partition_chunks, record_bases
+    rng = np.random.default_rng(0)
+    for n_pts in (1, 2, 3, 9, 99, 1000):
+        inputs = np.cumsum(rng.integers(1000, 2_000_000, n_pts)) + 10
+        for world in (1, 2, 3, 4, 8):
+            parts = partition_chunks(inputs, world)
+            assert len(parts) == world
+            nxt = 0
+            for f, n in parts:
+                assert f == nxt and n >= 0
+                nxt = f + n
+            assert nxt == max(n_pts - 1, 0)
+            if n_pts - 1 >= 8 * world:
+                sizes = [int(inputs[f + n] - inputs[f]) for f, n in parts]
+                assert max(sizes) - min(sizes) <= 2 * int(np.diff(inputs).max())
+    assert list(record_bases([5, 0, 7])) == [0, 5, 5]
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200.shard import partition_chunks, record_bases
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gz = np.fromfile(os.path.join(GOLD, "gen600.fastq.gz"), np.uint8)
+    ix = pp.IndexIO.Deserialize(os.path.join(GOLD, "gen600.chunk50.gzi"))
+    first, n = partition_chunks(ix.scalars()[1], world)[rank]
+    # the per-rank decode is the GPU job on a B200; here (no device) the oracle stands in as the checker
+    ox = O.OracleIndex.deserialize(os.path.join(GOLD, "gen600.chunk50.gzi"))
+    recs, nbytes = O.decompress_all_mt(gz, ox, first, n, threads=1) if n else (0, 0)
+    t = torch.tensor([recs, nbytes, n], dtype=torch.int64)
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    counts = [int(g[0]) for g in gathered]
+    q.put((rank, first, n, counts, int(record_bases(counts)[rank]), sum(int(g[1]) for g in gathered),
+           sum(int(g[2]) for g in gathered)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_over_gloo():
+    """world_size 2 on CPU: contiguous chunk ranges, no data-path collective; only the per-rank
+    record counts are exchanged to number the records globally."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, f0, n0, c0, b0, tb0, tn0), (r1, f1, n1, c1, b1, tb1, tn1) = res
+    assert f0 == 0 and f1 == n0 and n0 + n1 == len(G["chunks"]) == tn0
+    assert c0 == c1 and sum(c0) == G["total_records"] and tb0 == G["index"]["end_output"]
+    assert b0 == 0 and b1 == c0[0]
+    assert c0[0] == sum(c["records"] for c in G["chunks"][:n0])
