@@ -53,9 +53,13 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
 cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
                                cudaStream_t st);
 cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,
-                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ScanTotals *totals, cudaStream_t st);
-cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines, int64_t line_stride,
-                         ParseOut *pout, const ScanTotals *totals, cudaStream_t st);
+                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ParseOut *pout, ScanTotals *totals,
+                        cudaStream_t st);
+uint32_t parse_tile_bytes();
+cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *tile_base,
+                         uint32_t total_tiles, uint32_t max_tiles, uint32_t *lines, int64_t line_stride,
+                         ParseOut *pout, const ScanTotals *totals, unsigned long long *work, int sm_count,
+                         cudaStream_t st);
 cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
                                const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st);
 cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,

@@ -43,42 +43,63 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
     return r;
 }
 
-// One CTA per chunk streams the chunk's combined memory in 16 KB steps.
+// Tile-parallel: the combined memory of every chunk is cut into 64 KB tiles and the tiles of
+// ALL chunks form one work list, so the kernel fills the GPU whatever the chunk count.  A tile
+// needs the number of '\n' before it inside its chunk: tiles are handed out by a global ticket
+// counter and chained with a decoupled look-back (each tile publishes its own count, then the
+// inclusive prefix; warp 0 sums its predecessors' counts, 32 at a time, until it meets a
+// prefix).  Tickets go round-robin over the chunks (tile r of every chunk, then tile r+1 ...),
+// so the predecessor of a running tile has normally finished long ago and the look-back is one
+// step.  One pass over the bytes, no second read.
 // lines: four arrays of `stride` u32 each (line 0..3), record r of the chunk at rec_base + r.
-__global__ void __launch_bounds__(kParseThreads) pp_parse_kernel(const uint8_t *__restrict__ slots,
-                                                                 const ParseDesc *__restrict__ pdesc, int n,
-                                                                 uint32_t *__restrict__ lines, int64_t stride,
-                                                                 ParseOut *__restrict__ pout,
-                                                                 const ScanTotals *__restrict__ totals)
-{
-    __shared__ uint32_t warp_tot[2][kParseWarps];
-    __shared__ uint32_t s_flags;
-    const int k = (int)blockIdx.x;
-    if (k >= n || totals->overflow) return;
-    const ParseDesc d = pdesc[k];
-    if (d.exact) return;  // handled by pp_exact_emit_kernel
-    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
-    if (threadIdx.x == 0) s_flags = 0;
+constexpr int kTileIters = 4;                               // 16 KB steps per tile
+constexpr int kTileBytesP = kIterBytes * kTileIters;        // 64 KB
+#define kFlagAgg (1ull << 32)
+#define kFlagPrefix (2ull << 32)
 
+__device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc, int n,
+                                              const uint32_t *__restrict__ tile_base, uint32_t tk, int order,
+                                              uint32_t *__restrict__ lines, int64_t stride, ParseOut *__restrict__ pout,
+                                              unsigned long long *tile_state, uint32_t (*warp_tot)[kParseWarps],
+                                              uint32_t *s_before_p, int lane, int warp)
+{
+    int k;
+    uint32_t ti;
+    if (order) {
+        k = (int)(tk % (uint32_t)n);
+        ti = tk / (uint32_t)n;
+        if (ti >= tile_base[k + 1] - tile_base[k]) return false;
+    } else {
+        int lo = 0, hi = n - 1;  // last chunk whose tile_base <= tk
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_base[mid] <= tk) lo = mid; else hi = mid - 1;
+        }
+        k = lo;
+        ti = tk - tile_base[k];
+    }
+    const ParseDesc d = pdesc[k];
+    if (d.exact) return false;  // handled by pp_exact_emit_kernel
     const uint8_t *data = slots + d.data_off;
     const uint32_t total = d.total;
     const uint32_t head = (uint32_t)((uintptr_t)data & 15u);  // bytes before `data` in its first vector
     const uint4 *vec0 = reinterpret_cast<const uint4 *>(data - head);
     const uint32_t span = head + total;                       // bytes from vec0 to the end
+    const uint32_t t0 = ti * (uint32_t)kTileBytesP;
+    if (t0 >= span) return false;  // the chunk produced less than planned: nothing here, nothing after
+    const uint32_t tile = tile_base[k] + ti;                  // slot of this tile in tile_state
     const uint32_t rec_total = d.rec_count + d.skip;          // records in the chunk before skipping
     uint32_t *const l_base = lines + d.rec_base;
+    if (threadIdx.x == 0 && ti == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
 
-    if (threadIdx.x == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
-    uint32_t run = 0;      // newlines before this iteration
-    uint32_t flags = 0;
-    uint32_t end_pos = 0;  // written by the thread that sees newline 4R-1
-
-    for (uint32_t it0 = 0; it0 < span; it0 += kIterBytes) {
-        const uint32_t wbase = it0 + (uint32_t)warp * kWarpBytes;  // byte offset (from vec0) of this warp's block
-        uint32_t m[kRows];
+    // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
+    uint32_t m[kTileIters][kRows];
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
-            const uint32_t off = wbase + (uint32_t)r * 512u + (uint32_t)lane * 16u;
+            const uint32_t off = t0 + (uint32_t)it * kIterBytes + (uint32_t)warp * kWarpBytes + (uint32_t)r * 512u +
+                                 (uint32_t)lane * 16u;
             uint32_t mask = 0;
             if (off < span) {
                 const uint4 v = ld_stream(vec0 + (off >> 4));
@@ -88,12 +109,92 @@ __global__ void __launch_bounds__(kParseThreads) pp_parse_kernel(const uint8_t *
                 if (off < head) mask &= 0xffffu << (head - off);
                 if (off + 16u > span) mask &= 0xffffu >> (off + 16u - span);
             }
-            m[r] = mask;
+            m[it][r] = mask;
         }
+    }
+    // 2. per-row counts, packed two per register, inclusive warp scans
+    uint32_t c01[kTileIters], c23[kTileIters], s01[kTileIters], s23[kTileIters];
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        c01[it] = __popc(m[it][0]) | (__popc(m[it][1]) << 16);
+        c23[it] = __popc(m[it][2]) | (__popc(m[it][3]) << 16);
+        s01[it] = c01[it];
+        s23[it] = c23[it];
+    }
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+#pragma unroll
+        for (int it = 0; it < kTileIters; it++) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, s01[it], sft), b = __shfl_up_sync(0xffffffffu, s23[it], sft);
+            if (lane >= sft) { s01[it] += a; s23[it] += b; }
+        }
+    }
+    uint32_t t01[kTileIters], t23[kTileIters];
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        t01[it] = __shfl_sync(0xffffffffu, s01[it], 31);
+        t23[it] = __shfl_sync(0xffffffffu, s23[it], 31);
+        if (lane == 0) warp_tot[it][warp] = (t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16);
+    }
+    __syncthreads();
+    uint32_t before[kTileIters], all = 0;
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        before[it] = all;
+#pragma unroll
+        for (int w = 0; w < kParseWarps; w++) {
+            const uint32_t t = warp_tot[it][w];
+            if (w < warp) before[it] += t;
+            all += t;
+        }
+    }
+    // 3. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
+    if (warp == 0) {
+        volatile unsigned long long *st = tile_state;
+        uint32_t excl = 0;
+        if (ti == 0) {
+            if (lane == 0) st[tile] = kFlagPrefix | all;
+        } else {
+            if (lane == 0) st[tile] = kFlagAgg | all;
+            const int64_t first = (int64_t)tile_base[k];
+            int64_t j = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t idx = j - lane;
+                unsigned long long v;
+                uint32_t ready, pfx;
+                do {
+                    v = idx >= first ? st[idx] : kFlagPrefix;  // before the chunk: prefix 0
+                    ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
+                    pfx = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+                    // lanes 0..p are needed, p = nearest tile holding a prefix (all 32 if none)
+                } while ((ready | ~(pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu)) != 0xffffffffu);
+                const uint32_t need = pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu;
+                uint32_t val = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
+                excl += val;
+                if (pfx) break;
+                j -= 32;
+            }
+            if (lane == 0) st[tile] = kFlagPrefix | (unsigned long long)(excl + all);
+        }
+        if (lane == 0) {
+            *s_before_p = excl;
+            if (t0 + (uint32_t)kTileBytesP >= span) pout[k].newlines = excl + all;
+        }
+    }
+    __syncthreads();
+    const uint32_t run = *s_before_p;
+    // 4. every newline knows its ordinal: line L = ordinal + 1 starts right after it
+    uint32_t flags = 0;
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        const uint32_t wbase = t0 + (uint32_t)it * kIterBytes + (uint32_t)warp * kWarpBytes;
+        if (wbase >= span) break;
         // successor bit of every vector: is the byte right after it a newline?
         uint32_t fb = 0;
 #pragma unroll
-        for (int r = 0; r < kRows; r++) fb |= (m[r] & 1u) << r;
+        for (int r = 0; r < kRows; r++) fb |= (m[it][r] & 1u) << r;
         uint32_t nfb = __shfl_down_sync(0xffffffffu, fb, 1);
         const uint32_t fb0 = __shfl_sync(0xffffffffu, fb, 0);
         if (lane == 31) {
@@ -101,41 +202,21 @@ __global__ void __launch_bounds__(kParseThreads) pp_parse_kernel(const uint8_t *
             const uint32_t nxt = wbase + (uint32_t)kWarpBytes;  // first byte after this warp's block
             if (nxt >= head && nxt < span && data[nxt - head] == '\n') nfb |= 1u << (kRows - 1);
         }
-        // per-row counts, packed two per register, inclusive warp scan
-        uint32_t c01 = __popc(m[0]) | (__popc(m[1]) << 16), c23 = __popc(m[2]) | (__popc(m[3]) << 16);
-        uint32_t s01 = c01, s23 = c23;
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, s01, sft), b = __shfl_up_sync(0xffffffffu, s23, sft);
-            if (lane >= sft) { s01 += a; s23 += b; }
-        }
-        const uint32_t t01 = __shfl_sync(0xffffffffu, s01, 31), t23 = __shfl_sync(0xffffffffu, s23, 31);
-        const uint32_t tot0 = t01 & 0xffffu, tot1 = t01 >> 16, tot2 = t23 & 0xffffu, tot3 = t23 >> 16;
-        const uint32_t wtot = tot0 + tot1 + tot2 + tot3;
-        const int buf = (int)((it0 / kIterBytes) & 1u);
-        if (lane == 0) warp_tot[buf][warp] = wtot;
-        __syncthreads();
-        uint32_t before = run, all = 0;
-#pragma unroll
-        for (int w = 0; w < kParseWarps; w++) {
-            const uint32_t t = warp_tot[buf][w];
-            if (w < warp) before += t;
-            all += t;
-        }
-        run += all;
-        // exclusive newline ordinal of each of this lane's vectors
+        const uint32_t tot0 = t01[it] & 0xffffu, tot1 = t01[it] >> 16, tot2 = t23[it] & 0xffffu;
+        const uint32_t bef = run + before[it];
         uint32_t ex[kRows];
-        ex[0] = before + (s01 & 0xffffu) - (c01 & 0xffffu);
-        ex[1] = before + tot0 + (s01 >> 16) - (c01 >> 16);
-        ex[2] = before + tot0 + tot1 + (s23 & 0xffffu) - (c23 & 0xffffu);
-        ex[3] = before + tot0 + tot1 + tot2 + (s23 >> 16) - (c23 >> 16);
+        ex[0] = bef + (s01[it] & 0xffffu) - (c01[it] & 0xffffu);
+        ex[1] = bef + tot0 + (s01[it] >> 16) - (c01[it] >> 16);
+        ex[2] = bef + tot0 + tot1 + (s23[it] & 0xffffu) - (c23[it] & 0xffffu);
+        ex[3] = bef + tot0 + tot1 + tot2 + (s23[it] >> 16) - (c23[it] >> 16);
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
-            uint32_t mask = m[r];
+            uint32_t mask = m[it][r];
             if (mask == 0) continue;
             const uint32_t off = wbase + (uint32_t)r * 512u + (uint32_t)lane * 16u;
             // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
-            const uint32_t pairs = (mask | (((nfb >> r) & 1u) << 16)) & ((mask | (((nfb >> r) & 1u) << 16)) >> 1) & 0xffffu;
+            const uint32_t mm = mask | (((nfb >> r) & 1u) << 16);
+            const uint32_t pairs = mm & (mm >> 1) & 0xffffu;
             uint32_t ord = ex[r];
             while (mask) {
                 const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
@@ -147,20 +228,43 @@ __global__ void __launch_bounds__(kParseThreads) pp_parse_kernel(const uint8_t *
                 if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
                 if (rec >= d.skip) {
                     if (rec < rec_total) l_base[(int64_t)f * stride + (rec - d.skip)] = pos + 1u;
-                    else if (L == rec_total * 4u) end_pos = pos + 1u;
+                    else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
                 }
                 ord++;
             }
         }
     }
-    if (end_pos) pout[k].parse_end = end_pos;
-    if (flags) atomicOr(&s_flags, flags);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (rec_total == 0) pout[k].parse_end = 0;
-        pout[k].flags = s_flags;
-        pout[k].newlines = run;
-        pout[k].records = d.rec_count;
+    if (flags) atomicOr(&pout[k].flags, flags);
+return true;
+}
+
+
+// order 0: ticket = global tile number (tile_base[k] + i); order 1: ticket = i * n + k
+__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel(const uint8_t *__restrict__ slots,
+                                                                 const ParseDesc *__restrict__ pdesc, int n,
+                                                                 const uint32_t *__restrict__ tile_base,
+                                                                 uint32_t n_tickets, int order,
+                                                                 uint32_t *__restrict__ lines, int64_t stride,
+                                                                 ParseOut *__restrict__ pout,
+                                                                 const ScanTotals *__restrict__ totals,
+                                                                 unsigned long long *tile_state, uint32_t *ticket)
+{
+    __shared__ uint32_t warp_tot[kTileIters][kParseWarps];
+    __shared__ uint32_t s_ticket, s_before;
+    if (totals->overflow) return;
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    // the ticket of the NEXT tile is drawn while the current one is processed (thread 32 holds it in
+    // a register until the end of the iteration), so its round trip never sits in front of the loads
+    if (threadIdx.x == 32) s_ticket = atomicAdd(ticket, 1u);
+    for (;;) {
+        __syncthreads();  // s_ticket published; previous tile is done with the shared variables
+        const uint32_t tk = s_ticket;
+        if (tk >= n_tickets) break;
+        __syncthreads();  // everyone has read s_ticket
+        uint32_t next_ticket = 0;
+        if (threadIdx.x == 32) next_ticket = atomicAdd(ticket, 1u);
+        if (pp_parse_tile(slots, pdesc, n, tile_base, tk, order, lines, stride, pout, tile_state, warp_tot, &s_before, lane, warp)) {}
+        if (threadIdx.x == 32) s_ticket = next_ticket;
     }
 }
 
@@ -283,6 +387,7 @@ __global__ void __launch_bounds__(kScanThreads) pp_scan_kernel(const ChunkDesc *
                                                                const int64_t *__restrict__ exact_counts, int n,
                                                                uint32_t strict, int64_t capacity,
                                                                ParseDesc *__restrict__ pdesc,
+                                                               ParseOut *__restrict__ pout,
                                                                ScanTotals *__restrict__ totals)
 {
     __shared__ int64_t s_part[kScanThreads];
@@ -316,6 +421,12 @@ __global__ void __launch_bounds__(kScanThreads) pp_scan_kernel(const ChunkDesc *
         p.exact = exact;
         p.rec_base = sum;  // local to this thread's range; rebased below
         pdesc[k] = p;
+        ParseOut o;  // the parse kernels fill these in (several CTAs per chunk: start from a clean slate)
+        o.parse_end = 0;
+        o.flags = 0;
+        o.newlines = 0;
+        o.records = cnt - skip;
+        pout[k] = o;
         sum += cnt - skip;
         bytes += r.produced;
         scanned += p.total;
@@ -361,16 +472,33 @@ cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, Chu
     return cudaGetLastError();
 }
 cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,
-                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ScanTotals *totals, cudaStream_t st)
+                        uint32_t strict, int64_t capacity, ParseDesc *pdesc, ParseOut *pout, ScanTotals *totals,
+                        cudaStream_t st)
 {
-    pp_scan_kernel<<<1, kScanThreads, 0, st>>>(descs, results, exact_counts, n, strict, capacity, pdesc, totals);
+    pp_scan_kernel<<<1, kScanThreads, 0, st>>>(descs, results, exact_counts, n, strict, capacity, pdesc, pout, totals);
     return cudaGetLastError();
 }
-cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines, int64_t line_stride,
-                         ParseOut *pout, const ScanTotals *totals, cudaStream_t st)
+uint32_t parse_tile_bytes() { return (uint32_t)kTileBytesP; }
+
+// tile_base: n+1 entries (device); max_tiles: largest tile count of one chunk;
+// work: total_tiles u64 tile states followed by the u32 ticket
+cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *tile_base,
+                         uint32_t total_tiles, uint32_t max_tiles, uint32_t *lines, int64_t line_stride,
+                         ParseOut *pout, const ScanTotals *totals, unsigned long long *work, int sm_count,
+                         cudaStream_t st)
 {
-    if (n <= 0) return cudaSuccess;
-    pp_parse_kernel<<<n, kParseThreads, 0, st>>>(slots, pdesc, n, lines, line_stride, pout, totals);
+    if (n <= 0 || total_tiles == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(work, 0, ((size_t)total_tiles + 1) * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(work + total_tiles);
+    // round-robin over the chunks unless very uneven chunks would waste most tickets
+    const uint64_t rr = (uint64_t)max_tiles * (uint64_t)n;
+    const int order = rr <= 4ull * total_tiles && rr < 0xffffffffull ? 1 : 0;
+    const uint32_t n_tickets = order ? (uint32_t)rr : total_tiles;
+    const uint32_t resident = (uint32_t)sm_count * (2048u / kParseThreads);
+    const uint32_t grid = n_tickets < resident ? n_tickets : resident;
+    pp_parse_kernel<<<grid, kParseThreads, 0, st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
+                                                    pout, totals, work, ticket);
     return cudaGetLastError();
 }
 cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,

@@ -107,6 +107,9 @@ struct pp_job {
     ScanTotals *d_totals = nullptr;
     int64_t *d_exact = nullptr;
     uint32_t *d_lines = nullptr;
+    uint32_t *d_tile_base = nullptr;        // first parse tile of every chunk (n+1 entries)
+    unsigned long long *d_parse_work = nullptr;  // look-back tile states + ticket
+    uint32_t total_tiles = 0, max_tiles = 0;
     // pinned host mirrors
     ChunkResult *h_results = nullptr;
     ParseDesc *h_pdesc = nullptr;
@@ -246,6 +249,8 @@ void pp_job_free(pp_job *j)
     cudaFree(j->d_totals);
     cudaFree(j->d_exact);
     cudaFree(j->d_lines);
+    cudaFree(j->d_tile_base);
+    cudaFree(j->d_parse_work);
     cudaFreeHost(j->h_lead);
     cudaFreeHost(j->h_results);
     cudaFreeHost(j->h_pdesc);
@@ -336,6 +341,23 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         }
         j->slots_bytes = std::max<uint64_t>(slot_off, 128);
         j->lead_bytes = std::max<uint64_t>(lead_off, 16);
+        // parse tiles: chunk k's combined memory starts prefix_len bytes before its output
+        std::vector<uint32_t> tile_base((size_t)n + 1, 0);
+        {
+            const uint64_t tb = parse_tile_bytes();
+            uint64_t acc = 0;
+            for (int k = 0; k < n; k++) {
+                const ChunkDesc &d = j->descs[(size_t)k];
+                const uint64_t head = (d.slot_off + d.lead_len - d.prefix_len) & 15u;
+                tile_base[(size_t)k] = (uint32_t)acc;
+                const uint64_t nt = (head + d.prefix_len + d.out_len + tb - 1) / tb;
+                j->max_tiles = std::max<uint32_t>(j->max_tiles, (uint32_t)std::min<uint64_t>(nt, 0xffffffffu));
+                acc += nt;
+            }
+            if (acc > 0xfffffff0ull) return fail(PP_E_ARG);
+            tile_base[(size_t)n] = (uint32_t)acc;
+            j->total_tiles = (uint32_t)acc;
+        }
 
         CK(cudaMalloc(&j->d_slots, j->slots_bytes));
         CK(cudaMalloc(&j->d_descs, sizeof(ChunkDesc) * (size_t)std::max(n, 1)));
@@ -344,6 +366,10 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         CK(cudaMalloc(&j->d_pout, sizeof(ParseOut) * (size_t)std::max(n, 1)));
         CK(cudaMalloc(&j->d_totals, sizeof(ScanTotals)));
         CK(cudaMalloc(&j->d_exact, sizeof(int64_t) * (size_t)std::max(n, 1)));
+        CK(cudaMalloc(&j->d_tile_base, sizeof(uint32_t) * ((size_t)n + 1)));
+        CK(cudaMalloc(&j->d_parse_work, sizeof(unsigned long long) * ((size_t)j->total_tiles + 1)));
+        CK(cudaMemcpyAsync(j->d_tile_base, tile_base.data(), sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice,
+                           ctx->stream));
         CK(cudaHostAlloc(&j->h_results, sizeof(ChunkResult) * (size_t)std::max(n, 1), cudaHostAllocDefault));
         CK(cudaHostAlloc(&j->h_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1), cudaHostAllocDefault));
         CK(cudaHostAlloc(&j->h_pout, sizeof(ParseOut) * (size_t)std::max(n, 1), cudaHostAllocDefault));
@@ -461,10 +487,11 @@ static int job_parse_stage(pp_job *j, cudaStream_t st, bool with_pout_flags, int
                            st) != cudaSuccess)
         return PP_E_CUDA;
     if (launch_scan(j->d_descs, j->d_results, j->d_exact, n, (j->flags & PP_JOB_STRICT) ? 1u : 0u, j->rec_cap,
-                    j->d_pdesc, j->d_totals, st) != cudaSuccess)
+                    j->d_pdesc, j->d_pout, j->d_totals, st) != cudaSuccess)
         return PP_E_CUDA;
     CK(cudaEventRecord(j->ev[4], st));
-    if (launch_parse(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st) != cudaSuccess)
+    if (launch_parse(j->d_slots, j->d_pdesc, n, j->d_tile_base, j->total_tiles, j->max_tiles, j->d_lines, j->rec_cap, j->d_pout,
+                     j->d_totals, j->d_parse_work, j->ctx->sm_count, st) != cudaSuccess)
         return PP_E_CUDA;
     CK(cudaEventRecord(j->ev[5], st));
     if (launch_exact_emit(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st) != cudaSuccess)
@@ -723,7 +750,13 @@ int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const
     count_prefix(prepend, (int32_t)prepend_len, &d.prefix_nl, &nul);
     const uint64_t slot_bytes = align_up((uint64_t)d.lead_len + d.out_len + 1, 128);
     const int64_t rec_cap = (prepend_len + rest_len) / 4 + 16;
-    DevBuf slot, desc, res, pdesc, pout, totals, exact, lines;
+    DevBuf slot, desc, res, pdesc, pout, totals, exact, lines, tbase, work;
+    const uint64_t head0 = ((uint64_t)d.lead_len - d.prefix_len) & 15u;
+    const uint32_t tiles0 = (uint32_t)((head0 + d.prefix_len + d.out_len + parse_tile_bytes() - 1) / parse_tile_bytes());
+    const uint32_t tb_host[2] = {0u, tiles0};
+    CK(tbase.alloc(sizeof tb_host));
+    CK(work.alloc(sizeof(unsigned long long) * ((size_t)tiles0 + 1)));
+    CK(cudaMemcpyAsync(tbase.p, tb_host, sizeof tb_host, cudaMemcpyHostToDevice, st));
     CK(slot.alloc(slot_bytes));
     CK(desc.alloc(sizeof d));
     CK(res.alloc(sizeof(ChunkResult)));
@@ -749,9 +782,10 @@ int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const
         if (launch_exact_count(slot.as<uint8_t>(), desc.as<ChunkDesc>(), res.as<ChunkResult>(),
                                pass ? pout.as<ParseOut>() : nullptr, 1, exact.as<int64_t>(), st) != cudaSuccess ||
             launch_scan(desc.as<ChunkDesc>(), res.as<ChunkResult>(), exact.as<int64_t>(), 1, 0, rec_cap,
-                        pdesc.as<ParseDesc>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
-            launch_parse(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, lines.as<uint32_t>(), rec_cap,
-                         pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
+                        pdesc.as<ParseDesc>(), pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
+            launch_parse(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, tbase.as<uint32_t>(), tiles0, tiles0,
+                         lines.as<uint32_t>(), rec_cap, pout.as<ParseOut>(), totals.as<ScanTotals>(),
+                         work.as<unsigned long long>(), ctx->sm_count, st) != cudaSuccess ||
             launch_exact_emit(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, lines.as<uint32_t>(), rec_cap,
                               pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess)
             return PP_E_CUDA;
