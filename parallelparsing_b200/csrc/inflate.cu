@@ -10,7 +10,7 @@ namespace pp {
 __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
     pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
                       uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
-                      uint16_t *map_scratch, uint32_t map_cap, int *next_chunk)
+                      uint32_t *scratch, size_t scratch_words, int *next_chunk)
 {
     extern __shared__ __align__(128) uint8_t pp_smem_raw[];
     ppinf::Sm sm;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint16_t *map = map_scratch + (size_t)blockIdx.x * map_cap;
+    uint32_t *map = scratch + (size_t)blockIdx.x * scratch_words;
     uint32_t stage_phase = 0;
     for (;;) {
         if (threadIdx.x == 0) sm.u[16] = (uint32_t)atomicAdd(next_chunk, 1);
@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         if (k >= n) break;
         ppinf::inflate_chunk(sm, descs[k], comp, comp_bytes, slots, lead, map, results[k], stage_phase);
     }
+}
+
+// Debug aid: cycles thread 0 of every CTA spent per phase since the last call (and reset).
+extern "C" int pp_internal_phase_cycles(unsigned long long *out, int n)
+{
+    unsigned long long h[ppinf::PH_COUNT];
+    if (cudaMemcpyFromSymbol(h, ppinf::g_phase_cycles, sizeof h) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < ppinf::PH_COUNT; i++) out[i] = h[i];
+    unsigned long long z[ppinf::PH_COUNT] = {};
+    cudaMemcpyToSymbol(ppinf::g_phase_cycles, z, sizeof z);
+    return ppinf::PH_COUNT;
 }
 
 int inflate_max_ctas_per_sm(int threads)
@@ -44,7 +55,7 @@ int inflate_max_ctas_per_sm(int threads)
 
 size_t inflate_scratch_bytes(int threads, int grid)
 {
-    return (size_t)grid * ppinf::map_cap_for(threads) * sizeof(uint16_t);
+    return (size_t)grid * ppinf::scratch_words_for(threads) * sizeof(uint32_t);
 }
 
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
@@ -58,7 +69,7 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     if (e != cudaSuccess) return e;
     const int grid = n < cfg.grid ? n : cfg.grid;
     pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
-                                                        ppinf::map_cap_for(cfg.threads), cfg.counter);
+                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter);
     return cudaGetLastError();
 }
 

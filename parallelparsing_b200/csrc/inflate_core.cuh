@@ -56,6 +56,9 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 #define PP_CONST static const
 #define PP_ATOMIC_ADD(p, v) (*(p) += (v))
 #define PP_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
+// per-thread state that lives across a barrier: registers on the device, one row per thread here
+#define PP_TLS_DECL(type, name, n) static type name##_tls[1024][n]
+#define PP_TLS(name) name##_tls[t]
 #else
 #define PP_DEV __device__ __forceinline__
 #define PP_HD __host__ __device__ __forceinline__
@@ -69,9 +72,28 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 #define PP_CONST __device__ const
 #define PP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define PP_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define PP_TLS_DECL(type, name, n) type name[n]
+#define PP_TLS(name) name
 #endif
 
 namespace ppinf {
+
+// ---- phase timers (thread 0's clock, summed over all CTAs; read with pp_internal_phase_cycles) ----
+enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_COUNT };
+#if defined(PP_HOST_EMU)
+#define PP_PHASE(ph)
+#else
+__device__ unsigned long long g_phase_cycles[PH_COUNT];
+#define PP_PHASE(ph)                                                               \
+    do {                                                                           \
+        if (threadIdx.x == 0) {                                                    \
+            const long long now_ = clock64();                                      \
+            atomicAdd(&g_phase_cycles[ph], (unsigned long long)(now_ - sm.u[24] - ((long long)sm.u[25] << 32))); \
+            sm.u[24] = (uint32_t)now_;                                             \
+            sm.u[25] = (uint32_t)((unsigned long long)now_ >> 32);                 \
+        }                                                                          \
+    } while (0)
+#endif
 
 // ---- geometry -------------------------------------------------------------
 constexpr int kRootL = 10;              // primary bits, literal/length table
@@ -90,12 +112,19 @@ constexpr int kTileB = 16;              // output bytes per thread per resolve t
 constexpr uint32_t kMinMapCap = 160u * 1024u;  // one sub-sequence can emit kSubBits/2*258 < 128 Ki bytes
 
 PP_HD uint32_t cw_words_for(int T) { return (uint32_t)(T * kSubW + kHdrWords + kSlackWords + 3) & ~3u; }
-// source-map entries one window may produce before the window is cut short
+// output bytes one window may produce before the window is cut short
 PP_HD uint32_t map_cap_for(int T)
 {
     const uint32_t c = (uint32_t)T * (uint32_t)kSubW * 4u * 8u;  // 8x expansion of a full window
     return c > kMinMapCap ? c : kMinMapCap;
 }
+// Per-CTA scratch in global memory (u32 words): the token rows of a window — token k of
+// sub-sequence s at tok[k * T + s], so the lanes of a warp store one row segment together —
+// followed by the group index (one word per 16 output bytes).
+constexpr int kTokRows = kSubBits + 8;  // a sub-sequence holds at most kSubBits symbols
+PP_HD uint32_t tok_words_for(int T) { return (uint32_t)kTokRows * (uint32_t)T; }
+PP_HD uint32_t idx_words_for(int T) { return map_cap_for(T) / 16u + 16u; }
+PP_HD size_t scratch_words_for(int T) { return (size_t)tok_words_for(T) + idx_words_for(T); }
 
 // ---- table entry ------------------------------------------------------------
 // [4:0] bits to consume (code + extra)  [7:5] kind  [12:8] code length
@@ -145,6 +174,7 @@ struct Sm {
     uint32_t *nl;       // per thread: '\n' bytes stored                            [T]
     uint32_t *nul;      // per thread: non-zero when a NUL byte was stored          [T]
     uint32_t *ns;       // per thread: its predecessor's end, latched for a SYNC round [T]
+    uint32_t *ntok;     // per thread: tokens its segment emitted                     [T]
     uint16_t *res;      // resolve tile: 0x8000|byte or tile-relative source index  [kTileB*T]
     uint16_t *sorted;   // symbols in canonical order                               [320]
     uint16_t *codes;    // canonical code of every symbol                           [320]
@@ -164,7 +194,7 @@ PP_HD uint32_t sm_bytes_for(int T)
     uint32_t b = 0;
     b += cw_words_for(T) * 4u;
     b += (kLitCap + kDistCap) * 4u;
-    b += (uint32_t)T * 4u * 7u;
+    b += (uint32_t)T * 4u * 8u;
     b += (uint32_t)T * kTileB * 2u;
     b += 320u * 2u * 2u + 320u;
     b += (16u * 3u + 32u * 2u) * 4u;
@@ -185,6 +215,7 @@ PP_DEV void sm_carve(Sm &s, uint8_t *raw, int T)
     s.nl = (uint32_t *)p; p += (uint32_t)T * 4u;
     s.nul = (uint32_t *)p; p += (uint32_t)T * 4u;
     s.ns = (uint32_t *)p; p += (uint32_t)T * 4u;
+    s.ntok = (uint32_t *)p; p += (uint32_t)T * 4u;
     s.res = (uint16_t *)p; p += (uint32_t)T * kTileB * 2u;
     s.count = (uint32_t *)p; p += 16u * 4u;
     s.first = (uint32_t *)p; p += 16u * 4u;
@@ -607,13 +638,23 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 }
 
 // ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
-// Decodes the symbols that START in [start, limit) (window-relative bits).  WRITE: also
-// writes the source map, entry i of the segment at map[o + i], never at or past map[oclip].
+// Decodes the symbols that START in [start, limit) (window-relative bits).
+// WRITE: also emits one TOKEN per symbol, token k of this thread at tok[k * T + t]
+//   literal: 0x80000000 | byte        match: len << 15 | (dist - 1)
+// and, for every multiple of 16 below oclip that a token's output range [o, o + len) covers,
+// the GROUP INDEX entry idx[m / 16] = t | k << 10 | (m - o) << 20, which tells the resolve
+// stage where the bytes of group m / 16 start.  `o` is the virtual output index (window
+// output offset + misalignment of the window's first byte).
 struct Seg {
-    uint32_t end, out, flag;
+    uint32_t end, out, flag, ntok;
 };
+PP_DEV uint32_t tok_lit(uint32_t byte) { return 0x80000000u | byte; }
+PP_DEV uint32_t tok_match(uint32_t len, uint32_t dist) { return (len << 15) | (dist - 1u); }
+PP_DEV uint32_t idx_pack(uint32_t t, uint32_t k, uint32_t off) { return t | (k << 10) | (off << 20); }
+
 template <int WRITE>
-PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *map, uint32_t o, uint32_t oclip)
+PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *tok, uint32_t *idx, uint32_t T,
+                      uint32_t t, uint32_t o, uint32_t oclip)
 {
     const uint32_t *cw = sm.cw;
     uint32_t wp = start >> 5;
@@ -621,7 +662,7 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *ma
     uint64_t buf = ((uint64_t)cw[wp] | ((uint64_t)cw[wp + 1] << 32)) >> sh;
     uint32_t cnt = 64u - sh;
     wp += 2;
-    uint32_t out = 0, flag = F_NONE;
+    uint32_t out = 0, flag = F_NONE, k = 0;
     for (;;) {
         if (wp * 32u - cnt >= limit) break;
         if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
@@ -630,7 +671,12 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *ma
         if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
         const uint32_t kind = e_kind(e), tot = e_tot(e);
         if (kind == K_LIT) {
-            if (WRITE) { if (o + out < oclip) map[o + out] = (uint16_t)e_val(e); }
+            if (WRITE) {
+                const uint32_t p0 = o + out;
+                tok[k * T + t] = tok_lit(e_val(e) & 0xffu);
+                if ((p0 & 15u) == 0u && p0 < oclip) idx[p0 >> 4] = idx_pack(t, k, 0);
+                k++;
+            }
             out++;
             buf >>= tot;
             cnt -= tot;
@@ -653,20 +699,11 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *ma
             // the reference primes a full 32 KB dictionary (Core.cs:158)
             if (WRITE) {
                 const uint32_t p0 = o + out;
-                uint32_t n = p0 < oclip ? oclip - p0 : 0u;
-                if (n > len) n = len;
-                if (dist >= len) {
-                    const uint16_t v = (uint16_t)(dist - 1u);
-                    for (uint32_t j = 0; j < n; j++) map[p0 + j] = v;
-                } else {
-                    // overlapping run: byte j repeats the `dist` bytes before the match, so its
-                    // source is dist*(j/dist+1) back — always in front of the match itself
-                    uint32_t v = dist - 1u, r = 0;
-                    for (uint32_t j = 0; j < n; j++) {
-                        map[p0 + j] = (uint16_t)v;
-                        if (++r == dist) { r = 0; v += dist; }
-                    }
-                }
+                tok[k * T + t] = tok_match(len, dist);
+                uint32_t end = p0 + len;
+                if (end > oclip) end = oclip;
+                for (uint32_t m = (p0 + 15u) & ~15u; m < end; m += 16u) idx[m >> 4] = idx_pack(t, k, m - p0);
+                k++;
             }
             out += len;
             continue;
@@ -684,6 +721,7 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint16_t *ma
     r.end = wp * 32u - cnt;
     r.out = out;
     r.flag = flag;
+    r.ntok = k;
     return r;
 }
 
@@ -695,104 +733,140 @@ struct WindowOut {
 };
 
 // ---- RESOLVE ------------------------------------------------------------------------
-// Source map -> bytes for window output [0, total) that lands at outp[0..total).
-// `a` = misalignment of outp (outp - a is 16-byte aligned); map entry of byte q is map[q + a].
-// Per tile: (1) every thread classifies its 16 bytes — literal, source in front of the tile
-// (gathered from global memory, all loads independent), or source inside the tile (the
-// tile-relative index of that byte) — and publishes them in shared memory; one barrier;
-// (2) in-tile sources are chased with no further barrier: an entry is always either the byte
-// or the index of an EARLIER byte with the same value, every hop is published, so chains
-// collapse like pointer jumping whatever the interleaving of the warps; (3) the 16 bytes
-// leave with one vector store; one barrier before the next tile gathers from them.
-PP_DEV void resolve_window(const Sm &sm, const uint16_t *map, uint8_t *outp, uint32_t a, uint32_t total)
+// Tokens -> bytes for window output [0, total) that lands at outp[0..total).
+// `a` = misalignment of outp (outp - a is 16-byte aligned); virtual index v = q + a.
+// The output is walked in tiles of 16 bytes per thread, three steps per tile:
+//  EXPAND   thread g owns group g (16 consecutive bytes): the group index names the token its
+//           first byte lies in; it walks the tokens and writes one u16 per byte into shared
+//           memory: 0x8000|literal, or distance-1 (overlapping matches are rewritten so that
+//           every source lies before the match).
+//  GATHER   lanes now own INTERLEAVED bytes (byte j*32+lane of the warp's 512): a source in
+//           front of the tile is final in global memory — the 32 lanes of a load mostly read
+//           one or two runs of consecutive bytes, so it costs a few sectors, not 32 — a source
+//           inside the tile becomes the tile-relative index of that byte.
+//  CHASE    in-tile sources are followed through shared memory with no barrier: an entry is
+//           always either the byte or the index of an EARLIER byte with the same value and
+//           every hop is published, so chains collapse like pointer jumping whatever the
+//           interleaving of the warps.  Then the bytes leave, 32 consecutive bytes per warp
+//           store; '\n' and NUL are counted on the way for the parse stage.
+PP_DEV uint32_t div_small(uint32_t i, uint32_t d)  // floor(i / d) for i, d < 512
+{
+#ifdef PP_HOST_EMU
+    return i / d;
+#else
+    return (uint32_t)__fdividef((float)i + 0.5f, (float)d);  // (i+0.5)/d is >= 0.5/d away from an integer
+#endif
+}
+
+PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *idx, uint8_t *outp, uint32_t a,
+                           uint32_t total)
 {
     const int T = PP_NT;
     const uint32_t R = (uint32_t)T * kTileB;
-    const uint32_t vend = a + total;         // virtual index = q + a; valid bytes: a <= v < vend
+    const uint32_t vend = a + total;         // valid bytes: a <= v < vend
     uint8_t *vbase = outp - a;               // 16-byte aligned; vbase[v] is the byte of virtual index v
+    volatile uint16_t *res = sm.res;
     for (uint32_t tb = 0; tb < vend; tb += R) {
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
+        // EXPAND
         PP_FOR_T(t)
         {
             const uint32_t v0 = tb + (uint32_t)t * kTileB;
-            if (v0 < vend) {
-                const uint4 m0 = *reinterpret_cast<const uint4 *>(map + v0);
-                const uint4 m1 = *reinterpret_cast<const uint4 *>(map + v0 + 8);
-                const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                uint32_t r[kTileB];
+            uint32_t r[kTileB];
+#pragma unroll
+            for (int j = 0; j < kTileB; j++) r[j] = 0x8000u;  // bytes outside the window: never stored, never a source
+            if (v0 < vend && v0 + kTileB > a) {
+                const uint32_t ie = idx[v0 >> 4];
+                uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
+                uint32_t tk = tok[k * (uint32_t)T + sgm];
+                bool fetch = false;
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
                     const uint32_t v = v0 + (uint32_t)j;
-                    const uint32_t e = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-                    const int32_t sv = (int32_t)v - (int32_t)e - 1;  // virtual index of the source
-                    uint32_t x = e;
-                    if (v - a >= total) x = 0x8000u;  // not part of this window: never stored, never a source
-                    else if (!(e & 0x8000u)) {
-                        if (sv < near_lo) x = 0x8000u | (uint32_t)vbase[sv];
-                        else x = (uint32_t)sv - tb;
+                    if (v >= a && v < vend) {
+                        if (fetch) {
+                            k++;
+                            while (k >= sm.ntok[sgm] && sgm + 1u < (uint32_t)T) { sgm++; k = 0; }
+                            tk = tok[k * (uint32_t)T + sgm];
+                            i = 0;
+                            fetch = false;
+                        }
+                        if (tk & 0x80000000u) {
+                            r[j] = 0x8000u | (tk & 0xffu);
+                            fetch = true;
+                        } else {
+                            const uint32_t len = tk >> 15, dist = (tk & 0x7fffu) + 1u;
+                            r[j] = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
+                            if (++i == len) fetch = true;
+                        }
                     }
-                    r[j] = x;
                 }
-                uint4 q0, q1;
-                q0.x = r[0] | (r[1] << 16); q0.y = r[2] | (r[3] << 16); q0.z = r[4] | (r[5] << 16); q0.w = r[6] | (r[7] << 16);
-                q1.x = r[8] | (r[9] << 16); q1.y = r[10] | (r[11] << 16); q1.z = r[12] | (r[13] << 16); q1.w = r[14] | (r[15] << 16);
-                uint4 *dst = reinterpret_cast<uint4 *>(sm.res + (uint32_t)t * kTileB);
-                dst[0] = q0;
-                dst[1] = q1;
             }
+            uint4 q0, q1;
+            q0.x = r[0] | (r[1] << 16); q0.y = r[2] | (r[3] << 16); q0.z = r[4] | (r[5] << 16); q0.w = r[6] | (r[7] << 16);
+            q1.x = r[8] | (r[9] << 16); q1.y = r[10] | (r[11] << 16); q1.z = r[12] | (r[13] << 16); q1.w = r[14] | (r[15] << 16);
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.res + (uint32_t)t * kTileB);
+            dst[0] = q0;
+            dst[1] = q1;
         }
         PP_END_T
         PP_SYNC();
+        // GATHER
         PP_FOR_T(t)
         {
-            const uint32_t v0 = tb + (uint32_t)t * kTileB;
-            if (v0 < vend && v0 + kTileB > a) {
-                volatile uint16_t *res = sm.res;
-                const uint4 *own = reinterpret_cast<const uint4 *>(sm.res + (uint32_t)t * kTileB);
-                const uint4 q0 = own[0], q1 = own[1];
-                uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                // (2) chase in-tile sources
-                uint32_t pend = ~(w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) & 0x80008000u;
-                while (pend) {
-                    pend = 0;
+            const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
+            uint32_t e[kTileB];
 #pragma unroll
-                    for (int j = 0; j < kTileB; j++) {
-                        const uint32_t sh = (uint32_t)(j & 1) * 16u;
-                        const uint32_t x = (w[j >> 1] >> sh) & 0xffffu;
-                        if (!(x & 0x8000u)) {
-                            const uint32_t y = res[x];
-                            res[(uint32_t)t * kTileB + (uint32_t)j] = (uint16_t)y;
-                            w[j >> 1] = (w[j >> 1] & ~(0xffffu << sh)) | (y << sh);
-                            if (!(y & 0x8000u)) pend = 1;
-                        }
-                    }
-                }
-                // (3) the bytes leave; '\n' and NUL are counted on the way
-                uint32_t b[4];
+            for (int j = 0; j < kTileB; j++) e[j] = res[qb + (uint32_t)j * 32u];
+            uint32_t g[kTileB];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t p = w[2 * j], q = w[2 * j + 1];
-                    b[j] = (p & 0xffu) | ((p >> 8) & 0xff00u) | ((q & 0xffu) << 16) | ((q << 8) & 0xff000000u);
-                }
-                if (v0 >= a && v0 + kTileB <= vend) {
-                    uint4 w4;
-                    w4.x = b[0]; w4.y = b[1]; w4.z = b[2]; w4.w = b[3];
-                    *reinterpret_cast<uint4 *>(vbase + v0) = w4;
-                    sm.nl[t] += popc32(eq_bytes(b[0], 0x0a0a0a0au)) + popc32(eq_bytes(b[1], 0x0a0a0a0au)) +
-                                popc32(eq_bytes(b[2], 0x0a0a0a0au)) + popc32(eq_bytes(b[3], 0x0a0a0a0au));
-                    sm.nul[t] |= eq_bytes(b[0], 0u) | eq_bytes(b[1], 0u) | eq_bytes(b[2], 0u) | eq_bytes(b[3], 0u);
-                } else {
-                    for (int j = 0; j < kTileB; j++) {
-                        const uint32_t v = v0 + (uint32_t)j;
-                        if (v >= a && v < vend) {
-                            const uint32_t c = (b[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-                            vbase[v] = (uint8_t)c;
-                            sm.nl[t] += (c == 10u);
-                            sm.nul[t] |= (c == 0u);
-                        }
+            for (int j = 0; j < kTileB; j++) {
+                const int32_t sv = (int32_t)(tb + qb + (uint32_t)j * 32u) - (int32_t)e[j] - 1;  // virtual index of the source
+                g[j] = 0xffffffffu;
+                if (!(e[j] & 0x8000u)) g[j] = sv < near_lo ? 0x8000u | (uint32_t)vbase[sv] : (uint32_t)(sv - (int32_t)tb);
+            }
+#pragma unroll
+            for (int j = 0; j < kTileB; j++)
+                if (g[j] != 0xffffffffu) res[qb + (uint32_t)j * 32u] = (uint16_t)g[j];
+        }
+        PP_END_T
+        PP_SYNC();
+        // CHASE + store
+        PP_FOR_T(t)
+        {
+            const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
+            uint32_t e[kTileB];
+            uint32_t pend = 0;
+#pragma unroll
+            for (int j = 0; j < kTileB; j++) {
+                e[j] = res[qb + (uint32_t)j * 32u];
+                pend |= ~e[j] & 0x8000u;
+            }
+            while (pend) {
+                pend = 0;
+#pragma unroll
+                for (int j = 0; j < kTileB; j++) {
+                    if (!(e[j] & 0x8000u)) {
+                        const uint32_t y = res[e[j]];
+                        e[j] = y;
+                        res[qb + (uint32_t)j * 32u] = (uint16_t)y;  // publish the hop
+                        pend |= ~y & 0x8000u;
                     }
                 }
             }
+            uint32_t nl = 0, nul = 0;
+#pragma unroll
+            for (int j = 0; j < kTileB; j++) {
+                const uint32_t v = tb + qb + (uint32_t)j * 32u;
+                if (v >= a && v < vend) {
+                    const uint32_t c = e[j] & 0xffu;
+                    vbase[v] = (uint8_t)c;
+                    nl += (c == 10u);
+                    nul |= (c == 0u);
+                }
+            }
+            sm.nl[t] += nl;
+            sm.nul[t] |= nul;
         }
         PP_END_T
         PP_SYNC();  // stores visible to the next tile's gathers; res free again
@@ -801,14 +875,15 @@ PP_DEV void resolve_window(const Sm &sm, const uint16_t *map, uint8_t *outp, uin
 
 // One window of a Huffman block: GUESS, SYNC, SCAN, EMIT, RESOLVE.
 // s0: window-relative bit of the first symbol; room: output bytes still wanted (> 0).
-PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32_t mapcap, uint8_t *outp, uint32_t room)
+PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t *idx, uint32_t mapcap, uint8_t *outp,
+                                uint32_t room)
 {
     const int T = PP_NT;
     // GUESS
     PP_FOR_T(t)
     {
         const uint32_t st = s0 + (uint32_t)t * kSubBits;
-        const Seg r = decode_seg<0>(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, nullptr, 0, 0);
+        const Seg r = decode_seg<0>(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, nullptr, nullptr, 0, 0, 0, 0);
         sm.start[t] = st;
         sm.end[t] = r.end;
         sm.outc[t] = r.out;
@@ -816,6 +891,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32
     }
     PP_END_T
     PP_SYNC();
+    PP_PHASE(PH_GUESS);
     // SYNC: u[8] = first thread whose start is not its predecessor's end, u[9] = first flagged thread
     uint32_t rounds = 0;
     for (;;) {
@@ -843,8 +919,8 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32
             if ((uint32_t)t >= m && ns != sm.start[t]) {
                 const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
                 Seg r;
-                if (ns >= lim) { r.end = ns; r.out = 0; r.flag = F_NONE; }
-                else r = decode_seg<0>(sm, ns, lim, nullptr, 0, 0);
+                if (ns >= lim) { r.end = ns; r.out = 0; r.flag = F_NONE; r.ntok = 0; }
+                else r = decode_seg<0>(sm, ns, lim, nullptr, nullptr, 0, 0, 0, 0);
                 sm.start[t] = ns;
                 sm.end[t] = r.end;
                 sm.outc[t] = r.out;
@@ -856,6 +932,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32
     }
     const uint32_t f = sm.u[9];
     PP_SYNC();
+    PP_PHASE(PH_SYNC);
     // SCAN: threads past the first flagged one produce nothing
     PP_FOR_T(t)
     if ((uint32_t)t > f) sm.outc[t] = 0;
@@ -890,17 +967,25 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint16_t *map, uint32
         if (flag == F_BAD) flag = F_NONE;
     }
     PP_SYNC();
+    PP_PHASE(PH_SCAN);
     // EMIT
     PP_FOR_T(t)
-    if ((uint32_t)t < nlive) {
-        const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
-        const uint32_t st = sm.start[t];
-        if (st < lim) decode_seg<1>(sm, st, lim, map, a + sm.outc[t], a + produced);
+    {
+        uint32_t nt = 0;
+        if ((uint32_t)t < nlive) {
+            const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
+            const uint32_t st = sm.start[t];
+            if (t == 0 && a) idx[0] = idx_pack(0, 0, 0);  // group 0 starts at the window's first byte, not at a multiple of 16
+            if (st < lim) nt = decode_seg<1>(sm, st, lim, tok, idx, (uint32_t)T, (uint32_t)t, a + sm.outc[t], a + produced).ntok;
+        }
+        sm.ntok[t] = nt;
     }
     PP_END_T
     PP_SYNC();
+    PP_PHASE(PH_EMIT);
     // RESOLVE
-    resolve_window(sm, map, outp, a, produced);
+    resolve_window(sm, tok, idx, outp, a, produced);
+    PP_PHASE(PH_RESOLVE);
     WindowOut w;
     w.next_bit = next_bit;
     w.produced = produced;
@@ -930,9 +1015,9 @@ PP_DEV void stored_copy(const Sm &sm, const uint8_t *src, uint8_t *dst, uint32_t
 }
 
 // Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
-// map: this CTA's source-map scratch (global memory, map_cap_for(T) entries, 16 B aligned).
+// scratch: this CTA's token rows + group index (global memory, scratch_words_for(T) words).
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                          const uint8_t *lead_src, uint16_t *map, ChunkResult &res, uint32_t &stage_phase)
+                          const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase)
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
@@ -948,9 +1033,17 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         PP_END_T
     }
     PP_SYNC();
+#ifndef PP_HOST_EMU
+    if (threadIdx.x == 0) {
+        const long long now_ = clock64();
+        sm.u[24] = (uint32_t)now_;
+        sm.u[25] = (uint32_t)((unsigned long long)now_ >> 32);
+    }
+#endif
     uint8_t *out = slot + d.lead_len;
     const uint32_t out_len = d.out_len;
     const uint32_t mapcap = map_cap_for(T);
+    uint32_t *tok = scratch, *idx = scratch + tok_words_for(T);
     const uint32_t cww = cw_words_for(T);
     // 2. bit cursor: 8*Input - Bits (Core.cs:151-157 inflatePrime semantics)
     uint64_t bit = d.in_bit;
@@ -960,7 +1053,9 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     while (produced < out_len) {
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
+        PP_PHASE(PH_OTHER);
         if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
+        PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
         if (need_header) {
             const uint32_t hdr = peek_bits(sm.cw, s0, 3);
@@ -980,6 +1075,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
                 stored_copy(sm, comp + byte0, out + produced, n);
                 produced += n;
                 bit = (byte0 + len) * 8u;
+                PP_PHASE(PH_STORED);
                 if (last) break;  // Z_STREAM_END (Core.cs:185)
                 continue;
             }
@@ -988,9 +1084,10 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
             else if (type == 2u) rc = dynamic_tables(sm, s0, &s0);
             else rc = -3;  // invalid block type
             if (rc) { status = rc; break; }
+            PP_PHASE(PH_HEADER);
             need_header = false;
         }
-        const WindowOut w = huffman_window(sm, s0, map, mapcap, out + produced, out_len - produced);
+        const WindowOut w = huffman_window(sm, s0, tok, idx, mapcap, out + produced, out_len - produced);
         produced += w.produced;
         bit = base_byte * 8u + w.next_bit;
 #ifdef PP_HOST_EMU
@@ -1006,6 +1103,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         }
     }
     PP_SYNC();
+    PP_PHASE(PH_OTHER);
     // 3. NUL terminator / clean tail for the parse stage
     {
         const uint32_t to = ((d.lead_len + d.out_len + 1u + 127u) & ~127u) - d.lead_len;

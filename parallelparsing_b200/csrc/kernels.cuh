@@ -43,7 +43,7 @@ struct ScanTotals {
 struct InflateLaunch {
     int threads = 0;         // CTA size (multiple of 32, <= 1024)
     int grid = 0;            // resident CTAs (SMs x CTAs per SM)
-    uint16_t *map = nullptr; // source-map scratch: grid x map_cap_for(threads) entries
+    uint32_t *map = nullptr; // token/index scratch: grid x scratch_words_for(threads) words
     int *counter = nullptr;  // chunk counter the CTAs pull work from
 };
 int inflate_max_ctas_per_sm(int threads);

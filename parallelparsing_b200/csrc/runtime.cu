@@ -51,7 +51,7 @@ struct pp_ctx {
     int sm_count = 0;
     // inflate launch geometries: few chunks -> large CTAs (one per SM), many chunks -> more CTAs per SM
     InflateLaunch wide, dense;
-    uint16_t *d_map = nullptr;
+    uint32_t *d_map = nullptr;
     int *d_counter = nullptr;
     const InflateLaunch &inflate_cfg(int n_chunks) const { return n_chunks <= wide.grid ? wide : dense; }
 };

@@ -19,8 +19,17 @@ gz = corpus.gz_parallel(fq, 6, segment=8 << 20, threads=os.cpu_count())
 ix = pp.Core.BuildDeflateIndex(gz, chunk)
 dev = pp.Device(0)
 job = pp.Job(dev, ix, gz.size)
+import ctypes as C  # noqa: E402
+L = pp.lib()
+ph = (C.c_ulonglong * 16)()
+L.pp_internal_phase_cycles(ph, 16)
 for _ in range(iters):
     info = job.run(gz)
+n = L.pp_internal_phase_cycles(ph, 16)
+names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other"]
+tot = sum(ph[i] for i in range(n)) or 1
+print("phase share of CTA time:", ", ".join(f"{names[i]} {100*ph[i]/tot:.1f}%" for i in range(n)),
+      f"| cycles/iter/CTA-sum {tot/iters:.3e}")
 assert info.status == 0
 print(f"chunks {info.n_chunks} records {info.total_records} bytes {info.total_bytes} "
       f"inflate {info.inflate_ms:.3f} ms parse {info.parse_ms:.3f} ms")

@@ -22,7 +22,7 @@ int emu_inflate_chunk(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t 
     d.lead_len = lead_len; d.out_len = out_len; d.prefix_len = 0; d.prefix_nl = 0;
     ppinf::ChunkResult r;
     uint8_t *raw = (uint8_t *)aligned_alloc(128, ppinf::sm_bytes_for(T));
-    uint16_t *map = (uint16_t *)aligned_alloc(128, (size_t)ppinf::map_cap_for(T) * 2);
+    uint32_t *map = (uint32_t *)aligned_alloc(128, (ppinf::scratch_words_for(T) * 4 + 127) / 128 * 128);
     ppinf::Sm sm;
     ppinf::sm_carve(sm, raw, T);
     uint32_t phase = 0;
