@@ -79,7 +79,7 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 namespace ppinf {
 
 // ---- phase timers (thread 0's clock, summed over all CTAs; read with pp_internal_phase_cycles) ----
-enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_COUNT };
+enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_COUNT };
 #if defined(PP_HOST_EMU)
 #define PP_PHASE(ph)
 #else
@@ -195,7 +195,7 @@ PP_HD uint32_t sm_bytes_for(int T)
     b += cw_words_for(T) * 4u;
     b += (kLitCap + kDistCap) * 4u;
     b += (uint32_t)T * 4u * 8u;
-    b += (uint32_t)T * kTileB * 2u;
+    b += ((uint32_t)T * kTileB + (uint32_t)T * kTileB / 32u + 2u + 7u) / 8u * 16u;
     b += 320u * 2u * 2u + 320u;
     b += (16u * 3u + 32u * 2u) * 4u;
     b += 16u;  // mbarrier
@@ -216,7 +216,7 @@ PP_DEV void sm_carve(Sm &s, uint8_t *raw, int T)
     s.nul = (uint32_t *)p; p += (uint32_t)T * 4u;
     s.ns = (uint32_t *)p; p += (uint32_t)T * 4u;
     s.ntok = (uint32_t *)p; p += (uint32_t)T * 4u;
-    s.res = (uint16_t *)p; p += (uint32_t)T * kTileB * 2u;
+    s.res = (uint16_t *)p; p += ((uint32_t)T * kTileB + (uint32_t)T * kTileB / 32u + 2u + 7u) / 8u * 16u;
     s.count = (uint32_t *)p; p += 16u * 4u;
     s.first = (uint32_t *)p; p += 16u * 4u;
     s.offs = (uint32_t *)p; p += 16u * 4u;
@@ -758,6 +758,12 @@ PP_DEV uint32_t div_small(uint32_t i, uint32_t d)  // floor(i / d) for i, d < 51
 #endif
 }
 
+// Shared layout of the tile's u16 entries: entry q lives at res[res_pos(q)], a skew of one word per
+// 32 words, so that both access patterns are free of bank conflicts: EXPAND (lane t touches
+// entries 16 t + j) and GATHER/CHASE (the lanes of a warp touch 32 consecutive entries).
+PP_DEV uint32_t res_pos(uint32_t q) { return q + ((q >> 6) << 1); }
+PP_HD uint32_t res_entries_for(int T) { return (uint32_t)T * kTileB + (uint32_t)T * kTileB / 32u + 2u; }
+
 PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *idx, uint8_t *outp, uint32_t a,
                            uint32_t total)
 {
@@ -768,56 +774,63 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
     volatile uint16_t *res = sm.res;
     for (uint32_t tb = 0; tb < vend; tb += R) {
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
-        // EXPAND
+        // EXPAND: token pieces -> one entry per byte (a short store loop per piece)
         PP_FOR_T(t)
         {
-            const uint32_t v0 = tb + (uint32_t)t * kTileB;
-            uint32_t r[kTileB];
-#pragma unroll
-            for (int j = 0; j < kTileB; j++) r[j] = 0x8000u;  // bytes outside the window: never stored, never a source
-            if (v0 < vend && v0 + kTileB > a) {
+            const uint32_t q0 = (uint32_t)t * kTileB;          // tile-relative index of the group's first byte
+            const uint32_t v0 = tb + q0;
+            uint32_t lo = v0 < a ? a - v0 : 0u;                // first valid byte of the group
+            uint32_t hi = v0 < vend ? (vend - v0 < (uint32_t)kTileB ? vend - v0 : (uint32_t)kTileB) : 0u;  // one past the last
+            if (lo > hi) lo = hi;
+            // bytes outside the window are never stored and never a source: give them a harmless literal
+            for (uint32_t j = 0; j < lo; j++) res[res_pos(q0 + j)] = 0x8000u;
+            for (uint32_t j = hi; j < (uint32_t)kTileB; j++) res[res_pos(q0 + j)] = 0x8000u;
+            if (lo < hi) {
                 const uint32_t ie = idx[v0 >> 4];
                 uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
-                uint32_t tk = tok[k * (uint32_t)T + sgm];
-                bool fetch = false;
-#pragma unroll
-                for (int j = 0; j < kTileB; j++) {
-                    const uint32_t v = v0 + (uint32_t)j;
-                    if (v >= a && v < vend) {
-                        if (fetch) {
-                            k++;
-                            while (k >= sm.ntok[sgm] && sgm + 1u < (uint32_t)T) { sgm++; k = 0; }
-                            tk = tok[k * (uint32_t)T + sgm];
-                            i = 0;
-                            fetch = false;
-                        }
-                        if (tk & 0x80000000u) {
-                            r[j] = 0x8000u | (tk & 0xffu);
-                            fetch = true;
+                uint32_t nts = sm.ntok[sgm];
+                uint32_t pos = lo;
+                while (pos < hi) {
+                    const uint32_t tk = tok[k * (uint32_t)T + sgm];
+                    if (tk & 0x80000000u) {
+                        res[res_pos(q0 + pos)] = (uint16_t)(0x8000u | (tk & 0xffu));
+                        pos++;
+                    } else {
+                        const uint32_t len = tk >> 15, dist = (tk & 0x7fffu) + 1u;
+                        uint32_t n = len - i;
+                        if (n > hi - pos) n = hi - pos;
+                        if (dist >= len) {
+                            const uint16_t val = (uint16_t)(dist - 1u);
+                            for (uint32_t c = 0; c < n; c++) res[res_pos(q0 + pos + c)] = val;
                         } else {
-                            const uint32_t len = tk >> 15, dist = (tk & 0x7fffu) + 1u;
-                            r[j] = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
-                            if (++i == len) fetch = true;
+                            // overlapping run: byte i repeats the `dist` bytes before the match, so its
+                            // source is dist*(i/dist+1) back — always in front of the match itself
+                            const uint32_t qd = div_small(i, dist);
+                            uint32_t val = dist * (qd + 1u) - 1u, rr = i - qd * dist;
+                            for (uint32_t c = 0; c < n; c++) {
+                                res[res_pos(q0 + pos + c)] = (uint16_t)val;
+                                if (++rr == dist) { rr = 0; val += dist; }
+                            }
                         }
+                        pos += n;
                     }
+                    i = 0;
+                    k++;
+                    while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }
                 }
             }
-            uint4 q0, q1;
-            q0.x = r[0] | (r[1] << 16); q0.y = r[2] | (r[3] << 16); q0.z = r[4] | (r[5] << 16); q0.w = r[6] | (r[7] << 16);
-            q1.x = r[8] | (r[9] << 16); q1.y = r[10] | (r[11] << 16); q1.z = r[12] | (r[13] << 16); q1.w = r[14] | (r[15] << 16);
-            uint4 *dst = reinterpret_cast<uint4 *>(sm.res + (uint32_t)t * kTileB);
-            dst[0] = q0;
-            dst[1] = q1;
         }
         PP_END_T
         PP_SYNC();
+        PP_PHASE(PH_R_EXPAND);
         // GATHER
         PP_FOR_T(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
+            const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);  // entries qb + 32 j sit at pb + 32 j + 2 (j >> 1)
             uint32_t e[kTileB];
 #pragma unroll
-            for (int j = 0; j < kTileB; j++) e[j] = res[qb + (uint32_t)j * 32u];
+            for (int j = 0; j < kTileB; j++) e[j] = res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)];
             uint32_t g[kTileB];
 #pragma unroll
             for (int j = 0; j < kTileB; j++) {
@@ -827,19 +840,21 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
             }
 #pragma unroll
             for (int j = 0; j < kTileB; j++)
-                if (g[j] != 0xffffffffu) res[qb + (uint32_t)j * 32u] = (uint16_t)g[j];
+                if (g[j] != 0xffffffffu) res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)] = (uint16_t)g[j];
         }
         PP_END_T
         PP_SYNC();
+        PP_PHASE(PH_R_GATHER);
         // CHASE + store
         PP_FOR_T(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
+            const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);
             uint32_t e[kTileB];
             uint32_t pend = 0;
 #pragma unroll
             for (int j = 0; j < kTileB; j++) {
-                e[j] = res[qb + (uint32_t)j * 32u];
+                e[j] = res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)];
                 pend |= ~e[j] & 0x8000u;
             }
             while (pend) {
@@ -847,9 +862,9 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
                     if (!(e[j] & 0x8000u)) {
-                        const uint32_t y = res[e[j]];
+                        const uint32_t y = res[res_pos(e[j])];
                         e[j] = y;
-                        res[qb + (uint32_t)j * 32u] = (uint16_t)y;  // publish the hop
+                        res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)] = (uint16_t)y;  // publish the hop
                         pend |= ~y & 0x8000u;
                     }
                 }
@@ -870,6 +885,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         }
         PP_END_T
         PP_SYNC();  // stores visible to the next tile's gathers; res free again
+        PP_PHASE(PH_R_CHASE);
     }
 }
 
