@@ -8,8 +8,10 @@ A "step" is one DecompressAll pass over the whole indexed gzip FASTQ (BASELINE.j
 configs[1]: Generator seed 0, 10 M reads x 150 bp, gzip level 6, chunk 10,000).
   value   : uncompressed GB/s with the compressed bytes and checkpoint windows already in
             HBM (pp_job_execute only: inflate kernel -> scan -> parse kernel)
-  e2e     : same metric through the C ABI with HOST buffers: H2D of the compressed range
-            and windows from pinned memory + kernels + D2H of the per-chunk results, every step
+  e2e     : same metric through the C ABI with HOST buffers, every step: the kernels pull the
+            compressed range and the checkpoint windows from pinned host memory over PCIe while
+            they decode (PP_JOB_ZEROCOPY), and the per-chunk results are copied back to the host;
+            the staged variant (cudaMemcpyAsync H2D first) is reported beside it
   roofline: the parse kernel against the measured HBM copy bandwidth (BASELINE.md §4:
             (U' + 16 R) / t_parse); the inflate kernel is branch/latency bound and is
             reported as decompressed GB/s in "inflate"
@@ -133,6 +135,19 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_ncu_traffic(reads, chunk):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    captures (profiles/ncu_traffic.json), for the workload they were taken on; else nothing."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        for e in json.load(open(p)):
+            if e.get("reads") == reads and e.get("chunk") == chunk:
+                return e.get("dram_bytes_per_launch", {})
+    except Exception:
+        pass
+    return {}
+
+
 def cpu_reference(gz, idx_path, threads, steps, warmup):
     """The host restatement of the reference's parallel DecompressAll, all cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -160,7 +175,6 @@ def main():
     ap.add_argument("--chunk", type=int, default=10_000)
     ap.add_argument("--fixed-len", type=int, default=150)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--zero-copy", action="store_true", help="kernels read pinned host memory directly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -198,6 +212,11 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    # stdout carries exactly ONE JSON line: anything a library prints while we run (NCCL's version
+    # banner, build output) is sent to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -223,70 +242,87 @@ def main():
     gz, gz_ptr = pp.pinned_copy(gz_np)           # pinned host memory: the e2e source buffer
     ix = pp.IndexIO.Deserialize(idx_path)
     dev = pp.Device(local_rank)
-    job = pp.Job(dev, ix, gz.size, 0, -1, zero_copy=args.zero_copy)
+    job = pp.Job(dev, ix, gz.size, 0, -1, zero_copy=False)     # staged: H2D copies, kernels read HBM
+    job_zc = pp.Job(dev, ix, gz.size, 0, -1, zero_copy=True)   # pull: kernels read pinned host memory
 
     def sync():
         torch.cuda.synchronize()
 
-    # correctness gate before timing: one full pass, byte total and record count must be sane
+    # correctness gate before timing: one full pass per mode; totals must agree
     info = job.run(gz)
     if info.status != 0:
         raise SystemExit(f"bench.py: DecompressAll failed status={info.status}")
     U, R, Us = info.total_bytes, info.total_records, info.scanned_bytes
     n_chunks = info.n_chunks
+    h2d_bytes = info.h2d_bytes
+    iz = job_zc.run(gz)
+    if iz.status != 0 or (iz.total_bytes, iz.total_records) != (U, R):
+        raise SystemExit("bench.py: zero-copy DecompressAll disagrees with the staged run")
 
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    # --- kernel-only: inputs resident in HBM ------------------------------------------------
+    def timed(step, steps, warmup):
+        """warmup, barrier+sync, K steps, sync; CUDA events bracket the K steps on the default stream
+        after the library's own stream has been joined (sync() on both sides)."""
+        for _ in range(warmup):
+            step()
+        sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        sync()
+        return (time.perf_counter() - t0) / steps
+
+    # --- kernel-only: inputs resident in HBM (pp_job_execute: inflate -> scan -> parse) -------------
     job.upload(gz_ptr)
     sync()
-    for _ in range(args.warmup):
-        job.execute()
-    sync()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        job.execute()
-    sync()
-    t_dev = (time.perf_counter() - t0) / args.steps
+    t_dev = timed(job.execute, args.steps, args.warmup)
     job.download()
     info = job.info()
     t_inflate, t_parse, t_scan = info.inflate_ms * 1e-3, info.parse_ms * 1e-3, info.scan_ms * 1e-3
     launches_per_step = info.launches
 
-    # --- end to end through the C ABI: H2D + kernels + D2H every step --------------------------
-    for _ in range(2):
-        job.upload(gz_ptr); job.execute(); job.download()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    # --- end to end through the C ABI, host buffers every step ------------------------------------
+    # (a) pull mode: the kernels read the compressed range and the windows from pinned host memory
+    #     (TMA bulk copies over PCIe) while they decode; per-chunk results come back to the host.
+    def step_zc():
+        job_zc.upload(gz_ptr)
+        job_zc.execute()
+        job_zc.download()     # synchronises: per-chunk status, counts, record bases on the host
+    t_e2e = timed(step_zc, args.steps, 2)
+    d2h_bytes = job_zc.info().d2h_bytes
+
+    # (b) staged mode: cudaMemcpyAsync of the same bytes, then the kernels, then the results
+    def step_staged():
         job.upload(gz_ptr)
         job.execute()
-        job.download()     # synchronises: per-chunk status, counts, record bases on the host
-    sync()
-    t_e2e = (time.perf_counter() - t0) / args.steps
-    info2 = job.info()
+        job.download()
+    t_e2e_staged = timed(step_staged, max(2, args.steps // 2), 1)
     barrier()
     clocks = sampler.finish()
 
     # --- optional: also bring every record's line offsets to the host ---------------------------
     t0 = time.perf_counter()
-    job.upload(gz_ptr); job.execute(); job.download()
-    ls = job.line_starts()
+    step_zc()
+    ls = job_zc.line_starts()
     t_e2e_offsets = time.perf_counter() - t0
     del ls
+    info2 = job.info()
 
     # max over ranks
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets, t_e2e_staged], device="cuda",
+                          dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets = [float(x) for x in tt.tolist()]
+        t_dev, t_e2e, t_inflate, t_parse, t_e2e_offsets, t_e2e_staged = [float(x) for x in tt.tolist()]
 
     if rank == 0:
         peak, peak_src = load_peaks()
         b_parse = Us + 16 * R                      # BASELINE.md §4: bytes scanned + four u32 line starts / record
         b_inflate = info2.compressed_bytes + 32768 * n_chunks + U
+        traffic = load_ncu_traffic(args.reads, args.chunk)
         line = {
             "metric": "DecompressAll uncompressed GB/s", "value": world * U / t_dev / 1e9, "unit": "GB/s",
             "reads_per_s": world * R / t_dev,
@@ -294,19 +330,25 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "chunks": n_chunks, "records": R, "uncompressed_bytes": U,
                        "compressed_bytes": info2.compressed_bytes, "per_gpu": "full workload per rank",
-                       "l2": "inputs larger than L2 (0.9 GB compressed, 3.8 GB inflated per step)",
-                       "zero_copy": bool(args.zero_copy)},
+                       "l2": "inputs larger than L2 (0.9 GB compressed in, 3.8 GB inflated out per step vs 126 MB L2)"},
             "e2e": {"value": world * U / t_e2e / 1e9, "unit": "GB/s", "reads_per_s": world * R / t_e2e,
-                    "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": info2.h2d_bytes,
-                    "d2h_bytes_per_step": info2.d2h_bytes,
+                    "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "mode": "pull: kernels read the compressed range + checkpoint windows from pinned host memory",
+                    "staged_copy": {"value": world * U / t_e2e_staged / 1e9, "unit": "GB/s",
+                                    "ms_per_step": t_e2e_staged * 1e3,
+                                    "mode": "cudaMemcpyAsync H2D, then kernels, then D2H of results"},
                     "with_line_offsets_to_host": {"value": world * U / t_e2e_offsets / 1e9, "unit": "GB/s",
-                                                  "d2h_bytes_per_step": info2.d2h_bytes + 16 * R}},
+                                                  "d2h_bytes_per_step": d2h_bytes + 16 * R}},
             "roofline": {"kernel": "pp_parse_kernel", "bound": "hbm", "achieved": b_parse / t_parse / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": b_parse / t_parse / 1e9 / peak, "traffic": None,
-                         "algorithmic_bytes": b_parse, "ms": t_parse * 1e3, "peak_source": peak_src},
-            "inflate": {"kernel": "pp_inflate_kernel", "bound": "latency/branch (serial Huffman decode per chunk)",
+                         "peak": peak, "unit": "GB/s", "frac": b_parse / t_parse / 1e9 / peak,
+                         "traffic": traffic.get("pp_parse_kernel"),
+                         "algorithmic_bytes": b_parse, "ms": t_parse * 1e3, "peak_source": peak_src,
+                         "timing": "CUDA events on the library stream around the kernel, last timed step"},
+            "inflate": {"kernel": "pp_inflate_kernel",
+                        "bound": "instruction issue / shared-memory latency (Huffman decode + LZ77 resolve), not HBM",
                         "decompressed_gbs": U / t_inflate / 1e9, "ms": t_inflate * 1e3,
-                        "bytes_moved": b_inflate, "hbm_frac": b_inflate / t_inflate / 1e9 / peak,
+                        "algorithmic_bytes": b_inflate, "hbm_frac": b_inflate / t_inflate / 1e9 / peak,
+                        "traffic": traffic.get("pp_inflate_kernel"),
                         "share_of_step": t_inflate / t_dev},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
@@ -315,8 +357,13 @@ def main():
             dt, recs, nbytes = cpu_reference(gz_np, idx_path, cores, 2, 1)
             assert recs == R and nbytes == U, (recs, R, nbytes, U)
             line["cpu_baseline"] = {"value": nbytes / dt / 1e9, "unit": "GB/s", "reads_per_s": recs / dt,
-                                    "cores": cores, "kind": "port", "sample": "whole workload (2 timed passes)"}
+                                    "cores": cores, "kind": "port",
+                                    "sample": "whole workload, 2 timed passes after 1 warm-up (oracle thread pool)"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    job_zc.free()
     job.free()
     L.pp_host_free(gz_ptr)
     if world > 1:

@@ -15,6 +15,8 @@
 // no concatenation or copy is needed.  Output is structure-of-arrays: four u32
 // arrays (one per FASTQ line) holding, for every record, the combined-memory index
 // of the first byte of that line.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace pp {
@@ -37,7 +39,7 @@ __device__ __forceinline__ uint32_t nibble(uint32_t t) { return ((t >> 7) * 0x01
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
@@ -94,22 +96,35 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
 
     // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
     uint32_t m[kTileIters][kRows];
+    const uint32_t last_vec = (span - 1u) >> 4;  // loads past the end are clamped to the last vector and masked out
 #pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
+    for (int half = 0; half < kTileIters; half += 2) {
+        uint4 v[2][kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            const uint32_t off = t0 + (uint32_t)it * kIterBytes + (uint32_t)warp * kWarpBytes + (uint32_t)r * 512u +
-                                 (uint32_t)lane * 16u;
-            uint32_t mask = 0;
-            if (off < span) {
-                const uint4 v = ld_stream(vec0 + (off >> 4));
-                mask = nibble(nl_bytes(v.x)) | (nibble(nl_bytes(v.y)) << 4) | (nibble(nl_bytes(v.z)) << 8) |
-                       (nibble(nl_bytes(v.w)) << 12);
-                // bytes outside [head, span) are not part of the chunk
-                if (off < head) mask &= 0xffffu << (head - off);
-                if (off + 16u > span) mask &= 0xffffu >> (off + 16u - span);
+        for (int i2 = 0; i2 < 2; i2++) {
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const uint32_t off = t0 + (uint32_t)(half + i2) * kIterBytes + (uint32_t)warp * kWarpBytes +
+                                     (uint32_t)r * 512u + (uint32_t)lane * 16u;
+                const uint32_t vi = off >> 4;
+                v[i2][r] = ld_stream(vec0 + (vi < last_vec ? vi : last_vec));
             }
-            m[it][r] = mask;
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 2; i2++) {
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const uint32_t off = t0 + (uint32_t)(half + i2) * kIterBytes + (uint32_t)warp * kWarpBytes +
+                                     (uint32_t)r * 512u + (uint32_t)lane * 16u;
+                const uint4 x = v[i2][r];
+                uint32_t mask = nibble(nl_bytes(x.x)) | (nibble(nl_bytes(x.y)) << 4) | (nibble(nl_bytes(x.z)) << 8) |
+                                (nibble(nl_bytes(x.w)) << 12);
+                // bytes outside [head, span) are not part of the chunk
+                if (off >= span) mask = 0;
+                if (off < head) mask &= 0xffffu << (head - off);
+                if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
+                m[half + i2][r] = mask;
+            }
         }
     }
     // 2. per-row counts, packed two per register, inclusive warp scans
@@ -240,7 +255,7 @@ return true;
 
 
 // order 0: ticket = global tile number (tile_base[k] + i); order 1: ticket = i * n + k
-__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel(const uint8_t *__restrict__ slots,
+__global__ void __launch_bounds__(kParseThreads, 3) pp_parse_kernel(const uint8_t *__restrict__ slots,
                                                                  const ParseDesc *__restrict__ pdesc, int n,
                                                                  const uint32_t *__restrict__ tile_base,
                                                                  uint32_t n_tickets, int order,
@@ -493,7 +508,8 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
     uint32_t *ticket = reinterpret_cast<uint32_t *>(work + total_tiles);
     // round-robin over the chunks unless very uneven chunks would waste most tickets
     const uint64_t rr = (uint64_t)max_tiles * (uint64_t)n;
-    const int order = rr <= 4ull * total_tiles && rr < 0xffffffffull ? 1 : 0;
+    int order = rr <= 4ull * total_tiles && rr < 0xffffffffull ? 1 : 0;
+    if (const char *e = getenv("PPB200_PARSE_ORDER")) order = atoi(e) ? order : 0;  // 0 forces linear tickets
     const uint32_t n_tickets = order ? (uint32_t)rr : total_tiles;
     const uint32_t resident = (uint32_t)sm_count * (2048u / kParseThreads);
     const uint32_t grid = n_tickets < resident ? n_tickets : resident;
