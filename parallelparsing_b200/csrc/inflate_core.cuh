@@ -118,10 +118,11 @@ PP_HD uint32_t map_cap_for(int T)
     const uint32_t c = (uint32_t)T * (uint32_t)kSubW * 4u * 8u;  // 8x expansion of a full window
     return c > kMinMapCap ? c : kMinMapCap;
 }
-// Per-CTA scratch in global memory (u32 words): the token rows of a window — token k of
-// sub-sequence s at tok[k * T + s], so the lanes of a warp store one row segment together —
-// followed by the group index (one word per 16 output bytes).
-constexpr int kTokRows = kSubBits + 8;  // a sub-sequence holds at most kSubBits symbols
+// Per-CTA scratch in global memory (u32 words): the tokens of a window — token k of
+// sub-sequence s at tok[s * kTokRows + k], so the tokens one 16-byte output group needs are
+// neighbours in memory (one or two sectors, fetched in a single round trip) — followed by
+// the group index (one word per 16 output bytes).
+constexpr int kTokRows = kSubBits + 16;  // a sub-sequence holds at most kSubBits symbols (+ read-ahead slack)
 PP_HD uint32_t tok_words_for(int T) { return (uint32_t)kTokRows * (uint32_t)T; }
 PP_HD uint32_t idx_words_for(int T) { return map_cap_for(T) / 16u + 16u; }
 PP_HD size_t scratch_words_for(int T) { return (size_t)tok_words_for(T) + idx_words_for(T); }
@@ -639,7 +640,7 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 
 // ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
 // Decodes the symbols that START in [start, limit) (window-relative bits).
-// WRITE: also emits one TOKEN per symbol, token k of this thread at tok[k * T + t]
+// WRITE: also emits one TOKEN per symbol, token k of this thread at tok[t * kTokRows + k]
 //   literal: 0x80000000 | byte        match: len << 15 | (dist - 1)
 // and, for every multiple of 16 below oclip that a token's output range [o, o + len) covers,
 // the GROUP INDEX entry idx[m / 16] = t | k << 10 | (m - o) << 20, which tells the resolve
@@ -673,7 +674,7 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
         if (kind == K_LIT) {
             if (WRITE) {
                 const uint32_t p0 = o + out;
-                tok[k * T + t] = tok_lit(e_val(e) & 0xffu);
+                tok[t * (uint32_t)kTokRows + k] = tok_lit(e_val(e) & 0xffu);
                 if ((p0 & 15u) == 0u && p0 < oclip) idx[p0 >> 4] = idx_pack(t, k, 0);
                 k++;
             }
@@ -699,7 +700,7 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
             // the reference primes a full 32 KB dictionary (Core.cs:158)
             if (WRITE) {
                 const uint32_t p0 = o + out;
-                tok[k * T + t] = tok_match(len, dist);
+                tok[t * (uint32_t)kTokRows + k] = tok_match(len, dist);
                 uint32_t end = p0 + len;
                 if (end > oclip) end = oclip;
                 for (uint32_t m = (p0 + 15u) & ~15u; m < end; m += 16u) idx[m >> 4] = idx_pack(t, k, m - p0);
@@ -774,7 +775,8 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
     volatile uint16_t *res = sm.res;
     for (uint32_t tb = 0; tb < vend; tb += R) {
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
-        // EXPAND: token pieces -> one entry per byte (a short store loop per piece)
+        // EXPAND: tokens -> one entry per byte.  Uniform control flow: sixteen predicated byte steps
+        // over a register queue of the group's next eight tokens (neighbours in memory, one round trip).
         PP_FOR_T(t)
         {
             const uint32_t q0 = (uint32_t)t * kTileB;          // tile-relative index of the group's first byte
@@ -782,43 +784,45 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
             uint32_t lo = v0 < a ? a - v0 : 0u;                // first valid byte of the group
             uint32_t hi = v0 < vend ? (vend - v0 < (uint32_t)kTileB ? vend - v0 : (uint32_t)kTileB) : 0u;  // one past the last
             if (lo > hi) lo = hi;
-            // bytes outside the window are never stored and never a source: give them a harmless literal
-            for (uint32_t j = 0; j < lo; j++) res[res_pos(q0 + j)] = 0x8000u;
-            for (uint32_t j = hi; j < (uint32_t)kTileB; j++) res[res_pos(q0 + j)] = 0x8000u;
+            uint32_t r[kTileB / 2];                            // entries, two per word
+#pragma unroll
+            for (int j = 0; j < kTileB / 2; j++) r[j] = 0x80008000u;  // bytes outside the window: harmless literals
             if (lo < hi) {
                 const uint32_t ie = idx[v0 >> 4];
                 uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
-                uint32_t nts = sm.ntok[sgm];
                 uint32_t pos = lo;
                 while (pos < hi) {
-                    const uint32_t tk = tok[k * (uint32_t)T + sgm];
-                    if (tk & 0x80000000u) {
-                        res[res_pos(q0 + pos)] = (uint16_t)(0x8000u | (tk & 0xffu));
-                        pos++;
-                    } else {
-                        const uint32_t len = tk >> 15, dist = (tk & 0x7fffu) + 1u;
-                        uint32_t n = len - i;
-                        if (n > hi - pos) n = hi - pos;
-                        if (dist >= len) {
-                            const uint16_t val = (uint16_t)(dist - 1u);
-                            for (uint32_t c = 0; c < n; c++) res[res_pos(q0 + pos + c)] = val;
-                        } else {
-                            // overlapping run: byte i repeats the `dist` bytes before the match, so its
-                            // source is dist*(i/dist+1) back — always in front of the match itself
-                            const uint32_t qd = div_small(i, dist);
-                            uint32_t val = dist * (qd + 1u) - 1u, rr = i - qd * dist;
-                            for (uint32_t c = 0; c < n; c++) {
-                                res[res_pos(q0 + pos + c)] = (uint16_t)val;
-                                if (++rr == dist) { rr = 0; val += dist; }
+                    uint32_t nts = sm.ntok[sgm];
+                    while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }  // next segment holding tokens
+                    const uint32_t *tp = tok + sgm * (uint32_t)kTokRows + k;
+                    uint32_t t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3], t4 = tp[4], t5 = tp[5], t6 = tp[6], t7 = tp[7];
+                    uint32_t avail = nts - k < 8u ? nts - k : 8u;  // tokens of this segment in the queue
+#pragma unroll
+                    for (int j = 0; j < kTileB; j++) {
+                        if ((uint32_t)j == pos && pos < hi && avail) {
+                            uint32_t val;
+                            bool adv;
+                            if (t0 & 0x80000000u) {
+                                val = 0x8000u | (t0 & 0xffu);
+                                adv = true;
+                            } else {
+                                const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;
+                                // overlapping run: byte i repeats the `dist` bytes before the match, so its
+                                // source is dist*(i/dist+1) back — always in front of the match itself
+                                val = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
+                                adv = ++i == len;
                             }
+                            r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (val << 16) : (r[j >> 1] & 0xffff0000u) | val;
+                            pos++;
+                            if (adv) { t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = t6; t6 = t7; i = 0; k++; avail--; }
                         }
-                        pos += n;
                     }
-                    i = 0;
-                    k++;
-                    while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }
                 }
             }
+            // entries 16 t + j sit at res_pos(16 t) + j: eight aligned words
+            volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(sm.res + res_pos(q0));
+#pragma unroll
+            for (int j = 0; j < kTileB / 2; j++) dst[j] = r[j];
         }
         PP_END_T
         PP_SYNC();
@@ -828,19 +832,28 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
             const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);  // entries qb + 32 j sit at pb + 32 j + 2 (j >> 1)
-            uint32_t e[kTileB];
+            // Unconditional loads (lanes with nothing to fetch read one shared, always valid byte), so
+            // that the eight loads of a batch are in flight together instead of one per branch.
+            const int32_t safe = near_lo - 1;  // the byte just before the tile/window: final, inside the slot
 #pragma unroll
-            for (int j = 0; j < kTileB; j++) e[j] = res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)];
-            uint32_t g[kTileB];
+            for (int h = 0; h < kTileB; h += 8) {
+                uint32_t e[8];
+                int32_t sv[8];
+                uint32_t b[8];
 #pragma unroll
-            for (int j = 0; j < kTileB; j++) {
-                const int32_t sv = (int32_t)(tb + qb + (uint32_t)j * 32u) - (int32_t)e[j] - 1;  // virtual index of the source
-                g[j] = 0xffffffffu;
-                if (!(e[j] & 0x8000u)) g[j] = sv < near_lo ? 0x8000u | (uint32_t)vbase[sv] : (uint32_t)(sv - (int32_t)tb);
+                for (int j = 0; j < 8; j++) {
+                    e[j] = res[pb + (uint32_t)(h + j) * 32u + 2u * (uint32_t)((h + j) >> 1)];
+                    sv[j] = (int32_t)(tb + qb + (uint32_t)(h + j) * 32u) - (int32_t)e[j] - 1;  // virtual index of the source
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) b[j] = vbase[(!(e[j] & 0x8000u) && sv[j] < near_lo) ? sv[j] : safe];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!(e[j] & 0x8000u))
+                        res[pb + (uint32_t)(h + j) * 32u + 2u * (uint32_t)((h + j) >> 1)] =
+                            (uint16_t)(sv[j] < near_lo ? 0x8000u | b[j] : (uint32_t)(sv[j] - (int32_t)tb));
+                }
             }
-#pragma unroll
-            for (int j = 0; j < kTileB; j++)
-                if (g[j] != 0xffffffffu) res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)] = (uint16_t)g[j];
         }
         PP_END_T
         PP_SYNC();
