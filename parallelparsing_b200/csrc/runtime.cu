@@ -483,19 +483,14 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
 static int job_parse_stage(pp_job *j, cudaStream_t st, bool with_pout_flags, int *launches)
 {
     const int n = j->n;
-    if (launch_exact_count(j->d_slots, j->d_descs, j->d_results, with_pout_flags ? j->d_pout : nullptr, n, j->d_exact,
-                           st) != cudaSuccess)
-        return PP_E_CUDA;
-    if (launch_scan(j->d_descs, j->d_results, j->d_exact, n, (j->flags & PP_JOB_STRICT) ? 1u : 0u, j->rec_cap,
-                    j->d_pdesc, j->d_pout, j->d_totals, st) != cudaSuccess)
-        return PP_E_CUDA;
+    CK(launch_exact_count(j->d_slots, j->d_descs, j->d_results, with_pout_flags ? j->d_pout : nullptr, n, j->d_exact, st));
+    CK(launch_scan(j->d_descs, j->d_results, j->d_exact, n, (j->flags & PP_JOB_STRICT) ? 1u : 0u, j->rec_cap, j->d_pdesc,
+                   j->d_pout, j->d_totals, st));
     CK(cudaEventRecord(j->ev[4], st));
-    if (launch_parse(j->d_slots, j->d_pdesc, n, j->d_tile_base, j->total_tiles, j->max_tiles, j->d_lines, j->rec_cap, j->d_pout,
-                     j->d_totals, j->d_parse_work, j->ctx->sm_count, st) != cudaSuccess)
-        return PP_E_CUDA;
+    CK(launch_parse(j->d_slots, j->d_pdesc, n, j->d_tile_base, j->total_tiles, j->max_tiles, j->d_lines, j->rec_cap,
+                    j->d_pout, j->d_totals, j->d_parse_work, j->ctx->sm_count, st));
     CK(cudaEventRecord(j->ev[5], st));
-    if (launch_exact_emit(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st) != cudaSuccess)
-        return PP_E_CUDA;
+    CK(launch_exact_emit(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st));
     *launches += n > 0 ? 4 : 1;
     return PP_OK;
 }
@@ -519,9 +514,8 @@ int pp_job_execute(pp_job *j)
         lead = (const uint8_t *)dp;
         comp_bytes = align_up(j->comp_copy, kTile) + kTile;  // pp_host_alloc keeps spare tiles behind the data
     }
-    if (launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
-                       st) != cudaSuccess)
-        return PP_E_CUDA;
+    CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
+                      st));
     launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)
     CK(cudaEventRecord(j->ev[3], st));
     int rc = job_parse_stage(j, st, false, &launches);

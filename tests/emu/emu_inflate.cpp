@@ -23,6 +23,8 @@ int emu_inflate_chunk(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t 
     ppinf::ChunkResult r;
     uint8_t *raw = (uint8_t *)aligned_alloc(128, ppinf::sm_bytes_for(T));
     uint32_t *map = (uint32_t *)aligned_alloc(128, (ppinf::scratch_words_for(T) * 4 + 127) / 128 * 128);
+    memset(map, 0xff, ppinf::scratch_words_for(T) * 4);  // scratch is never zero on the device either
+    memset(raw, 0xff, ppinf::sm_bytes_for(T));
     ppinf::Sm sm;
     ppinf::sm_carve(sm, raw, T);
     uint32_t phase = 0;
