@@ -94,9 +94,16 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
     uint32_t *const l_base = lines + d.rec_base;
     if (threadIdx.x == 0 && ti == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
 
+    // the byte right after the tile (successor of its last vector), fetched with the tile's loads
+    uint32_t tile_next = 0;
+    {
+        const uint32_t nxt = t0 + (uint32_t)kTileBytesP;
+        if (warp == kParseWarps - 1 && lane == 31 && nxt >= head && nxt < span) tile_next = data[nxt - head];
+    }
     // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
     uint32_t m[kTileIters][kRows];
     const uint32_t last_vec = (span - 1u) >> 4;  // loads past the end are clamped to the last vector and masked out
+    const bool edge = t0 == 0u || t0 + (uint32_t)kTileBytesP > span;  // block-uniform
 #pragma unroll
     for (int half = 0; half < kTileIters; half += 2) {
         uint4 v[2][kRows];
@@ -119,10 +126,12 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
                 const uint4 x = v[i2][r];
                 uint32_t mask = nibble(nl_bytes(x.x)) | (nibble(nl_bytes(x.y)) << 4) | (nibble(nl_bytes(x.z)) << 8) |
                                 (nibble(nl_bytes(x.w)) << 12);
-                // bytes outside [head, span) are not part of the chunk
-                if (off >= span) mask = 0;
-                if (off < head) mask &= 0xffffu << (head - off);
-                if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
+                // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
+                if (edge) {
+                    if (off >= span) mask = 0;
+                    if (off < head) mask &= 0xffffu << (head - off);
+                    if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
+                }
                 m[half + i2][r] = mask;
             }
         }
@@ -149,7 +158,10 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
     for (int it = 0; it < kTileIters; it++) {
         t01[it] = __shfl_sync(0xffffffffu, s01[it], 31);
         t23[it] = __shfl_sync(0xffffffffu, s23[it], 31);
-        if (lane == 0) warp_tot[it][warp] = (t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16);
+        // bit 31: the block's first byte is a newline (the successor bit of the block before it)
+        if (lane == 0)
+            warp_tot[it][warp] = ((t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16)) |
+                                 ((m[it][0] & 1u) << 31);
     }
     __syncthreads();
     uint32_t before[kTileIters], all = 0;
@@ -158,7 +170,7 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
         before[it] = all;
 #pragma unroll
         for (int w = 0; w < kParseWarps; w++) {
-            const uint32_t t = warp_tot[it][w];
+            const uint32_t t = warp_tot[it][w] & 0x7fffffffu;
             if (w < warp) before[it] += t;
             all += t;
         }
@@ -214,8 +226,13 @@ __device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots,
         const uint32_t fb0 = __shfl_sync(0xffffffffu, fb, 0);
         if (lane == 31) {
             nfb = fb0 >> 1;  // rows 0..2 continue at lane 0 of the next row
-            const uint32_t nxt = wbase + (uint32_t)kWarpBytes;  // first byte after this warp's block
-            if (nxt >= head && nxt < span && data[nxt - head] == '\n') nfb |= 1u << (kRows - 1);
+            // first byte after this warp's block: the next warp's block, the next step's first
+            // block, or (last block of the tile) the byte fetched above
+            uint32_t nb;
+            if (warp + 1 < kParseWarps) nb = warp_tot[it][warp + 1] >> 31;
+            else if (it + 1 < kTileIters) nb = warp_tot[it + 1][0] >> 31;
+            else nb = tile_next == '\n';
+            nfb |= nb << (kRows - 1);
         }
         const uint32_t tot0 = t01[it] & 0xffffu, tot1 = t01[it] >> 16, tot2 = t23[it] & 0xffffu;
         const uint32_t bef = run + before[it];
