@@ -5,9 +5,9 @@ The product is libppb200.so (C ABI: include/ppb200.h) — hand-written CUDA kern
 plus a C++ host runtime.  This package is the host-side mirror of the reference's
 interface for that path (see api.py) and the in-tree build driver (build.py).
 """
-from .api import (BatchedFASTQ, Core, Device, FastqRecord, Index, IndexIO, Job, Parsing, Point, ZException,
+from .api import (BatchedFASTQ, Core, Device, FastqRecord, Index, IndexIO, Job, PairedFASTQ, Parsing, Point, ZException,
                   fields_from_line_starts, pinned_copy)
 from ._lib import LIB_PATH, SYMBOLS, lib
 
-__all__ = ["BatchedFASTQ", "Core", "Device", "FastqRecord", "Index", "IndexIO", "Job", "Parsing", "Point",
+__all__ = ["BatchedFASTQ", "Core", "Device", "FastqRecord", "Index", "IndexIO", "Job", "PairedFASTQ", "Parsing", "Point",
            "ZException", "fields_from_line_starts", "pinned_copy", "LIB_PATH", "SYMBOLS", "lib"]

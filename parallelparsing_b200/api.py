@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import WINSIZE, ZException, check, lib
 
-__all__ = ["Device", "Index", "Point", "IndexIO", "Core", "Parsing", "BatchedFASTQ", "FastqRecord", "Job",
+__all__ = ["Device", "Index", "Point", "IndexIO", "Core", "Parsing", "BatchedFASTQ", "PairedFASTQ", "FastqRecord", "Job",
            "ZException", "pinned_copy"]
 
 
@@ -354,3 +354,32 @@ def pinned_copy(a: np.ndarray):
     view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(a.size,))
     view[:] = a
     return view, p
+
+
+class PairedFASTQ:
+    """Paired-end R1/R2 (BASELINE config 3).  The reference has no paired-end code (README.md:9
+    only names it), so this is new design kept minimal: the two files are decoded as two
+    DecompressAll jobs on the same GPU and records are paired by their GLOBAL ordinal — record r
+    of R1 with record r of R2 — which the per-chunk `record_base` prefix sums provide without
+    requiring both files to cut their chunks at the same records (checkpoints sit on deflate block
+    boundaries, which differ between the files).  Quirk H1 (a duplicate record when a checkpoint
+    falls on a record boundary) would shift the ordinals of one file only, so both jobs run with
+    PP_JOB_STRICT.  Iteration yields (FastqRecord, FastqRecord) pairs."""
+
+    def __init__(self, index1, gzip1, index2, gzip2, device=None):
+        self._a = BatchedFASTQ(index1, gzip1, device=device, strict=True)
+        self._b = BatchedFASTQ(index2, gzip2, device=device, strict=True)
+
+    def Count(self):
+        n1, n2 = self._a.Count(), self._b.Count()
+        if n1 != n2:
+            raise ValueError(f"R1 holds {n1} records, R2 holds {n2}: not a paired-end pair of files")
+        return n1
+
+    def __iter__(self):
+        self.Count()
+        return zip(iter(self._a), iter(self._b))
+
+    def Dispose(self):
+        self._a.Dispose()
+        self._b.Dispose()

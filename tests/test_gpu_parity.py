@@ -188,3 +188,95 @@ def test_corrupt_stream_reports_data_error(device):
         assert job.chunk(1).status == 0 and np.array_equal(job.chunk_bytes(1), ref)
     assert job.chunk(0).status == 0
     job.free()
+
+
+def test_golden_fixture(device):
+    """Committed fixture (tests/golden): expected values do not depend on the oracle being rebuilt."""
+    import hashlib
+    import json
+    import os
+    import parallelparsing_b200 as pp
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    G = json.load(open(os.path.join(gold, "golden.json")))
+    gz = np.fromfile(os.path.join(gold, "gen600.fastq.gz"), np.uint8)
+    ix = pp.IndexIO.Deserialize(os.path.join(gold, "gen600.chunk50.gzi"))
+    job = pp.Job(device, ix, gz.size)
+    info = job.run(gz)
+    assert info.status == 0 and info.total_records == G["total_records"] and info.n_chunks == len(G["chunks"])
+    l0, l1, l2, l3 = job.line_starts()
+    for k, c in enumerate(G["chunks"]):
+        ci = job.chunk(k)
+        assert (ci.inflated, ci.records) == (c["inflated"], c["records"])
+        assert hashlib.md5(job.chunk_bytes(k).tobytes()).hexdigest() == c["bytes_md5"]
+        s = slice(ci.record_base, ci.record_base + ci.records)
+        f = pp.fields_from_line_starts(l0[s], l1[s], l2[s], l3[s], ci.parse_end)
+        assert hashlib.md5(f.astype("<i8").tobytes()).hexdigest() == c["fields_md5"]
+    job.free()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partitioned_ranges_equal_whole(device, world):
+    """Multi-GPU sharding: contiguous chunk ranges decoded as separate jobs (here on one
+    GPU) give exactly the whole-file result; global record ordinals come from the per-range counts."""
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200.shard import partition_chunks, record_bases
+    fq = corpus.fastq(30000, fixed=150)
+    gz = corpus.gz_member(fq, 6)
+    ix = pp.Core.BuildDeflateIndex(gz, 2000)
+    whole = pp.Job(device, ix, gz.size)
+    wi = whole.run(gz)
+    parts = partition_chunks(ix.scalars()[1], world)
+    counts, cat = [], []
+    for first, n in parts:
+        j = pp.Job(device, ix, gz.size, first, n)
+        info = j.run(gz)
+        assert info.status == 0 and info.n_chunks == n
+        for k in range(n):
+            a, b = j.chunk(k), whole.chunk(first + k)
+            assert (a.inflated, a.records, a.parse_end) == (b.inflated, b.records, b.parse_end)
+        counts.append(info.total_records)
+        cat.append(j.all_bytes().tobytes())
+        j.free()
+    assert sum(counts) == wi.total_records and b"".join(cat) == fq
+    bases = record_bases(counts)
+    assert [whole.chunk(f).record_base if n else None for f, n in parts] == \
+        [int(b) if n else None for b, (f, n) in zip(bases, parts)]
+    whole.free()
+
+
+def test_zero_copy_matches_staged(device):
+    """PP_JOB_ZEROCOPY: kernels pull the compressed bytes and windows from pinned host memory."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(20000, fixed=150)
+    gz_np = corpus.gz_parallel(fq, 6, segment=1 << 20)
+    gz, ptr = pp.pinned_copy(gz_np)
+    ix = pp.Core.BuildDeflateIndex(gz_np, 1000)
+    a = pp.Job(device, ix, gz.size)
+    b = pp.Job(device, ix, gz.size, zero_copy=True)
+    ia = a.run(gz)
+    b.upload(ptr); b.execute(); b.download()
+    ib = b.info()
+    assert (ia.status, ia.total_records, ia.total_bytes) == (ib.status, ib.total_records, ib.total_bytes) == (0, ia.total_records, len(fq))
+    assert b.all_bytes().tobytes() == fq
+    for x, y in zip(a.line_starts(), b.line_starts()):
+        assert np.array_equal(x, y)
+    a.free(); b.free()
+    pp.lib().pp_host_free(ptr)
+
+
+def test_paired_end_pairs_by_global_ordinal(device):
+    """BASELINE config 3 (small): R1/R2 from two Generator streams with the same read count."""
+    import parallelparsing_b200 as pp
+    r1, r2 = corpus.fastq(6000, fixed=150, seed=0), corpus.fastq(6000, fixed=150, seed=1)
+    g1, g2 = corpus.gz_member(r1, 6), corpus.gz_member(r2, 1)   # different block boundaries on purpose
+    i1, i2 = pp.Core.BuildDeflateIndex(g1, 1000), pp.Core.BuildDeflateIndex(g2, 700)
+    pe = pp.PairedFASTQ(i1, g1, i2, g2, device=device)
+    assert pe.Count() == 6000
+    l1, l2 = r1.split(b"\n"), r2.split(b"\n")
+    n = 0
+    for a, b in pe:
+        assert a.Identifier.encode() == l1[4 * n][1:] and b.Identifier.encode() == l2[4 * n][1:]
+        assert a.Sequence.encode() == l1[4 * n + 1] and b.Quality.encode() == l2[4 * n + 3]
+        n += 1
+    assert n == 6000
+    pe.Dispose()
