@@ -726,6 +726,99 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
     return r;
 }
 
+// GUESS / SYNC walk of one segment with CHECKPOINTS.  Slot c (c = 0..kCkpt-1) of a thread is the
+// first symbol boundary at or after bit tgt0 + c * kCkptStep of its sub-sequence, stored as
+// {position, output bytes from there to the end of the segment}.  A decoder that restarts at a
+// corrected bit falls back onto the old path's boundaries after a few symbols; as soon as it
+// stands exactly on the old path's boundary for the slot it is passing, the rest of the segment is
+// already known: it stops there and reuses the stored suffix (end, flag and later slots are
+// unchanged), so a SYNC round costs a fraction of a full pass.  cp: [2 * kCkpt][T] words,
+// positions first, then suffixes (aliases the resolve tile buffer, which is idle while decoding).
+constexpr int kCkpt = 3;
+constexpr uint32_t kCkptStep = (uint32_t)kSubBits / (kCkpt + 1);
+constexpr uint32_t kNoCkpt = 0xffffffffu;
+
+PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t tgt0, uint32_t *cp, uint32_t T,
+                        uint32_t t, bool have_old, uint32_t old_end, uint32_t old_flag)
+{
+    const uint32_t *cw = sm.cw;
+    uint32_t wp = start >> 5;
+    const uint32_t sh = start & 31u;
+    uint64_t buf = ((uint64_t)cw[wp] | ((uint64_t)cw[wp + 1] << 32)) >> sh;
+    uint32_t cnt = 64u - sh;
+    wp += 2;
+    uint32_t out = 0, flag = F_NONE;
+    uint32_t c = 0, next_t = tgt0;
+    uint32_t npos0 = kNoCkpt, npos1 = kNoCkpt, npos2 = kNoCkpt, ncum0 = 0, ncum1 = 0, ncum2 = 0;
+    bool reused = false;
+    for (;;) {
+        const uint32_t pos = wp * 32u - cnt;
+        if (pos >= limit) break;
+        if (pos >= next_t && c < (uint32_t)kCkpt) {
+            if (have_old && cp[c * T + t] == pos) {  // on the old path: the rest is known
+                out += cp[((uint32_t)kCkpt + c) * T + t];
+                reused = true;
+                break;
+            }
+            if (c == 0) { npos0 = pos; ncum0 = out; }
+            else if (c == 1) { npos1 = pos; ncum1 = out; }
+            else { npos2 = pos; ncum2 = out; }
+            c++;
+            next_t += kCkptStep;
+        }
+        if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+        uint32_t lo = (uint32_t)buf;
+        uint32_t e = sm.lit[lo & ((1u << kRootL) - 1u)];
+        if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
+        const uint32_t kind = e_kind(e), tot = e_tot(e);
+        if (kind == K_LIT) {
+            out++;
+            buf >>= tot;
+            cnt -= tot;
+            continue;
+        }
+        if (kind == K_BASE) {
+            const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
+            buf >>= tot;
+            cnt -= tot;
+            if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+            lo = (uint32_t)buf;
+            uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
+            if (e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
+            if (e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
+            const uint32_t dtot = e_tot(d);
+            buf >>= dtot;
+            cnt -= dtot;
+            out += len;
+            continue;
+        }
+        if (kind == K_EOB) {
+            buf >>= tot;
+            cnt -= tot;
+            flag = F_EOB;
+            break;
+        }
+        flag = F_BAD;  // invalid literal/length code
+        break;
+    }
+    Seg r;
+    if (reused) {
+        r.end = old_end;
+        r.flag = old_flag;
+    } else {
+        r.end = wp * 32u - cnt;
+        r.flag = flag;
+        for (uint32_t j = c; j < (uint32_t)kCkpt; j++) cp[j * T + t] = kNoCkpt;  // slots the new path never reached
+    }
+    r.out = out;
+    r.ntok = 0;
+    // slots passed on the way (before the reuse point, or all of them) now describe the new path
+    if (c > 0) { cp[0 * T + t] = npos0; cp[((uint32_t)kCkpt + 0) * T + t] = out - ncum0; }
+    if (c > 1) { cp[1 * T + t] = npos1; cp[((uint32_t)kCkpt + 1) * T + t] = out - ncum1; }
+    if (c > 2) { cp[2 * T + t] = npos2; cp[((uint32_t)kCkpt + 2) * T + t] = out - ncum2; }
+    return r;
+}
+
 struct WindowOut {
     uint32_t next_bit;   // window-relative bit after the last symbol used
     uint32_t produced;   // output bytes (clipped to the room left)
@@ -908,11 +1001,13 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
                                 uint32_t room)
 {
     const int T = PP_NT;
+    uint32_t *cp = reinterpret_cast<uint32_t *>(sm.res);  // checkpoints live in the (idle) resolve tile buffer
     // GUESS
     PP_FOR_T(t)
     {
         const uint32_t st = s0 + (uint32_t)t * kSubBits;
-        const Seg r = decode_seg<0>(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, nullptr, nullptr, 0, 0, 0, 0);
+        const Seg r = decode_count(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, st + kCkptStep, cp, (uint32_t)T, (uint32_t)t,
+                                   false, 0, 0);
         sm.start[t] = st;
         sm.end[t] = r.end;
         sm.outc[t] = r.out;
@@ -948,8 +1043,12 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
             if ((uint32_t)t >= m && ns != sm.start[t]) {
                 const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
                 Seg r;
-                if (ns >= lim) { r.end = ns; r.out = 0; r.flag = F_NONE; r.ntok = 0; }
-                else r = decode_seg<0>(sm, ns, lim, nullptr, nullptr, 0, 0, 0, 0);
+                if (ns >= lim) {
+                    r.end = ns; r.out = 0; r.flag = F_NONE; r.ntok = 0;
+                    for (int j = 0; j < kCkpt; j++) cp[(uint32_t)j * (uint32_t)T + (uint32_t)t] = kNoCkpt;  // no path left to reuse
+                }
+                else r = decode_count(sm, ns, lim, s0 + (uint32_t)t * kSubBits + kCkptStep, cp, (uint32_t)T, (uint32_t)t, true,
+                                      sm.end[t], sm.flag[t]);
                 sm.start[t] = ns;
                 sm.end[t] = r.end;
                 sm.outc[t] = r.out;
