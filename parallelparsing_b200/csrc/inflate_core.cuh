@@ -866,6 +866,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
     const uint32_t vend = a + total;         // valid bytes: a <= v < vend
     uint8_t *vbase = outp - a;               // 16-byte aligned; vbase[v] is the byte of virtual index v
     volatile uint16_t *res = sm.res;
+    volatile uint32_t *stq = sm.cw;  // per-thread token queue [8][T] (cw is restaged for every window anyway)
     for (uint32_t tb = 0; tb < vend; tb += R) {
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
         // EXPAND: tokens -> one entry per byte.  Uniform control flow: sixteen predicated byte steps
@@ -884,33 +885,52 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 const uint32_t ie = idx[v0 >> 4];
                 uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
                 uint32_t pos = lo;
-                while (pos < hi) {
-                    uint32_t nts = sm.ntok[sgm];
-                    while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }  // next segment holding tokens
-                    const uint32_t *tp = tok + sgm * (uint32_t)kTokRows + k;
-                    uint32_t t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3], t4 = tp[4], t5 = tp[5], t6 = tp[6], t7 = tp[7];
-                    uint32_t avail = nts - k < 8u ? nts - k : 8u;  // tokens of this segment in the queue
+                // the group's next eight tokens: one round trip, parked in shared memory (the compressed
+                // staging buffer is idle during RESOLVE) so that advancing is one indexed load.  A refill
+                // (more than eight tokens in the group, or the sub-sequence ends inside it) happens inside
+                // the byte step that runs dry, so no lane ever repeats the sixteen steps.
+                uint32_t t0 = 0, avail = 0, qi = 0;
+#define PP_REFILL()                                                                                    \
+    do {                                                                                               \
+        uint32_t nts = sm.ntok[sgm];                                                                   \
+        while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }               \
+        const uint32_t *tp = tok + sgm * (uint32_t)kTokRows + k;                                       \
+        t0 = tp[0];                                                                                    \
+        const uint32_t t1 = tp[1], t2 = tp[2], t3 = tp[3], t4 = tp[4], t5 = tp[5], t6 = tp[6], t7 = tp[7]; \
+        stq[1u * (uint32_t)T + (uint32_t)t] = t1; stq[2u * (uint32_t)T + (uint32_t)t] = t2;            \
+        stq[3u * (uint32_t)T + (uint32_t)t] = t3; stq[4u * (uint32_t)T + (uint32_t)t] = t4;            \
+        stq[5u * (uint32_t)T + (uint32_t)t] = t5; stq[6u * (uint32_t)T + (uint32_t)t] = t6;            \
+        stq[7u * (uint32_t)T + (uint32_t)t] = t7;                                                      \
+        avail = nts - k < 8u ? nts - k : 8u;                                                           \
+        if (avail == 0u) avail = 1u; /* cannot happen for consistent tokens; never spin */             \
+        qi = 0;                                                                                        \
+    } while (0)
+                PP_REFILL();
 #pragma unroll
-                    for (int j = 0; j < kTileB; j++) {
-                        if ((uint32_t)j == pos && pos < hi && avail) {
-                            uint32_t val;
-                            bool adv;
-                            if (t0 & 0x80000000u) {
-                                val = 0x8000u | (t0 & 0xffu);
-                                adv = true;
-                            } else {
-                                const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;
-                                // overlapping run: byte i repeats the `dist` bytes before the match, so its
-                                // source is dist*(i/dist+1) back — always in front of the match itself
-                                val = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
-                                adv = ++i == len;
-                            }
-                            r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (val << 16) : (r[j >> 1] & 0xffff0000u) | val;
-                            pos++;
-                            if (adv) { t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = t6; t6 = t7; i = 0; k++; avail--; }
+                for (int j = 0; j < kTileB; j++) {
+                    if ((uint32_t)j == pos && pos < hi) {
+                        uint32_t val;
+                        bool adv;
+                        if (t0 & 0x80000000u) {
+                            val = 0x8000u | (t0 & 0xffu);
+                            adv = true;
+                        } else {
+                            const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;
+                            // overlapping run: byte i repeats the `dist` bytes before the match, so its
+                            // source is dist*(i/dist+1) back — always in front of the match itself
+                            val = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
+                            adv = ++i == len;
+                        }
+                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (val << 16) : (r[j >> 1] & 0xffff0000u) | val;
+                        pos++;
+                        if (adv) {
+                            i = 0; k++; qi++;
+                            if (--avail == 0u) { if (pos < hi) PP_REFILL(); }
+                            else t0 = stq[qi * (uint32_t)T + (uint32_t)t];
                         }
                     }
                 }
+#undef PP_REFILL
             }
             // entries 16 t + j sit at res_pos(16 t) + j: eight aligned words
             volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(sm.res + res_pos(q0));
