@@ -57,6 +57,10 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 #define PP_ATOMIC_ADD(p, v) (*(p) += (v))
 #define PP_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
 // per-thread state that lives across a barrier: registers on the device, one row per thread here
+// two warp-synchronous steps: every lane of a warp finishes the first before any starts the second
+#define PP_FOR_W(t) for (int w_ = 0; w_ < PP_NT; w_ += 32) { for (int t = w_; t < w_ + 32 && t < PP_NT; ++t) {
+#define PP_WARP_SPLIT(t) } for (int t = w_; t < w_ + 32 && t < PP_NT; ++t) {
+#define PP_END_W } }
 #define PP_TLS_DECL(type, name, n) static type name##_tls[1024][n]
 #define PP_TLS(name) name##_tls[t]
 #else
@@ -72,6 +76,9 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 #define PP_CONST __device__ const
 #define PP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define PP_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define PP_FOR_W(t) { { const int t = (int)threadIdx.x;
+#define PP_WARP_SPLIT(t) } __syncwarp(); { const int t = (int)threadIdx.x;
+#define PP_END_W } }
 #define PP_TLS_DECL(type, name, n) type name[n]
 #define PP_TLS(name) name
 #endif
@@ -79,7 +86,7 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 namespace ppinf {
 
 // ---- phase timers (thread 0's clock, summed over all CTAs; read with pp_internal_phase_cycles) ----
-enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_COUNT };
+enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_COUNT };  // PH_R_EXPAND is folded into PH_R_GATHER
 #if defined(PP_HOST_EMU)
 #define PP_PHASE(ph)
 #else
@@ -871,7 +878,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
         // EXPAND: tokens -> one entry per byte.  Uniform control flow: sixteen predicated byte steps
         // over a register queue of the group's next eight tokens (neighbours in memory, one round trip).
-        PP_FOR_T(t)
+        PP_FOR_W(t)
         {
             const uint32_t q0 = (uint32_t)t * kTileB;          // tile-relative index of the group's first byte
             const uint32_t v0 = tb + q0;
@@ -937,11 +944,9 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
 #pragma unroll
             for (int j = 0; j < kTileB / 2; j++) dst[j] = r[j];
         }
-        PP_END_T
-        PP_SYNC();
-        PP_PHASE(PH_R_EXPAND);
-        // GATHER
-        PP_FOR_T(t)
+        // GATHER: the entries a lane reads (bytes j*32+lane of the warp's 512) were written by its own warp,
+        // so a warp-level sync is all that separates the two steps
+        PP_WARP_SPLIT(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
             const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);  // entries qb + 32 j sit at pb + 32 j + 2 (j >> 1)
@@ -968,7 +973,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 }
             }
         }
-        PP_END_T
+        PP_END_W
         PP_SYNC();
         PP_PHASE(PH_R_GATHER);
         // CHASE + store
