@@ -272,7 +272,7 @@ return true;
 
 
 // order 0: ticket = global tile number (tile_base[k] + i); order 1: ticket = i * n + k
-__global__ void __launch_bounds__(kParseThreads, 3) pp_parse_kernel(const uint8_t *__restrict__ slots,
+__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel(const uint8_t *__restrict__ slots,
                                                                  const ParseDesc *__restrict__ pdesc, int n,
                                                                  const uint32_t *__restrict__ tile_base,
                                                                  uint32_t n_tickets, int order,
