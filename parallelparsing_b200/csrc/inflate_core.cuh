@@ -913,30 +913,48 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         qi = 0;                                                                                        \
     } while (0)
                 PP_REFILL();
+                // The current token is kept DECODED: cur = the entry its bytes get, rem = bytes still to
+                // emit, odist != 0 only for an overlapping run (dist < len: byte i repeats the `dist` bytes
+                // before the match, so its source is dist*(i/dist+1) back — always in front of the match
+                // itself).  A byte step is then: take cur, count down, and only at a token's last byte
+                // decode the next one.
+                uint32_t cur, rem, odist = 0, orr = 0;
+#define PP_DECODE_TOKEN(first)                                                                         \
+    do {                                                                                               \
+        if (t0 & 0x80000000u) {                                                                        \
+            cur = 0x8000u | (t0 & 0xffu);                                                              \
+            rem = 1u;                                                                                  \
+            odist = 0u;                                                                                \
+        } else {                                                                                       \
+            const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;                                 \
+            const uint32_t i0 = (first) ? i : 0u;                                                      \
+            rem = len - i0;                                                                            \
+            cur = dist - 1u;                                                                           \
+            odist = 0u;                                                                                \
+            if (dist < len) {                                                                          \
+                const uint32_t qd = div_small(i0, dist);                                               \
+                cur = dist * (qd + 1u) - 1u;                                                           \
+                orr = i0 - qd * dist;                                                                  \
+                odist = dist;                                                                          \
+            }                                                                                          \
+        }                                                                                              \
+    } while (0)
+                PP_DECODE_TOKEN(true);
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
                     if ((uint32_t)j == pos && pos < hi) {
-                        uint32_t val;
-                        bool adv;
-                        if (t0 & 0x80000000u) {
-                            val = 0x8000u | (t0 & 0xffu);
-                            adv = true;
-                        } else {
-                            const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;
-                            // overlapping run: byte i repeats the `dist` bytes before the match, so its
-                            // source is dist*(i/dist+1) back — always in front of the match itself
-                            val = dist >= len ? dist - 1u : dist * (div_small(i, dist) + 1u) - 1u;
-                            adv = ++i == len;
-                        }
-                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (val << 16) : (r[j >> 1] & 0xffff0000u) | val;
+                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (cur << 16) : (r[j >> 1] & 0xffff0000u) | cur;
                         pos++;
-                        if (adv) {
-                            i = 0; k++; qi++;
+                        if (odist) { if (++orr == odist) { orr = 0; cur += odist; } }
+                        if (--rem == 0u) {
+                            k++; qi++;
                             if (--avail == 0u) { if (pos < hi) PP_REFILL(); }
                             else t0 = stq[qi * (uint32_t)T + (uint32_t)t];
+                            PP_DECODE_TOKEN(false);
                         }
                     }
                 }
+#undef PP_DECODE_TOKEN
 #undef PP_REFILL
             }
             // entries 16 t + j sit at res_pos(16 t) + j: eight aligned words
