@@ -258,6 +258,14 @@ def main():
     iz = job_zc.run(gz)
     if iz.status != 0 or (iz.total_bytes, iz.total_records) != (U, R):
         raise SystemExit("bench.py: zero-copy DecompressAll disagrees with the staged run")
+    # size-independent properties at the full workload size: every byte of the stream is produced
+    # (the end sentinel's Output), every chunk is exactly to.Output-from.Output long, no read is lost
+    outs = ix.scalars()[0]
+    if U != int(outs[-1] - outs[0]) or R < args.reads:
+        raise SystemExit(f"bench.py: DecompressAll produced {U} bytes / {R} records, expected {int(outs[-1] - outs[0])} / >= {args.reads}")
+    for k in (0, n_chunks // 2, n_chunks - 1):
+        if job.chunk(k).inflated != int(outs[k + 1] - outs[k]):
+            raise SystemExit(f"bench.py: chunk {k} has the wrong length")
 
     sampler = ClockSampler(local_rank)
     sampler.start()

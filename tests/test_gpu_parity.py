@@ -280,3 +280,32 @@ def test_paired_end_pairs_by_global_ordinal(device):
         n += 1
     assert n == 6000
     pe.Dispose()
+
+
+@pytest.mark.parametrize("chunk", [1000, 5000, 20000, 100000])
+def test_chunk_size_sweep_properties(device, chunk):
+    """BASELINE config 5 in small: the same file under a sweep of chunk sizes.  Size-independent
+    properties only (no per-chunk oracle): every chunk inflates to exactly to.Output-from.Output
+    bytes, the concatenation is the generator's output, every read is found once (plus the H1
+    duplicates the oracle's index-only count predicts), record bases are the running sum."""
+    import hashlib
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(150000, fixed=150)
+    gz = corpus.gz_parallel(fq, 6, segment=4 << 20, threads=4)
+    ix = pp.Core.BuildDeflateIndex(gz, chunk)
+    outs = ix.scalars()[0]
+    job = pp.Job(device, ix, gz.size)
+    info = job.run(gz)
+    assert info.status == 0 and info.total_bytes == len(fq) == int(outs[-1])
+    base = 0
+    dup = 0
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        assert c.status == 0 and c.inflated == int(outs[k + 1] - outs[k]) and c.record_base == base
+        base += c.records
+        p = ix[k]
+        # a checkpoint exactly on a record boundary: Point.offset holds one complete record (quirk H1)
+        dup += int(k > 0 and p.offset.size > 0 and p.offset[-1] == 10 and int((p.offset == 10).sum()) == 4)
+    assert info.total_records == base == 150000 + dup
+    assert hashlib.md5(job.all_bytes().tobytes()).hexdigest() == hashlib.md5(fq).hexdigest()
+    job.free()
