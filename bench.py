@@ -266,6 +266,15 @@ def main():
     for k in (0, n_chunks // 2, n_chunks - 1):
         if job.chunk(k).inflated != int(outs[k + 1] - outs[k]):
             raise SystemExit(f"bench.py: chunk {k} has the wrong length")
+    # checksum of checksums: the gzip trailer holds CRC-32 and length of the whole uncompressed stream;
+    # the concatenation of all inflated chunks (pull-mode run) must reproduce both
+    import zlib
+    allb = job_zc.all_bytes()
+    crc = zlib.crc32(memoryview(allb)) & 0xffffffff
+    want_crc, want_len = int(gz_np[-8:-4].view("<u4")[0]), int(gz_np[-4:].view("<u4")[0])
+    if crc != want_crc or (allb.size & 0xffffffff) != want_len:
+        raise SystemExit(f"bench.py: CRC-32/ISIZE of the inflated stream {crc:#x}/{allb.size} != gzip trailer {want_crc:#x}/{want_len}")
+    del allb
 
     sampler = ClockSampler(local_rank)
     sampler.start()
