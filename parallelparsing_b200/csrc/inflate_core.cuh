@@ -859,10 +859,10 @@ PP_DEV uint32_t div_small(uint32_t i, uint32_t d)  // floor(i / d) for i, d < 51
 #endif
 }
 
-// Shared layout of the tile's u16 entries: entry q lives at res[res_pos(q)], a skew of one word per
-// 32 words, so that both access patterns are free of bank conflicts: EXPAND (lane t touches
-// entries 16 t + j) and GATHER/CHASE (the lanes of a warp touch 32 consecutive entries).
-PP_DEV uint32_t res_pos(uint32_t q) { return q + ((q >> 6) << 1); }
+// Shared layout of the tile's u16 entries: entry q lives at res[q].  GATHER/CHASE touch 32
+// consecutive entries per warp access (no bank conflicts); EXPAND stores its 16 entries as two
+// 16-byte vectors (lanes 32 bytes apart: two-way conflicts at most).
+PP_DEV uint32_t res_pos(uint32_t q) { return q; }
 PP_HD uint32_t res_entries_for(int T) { return (uint32_t)T * kTileB + (uint32_t)T * kTileB / 32u + 2u; }
 
 PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *idx, uint8_t *outp, uint32_t a,
@@ -957,17 +957,20 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
 #undef PP_DECODE_TOKEN
 #undef PP_REFILL
             }
-            // entries 16 t + j sit at res_pos(16 t) + j: eight aligned words
-            volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(sm.res + res_pos(q0));
-#pragma unroll
-            for (int j = 0; j < kTileB / 2; j++) dst[j] = r[j];
+            // entries 16 t .. 16 t + 15: two 16-byte vectors
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.res + q0);
+            uint4 w0, w1;
+            w0.x = r[0]; w0.y = r[1]; w0.z = r[2]; w0.w = r[3];
+            w1.x = r[4]; w1.y = r[5]; w1.z = r[6]; w1.w = r[7];
+            dst[0] = w0;
+            dst[1] = w1;
         }
         // GATHER: the entries a lane reads (bytes j*32+lane of the warp's 512) were written by its own warp,
         // so a warp-level sync is all that separates the two steps
         PP_WARP_SPLIT(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
-            const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);  // entries qb + 32 j sit at pb + 32 j + 2 (j >> 1)
+            const uint32_t pb = qb;
             // Unconditional loads (lanes with nothing to fetch read one shared, always valid byte), so
             // that the eight loads of a batch are in flight together instead of one per branch.
             const int32_t safe = near_lo - 1;  // the byte just before the tile/window: final, inside the slot
@@ -978,7 +981,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 uint32_t b[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    e[j] = res[pb + (uint32_t)(h + j) * 32u + 2u * (uint32_t)((h + j) >> 1)];
+                    e[j] = res[pb + (uint32_t)(h + j) * 32u];
                     sv[j] = (int32_t)(tb + qb + (uint32_t)(h + j) * 32u) - (int32_t)e[j] - 1;  // virtual index of the source
                 }
 #pragma unroll
@@ -986,7 +989,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     if (!(e[j] & 0x8000u))
-                        res[pb + (uint32_t)(h + j) * 32u + 2u * (uint32_t)((h + j) >> 1)] =
+                        res[pb + (uint32_t)(h + j) * 32u] =
                             (uint16_t)(sv[j] < near_lo ? 0x8000u | b[j] : (uint32_t)(sv[j] - (int32_t)tb));
                 }
             }
@@ -998,12 +1001,12 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         PP_FOR_T(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
-            const uint32_t pb = res_pos(qb & ~31u) + (qb & 31u);
+            const uint32_t pb = qb;
             uint32_t e[kTileB];
             uint32_t pend = 0;
 #pragma unroll
             for (int j = 0; j < kTileB; j++) {
-                e[j] = res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)];
+                e[j] = res[pb + (uint32_t)j * 32u];
                 pend |= ~e[j] & 0x8000u;
             }
             while (pend) {
@@ -1013,7 +1016,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                     if (!(e[j] & 0x8000u)) {
                         const uint32_t y = res[res_pos(e[j])];
                         e[j] = y;
-                        res[pb + (uint32_t)j * 32u + 2u * (uint32_t)(j >> 1)] = (uint16_t)y;  // publish the hop
+                        res[pb + (uint32_t)j * 32u] = (uint16_t)y;  // publish the hop
                         pend |= ~y & 0x8000u;
                     }
                 }
