@@ -648,7 +648,7 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 // ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
 // Decodes the symbols that START in [start, limit) (window-relative bits).
 // WRITE: also emits one TOKEN per symbol, token k of this thread at tok[t * kTokRows + k]
-//   literal: 0x80000000 | byte        match: len << 15 | (dist - 1)
+//   literal: 1 << 16 | 0x8000 | byte      match: len << 16 | (dist - 1) | (dist < len) << 25
 // and, for every multiple of 16 below oclip that a token's output range [o, o + len) covers,
 // the GROUP INDEX entry idx[m / 16] = t | k << 10 | (m - o) << 20, which tells the resolve
 // stage where the bytes of group m / 16 start.  `o` is the virtual output index (window
@@ -656,8 +656,10 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 struct Seg {
     uint32_t end, out, flag, ntok;
 };
-PP_DEV uint32_t tok_lit(uint32_t byte) { return 0x80000000u | byte; }
-PP_DEV uint32_t tok_match(uint32_t len, uint32_t dist) { return (len << 15) | (dist - 1u); }
+// token = entry | len << 16 | overlap << 25: `entry` is what the resolve stage writes for every byte
+// of the token (0x8000|byte for a literal, dist-1 for a match), `overlap` marks dist < len
+PP_DEV uint32_t tok_lit(uint32_t byte) { return (1u << 16) | 0x8000u | byte; }
+PP_DEV uint32_t tok_match(uint32_t len, uint32_t dist) { return (len << 16) | (dist - 1u) | (dist < len ? 1u << 25 : 0u); }
 PP_DEV uint32_t idx_pack(uint32_t t, uint32_t k, uint32_t off) { return t | (k << 10) | (off << 20); }
 
 template <int WRITE>
@@ -921,22 +923,16 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 uint32_t cur, rem, odist = 0, orr = 0;
 #define PP_DECODE_TOKEN(first)                                                                         \
     do {                                                                                               \
-        if (t0 & 0x80000000u) {                                                                        \
-            cur = 0x8000u | (t0 & 0xffu);                                                              \
-            rem = 1u;                                                                                  \
-            odist = 0u;                                                                                \
-        } else {                                                                                       \
-            const uint32_t len = t0 >> 15, dist = (t0 & 0x7fffu) + 1u;                                 \
-            const uint32_t i0 = (first) ? i : 0u;                                                      \
-            rem = len - i0;                                                                            \
-            cur = dist - 1u;                                                                           \
-            odist = 0u;                                                                                \
-            if (dist < len) {                                                                          \
-                const uint32_t qd = div_small(i0, dist);                                               \
-                cur = dist * (qd + 1u) - 1u;                                                           \
-                orr = i0 - qd * dist;                                                                  \
-                odist = dist;                                                                          \
-            }                                                                                          \
+        const uint32_t i0 = (first) ? i : 0u;                                                          \
+        cur = t0 & 0xffffu;                                                                            \
+        rem = ((t0 >> 16) & 0x1ffu) - i0;                                                              \
+        odist = 0u;                                                                                    \
+        if (t0 >> 25) {                                                                                \
+            const uint32_t dist = cur + 1u;                                                            \
+            const uint32_t qd = div_small(i0, dist);                                                   \
+            cur = dist * (qd + 1u) - 1u;                                                               \
+            orr = i0 - qd * dist;                                                                      \
+            odist = dist;                                                                              \
         }                                                                                              \
     } while (0)
                 PP_DECODE_TOKEN(true);
