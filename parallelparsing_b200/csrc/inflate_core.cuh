@@ -893,7 +893,6 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
             if (lo < hi) {
                 const uint32_t ie = idx[v0 >> 4];
                 uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
-                uint32_t pos = lo;
                 // the group's next eight tokens: one round trip, parked in shared memory (the compressed
                 // staging buffer is idle during RESOLVE) so that advancing is one indexed load.  A refill
                 // (more than eight tokens in the group, or the sub-sequence ends inside it) happens inside
@@ -901,6 +900,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 uint32_t t0 = 0, avail = 0, qi = 0;
 #define PP_REFILL()                                                                                    \
     do {                                                                                               \
+        k += qi; /* tokens taken from the queue since the last refill */                               \
         uint32_t nts = sm.ntok[sgm];                                                                   \
         while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }               \
         const uint32_t *tp = tok + sgm * (uint32_t)kTokRows + k;                                       \
@@ -938,13 +938,12 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                 PP_DECODE_TOKEN(true);
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
-                    if ((uint32_t)j == pos && pos < hi) {
-                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (cur << 16) : (r[j >> 1] & 0xffff0000u) | cur;
-                        pos++;
+                    if ((uint32_t)j >= lo && (uint32_t)j < hi) {  // the group's valid bytes: one byte per step
+                        // even byte: the odd half keeps its harmless literal until the next step overwrites it
+                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (cur << 16) : 0x80000000u | cur;
                         if (odist) { if (++orr == odist) { orr = 0; cur += odist; } }
                         if (--rem == 0u) {
-                            k++; qi++;
-                            if (--avail == 0u) { if (pos < hi) PP_REFILL(); }
+                            if (++qi == avail) { if ((uint32_t)j + 1u < hi) PP_REFILL(); }
                             else t0 = stq[qi * (uint32_t)T + (uint32_t)t];
                             PP_DECODE_TOKEN(false);
                         }
