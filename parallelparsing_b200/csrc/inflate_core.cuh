@@ -1009,26 +1009,27 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
 #pragma unroll
                 for (int j = 0; j < kTileB; j++) {
                     if (!(e[j] & 0x8000u)) {
-                        const uint32_t y = res[res_pos(e[j])];
+                        uint32_t y = res[res_pos(e[j])];
+                        if (!(y & 0x8000u)) y = res[res_pos(y)];  // two hops per round
                         e[j] = y;
                         res[pb + (uint32_t)j * 32u] = (uint16_t)y;  // publish the hop
                         pend |= ~y & 0x8000u;
                     }
                 }
             }
-            uint32_t nl = 0, nul = 0;
+            // every entry is 0x8000|byte now: '\n' is 0x800a, NUL is the smallest possible value 0x8000
+            uint32_t nl = 0, mn = 0xffffu;
 #pragma unroll
             for (int j = 0; j < kTileB; j++) {
                 const uint32_t v = tb + qb + (uint32_t)j * 32u;
-                if (v >= a && v < vend) {
-                    const uint32_t c = e[j] & 0xffu;
-                    vbase[v] = (uint8_t)c;
-                    nl += (c == 10u);
-                    nul |= (c == 0u);
+                if (v - a < total) {  // a <= v < vend
+                    vbase[v] = (uint8_t)e[j];
+                    nl += (e[j] == 0x800au);
+                    mn = e[j] < mn ? e[j] : mn;
                 }
             }
             sm.nl[t] += nl;
-            sm.nul[t] |= nul;
+            sm.nul[t] |= (mn == 0x8000u);
         }
         PP_END_T
         PP_SYNC();  // stores visible to the next tile's gathers; res free again
