@@ -148,6 +148,31 @@ def load_ncu_traffic(reads, chunk):
     return {}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers
+    it allocates and fills (first touch) are local to that GPU's PCIe root.  Best effort: any failure
+    leaves the affinity alone."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(gpu).pci_bus_id
+        dom = torch.cuda.get_device_properties(gpu).pci_domain_id
+        dev = torch.cuda.get_device_properties(gpu).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"[bench] rank on GPU {gpu}: NUMA node {node}, {len(cpus)} CPUs")
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] NUMA binding skipped: {e}")
+
+
 def cpu_reference(gz, idx_path, threads, steps, warmup):
     """The host restatement of the reference's parallel DecompressAll, all cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -234,6 +259,8 @@ def main():
         ensure_built()
         make_corpus(args.reads, args.fixed_len, args.seed, args.chunk)
     barrier()
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)  # several GPUs pull from host memory at once: keep each rank's buffers local
     import parallelparsing_b200 as pp
     from parallelparsing_b200 import _lib
     L = pp.lib()
