@@ -194,6 +194,13 @@ int pp_job_fetch_bytes(pp_job *job, uint8_t *dst, int64_t cap);
 /* Device pointers for on-device consumers (valid until the job is freed). */
 int pp_job_device_ptrs(const pp_job *job, const uint8_t **slots, const uint64_t **chunk_data_off,
                        const uint32_t **l0, const uint32_t **l1, const uint32_t **l2, const uint32_t **l3);
+/*
+ * On-device consumer (what the reference's driver and benchmark do with the records:
+ * records.Count() and counting 'A's, Decompressor/Program.cs:51-52, Benchmark/Naive.cs:158-178):
+ * histogram of the bytes of every record's SEQUENCE line, computed on the GPU from the
+ * structure-of-arrays line starts.  Only the 256 counters cross PCIe.  Needs pp_job_download first.
+ */
+int pp_job_base_histogram(pp_job *job, uint64_t counts[256]);
 void pp_job_free(pp_job *job);
 
 /* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */

@@ -281,6 +281,12 @@ class Job:
         check(lib().pp_job_fetch_line_starts(self.h, *[_ptr(x) if n else None for x in a]), "fetch_line_starts")
         return a
 
+    def base_histogram(self):
+        """On-device consumer: byte histogram of all sequence lines (uint64[256])."""
+        out = np.zeros(256, np.uint64)
+        check(lib().pp_job_base_histogram(self.h, _ptr(out)), "pp_job_base_histogram")
+        return out
+
     def chunk_bytes(self, k):
         c = self.chunk(k)
         out = np.zeros(max(c.inflated, 1), np.uint8)

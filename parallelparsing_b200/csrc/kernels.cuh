@@ -60,6 +60,8 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
                          uint32_t total_tiles, uint32_t max_tiles, uint32_t *lines, int64_t line_stride,
                          ParseOut *pout, const ScanTotals *totals, unsigned long long *work, int sm_count,
                          cudaStream_t st);
+cudaError_t launch_base_histogram(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
+                                  int64_t line_stride, unsigned long long *counts, int sm_count, cudaStream_t st);
 cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
                                const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st);
 cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,

@@ -495,6 +495,67 @@ __global__ void __launch_bounds__(kScanThreads) pp_scan_kernel(const ChunkDesc *
     }
 }
 
+// ---- on-device consumer: histogram of the sequence lines -------------------------------------
+// One CTA per chunk (grid-stride), one warp per record: the 32 lanes stream the record's sequence
+// line; the five letters FASTQ sequences are made of live in registers, anything else goes through
+// a shared-memory histogram.  Replaces the host loops of Decompressor/Program.cs:51-52.
+__global__ void __launch_bounds__(256) pp_base_histogram_kernel(const uint8_t *__restrict__ slots,
+                                                                const ParseDesc *__restrict__ pdesc, int n,
+                                                                const uint32_t *__restrict__ lines, int64_t stride,
+                                                                unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned int s_hist[256];
+    for (int i = (int)threadIdx.x; i < 256; i += (int)blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5), nwarps = (int)(blockDim.x >> 5);
+    unsigned long long cA = 0, cC = 0, cG = 0, cT = 0, cN = 0;
+    for (int k = (int)blockIdx.x; k < n; k += (int)gridDim.x) {
+        const ParseDesc d = pdesc[k];
+        const uint8_t *data = slots + d.data_off;
+        const uint32_t *l1 = lines + stride + d.rec_base, *l2 = lines + 2 * stride + d.rec_base;
+        for (uint32_t r = (uint32_t)warp; r < d.rec_count; r += (uint32_t)nwarps) {
+            const uint32_t a = l1[r], b = l2[r] - 1u;  // sequence = [l1, l2 - 1): without its '\n'
+            for (uint32_t p = a + (uint32_t)lane; p < b; p += 32u) {
+                const unsigned int c = data[p];
+                if (c == 'A') cA++;
+                else if (c == 'C') cC++;
+                else if (c == 'G') cG++;
+                else if (c == 'T') cT++;
+                else if (c == 'N') cN++;
+                else atomicAdd(&s_hist[c], 1u);
+            }
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        cA += __shfl_xor_sync(0xffffffffu, cA, sft);
+        cC += __shfl_xor_sync(0xffffffffu, cC, sft);
+        cG += __shfl_xor_sync(0xffffffffu, cG, sft);
+        cT += __shfl_xor_sync(0xffffffffu, cT, sft);
+        cN += __shfl_xor_sync(0xffffffffu, cN, sft);
+    }
+    if (lane == 0) {
+        if (cA) atomicAdd(&counts['A'], cA);
+        if (cC) atomicAdd(&counts['C'], cC);
+        if (cG) atomicAdd(&counts['G'], cG);
+        if (cT) atomicAdd(&counts['T'], cT);
+        if (cN) atomicAdd(&counts['N'], cN);
+    }
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < 256; i += (int)blockDim.x)
+        if (s_hist[i]) atomicAdd(&counts[i], (unsigned long long)s_hist[i]);
+}
+
+cudaError_t launch_base_histogram(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
+                                  int64_t line_stride, unsigned long long *counts, int sm_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(counts, 0, 256 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess || n <= 0) return e;
+    const int grid = n < sm_count * 8 ? n : sm_count * 8;
+    pp_base_histogram_kernel<<<grid, 256, 0, st>>>(slots, pdesc, n, lines, line_stride, counts);
+    return cudaGetLastError();
+}
+
 // ---- launchers ------------------------------------------------------------------------
 cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
                                cudaStream_t st)

@@ -647,6 +647,20 @@ int pp_job_fetch_bytes(pp_job *j, uint8_t *dst, int64_t cap)
     return PP_OK;
 }
 
+int pp_job_base_histogram(pp_job *j, uint64_t counts[256])
+{
+    if (!j || !j->ctx || !counts || !j->have_results) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    DevBuf d;
+    CK(d.alloc(256 * sizeof(unsigned long long)));
+    CK(launch_base_histogram(j->d_slots, j->d_pdesc, j->n, j->d_lines, j->rec_cap, d.as<unsigned long long>(),
+                             j->ctx->sm_count, j->ctx->stream));
+    CK(cudaMemcpyAsync(counts, d.p, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, j->ctx->stream));
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
 int pp_job_device_ptrs(const pp_job *j, const uint8_t **slots, const uint64_t **chunk_data_off, const uint32_t **l0,
                        const uint32_t **l1, const uint32_t **l2, const uint32_t **l3)
 {

@@ -309,3 +309,21 @@ def test_chunk_size_sweep_properties(device, chunk):
     assert info.total_records == base == 150000 + dup
     assert hashlib.md5(job.all_bytes().tobytes()).hexdigest() == hashlib.md5(fq).hexdigest()
     job.free()
+
+
+def test_on_device_base_histogram(device):
+    """On-device consumer (Decompressor/Program.cs:51-52 counts records and 'A's): the histogram of
+    all sequence lines computed on the GPU equals the host count over the generator's output."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(20000)  # native U[128,512) lengths
+    gz = corpus.gz_member(fq, 6)
+    ix = pp.Core.BuildDeflateIndex(gz, 3000)
+    job = pp.Job(device, ix, gz.size, strict=True)  # strict: a duplicated record would be counted twice
+    info = job.run(gz)
+    assert info.status == 0 and info.total_records == 20000
+    h = job.base_histogram()
+    seq = b"".join(fq.split(b"\n")[1::4])
+    want = np.bincount(np.frombuffer(seq, np.uint8), minlength=256).astype(np.uint64)
+    assert np.array_equal(h, want)
+    assert int(h.sum()) == len(seq) and int(h[ord("A")]) > 0
+    job.free()
