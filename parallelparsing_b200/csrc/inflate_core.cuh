@@ -593,32 +593,43 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
             }
             uint32_t have = 0;
             const uint32_t total = nlen + ndist;
+            // bit buffer in registers: one table lookup per code-length symbol on the critical path
+            uint32_t wq = p >> 5;
+            uint64_t bb = ((uint64_t)sm.cw[wq] | ((uint64_t)sm.cw[wq + 1] << 32)) >> (p & 31u);
+            uint32_t bc = 64u - (p & 31u);
+            wq += 2;
             while (have < total && !err) {
-                const uint32_t e = sm.dist[peek_bits(sm.cw, p, 7)];
+                if (bc < 32u) { bb |= (uint64_t)sm.cw[wq] << bc; bc += 32u; wq++; }
+                const uint32_t e = sm.dist[(uint32_t)bb & 127u];
                 if (!e) { err = 1; break; }
-                p += (e >> 8) & 15u;
+                const uint32_t l = (e >> 8) & 15u;
+                bb >>= l;
+                bc -= l;
                 const uint32_t sym = e & 255u;
                 if (sym < 16u) {
                     sm.lens[have++] = (uint8_t)sym;
                 } else {
-                    uint32_t rep, val = 0;
+                    uint32_t rep, val = 0, xb;
                     if (sym == 16u) {
                         if (have == 0) { err = 1; break; }  // invalid bit length repeat
                         val = sm.lens[have - 1];
-                        rep = 3u + peek_bits(sm.cw, p, 2);
-                        p += 2;
+                        rep = 3u + ((uint32_t)bb & 3u);
+                        xb = 2;
                     } else if (sym == 17u) {
-                        rep = 3u + peek_bits(sm.cw, p, 3);
-                        p += 3;
+                        rep = 3u + ((uint32_t)bb & 7u);
+                        xb = 3;
                     } else {
-                        rep = 11u + peek_bits(sm.cw, p, 7);
-                        p += 7;
+                        rep = 11u + ((uint32_t)bb & 127u);
+                        xb = 7;
                     }
+                    bb >>= xb;
+                    bc -= xb;
                     if (have + rep > total) { err = 1; break; }  // invalid bit length repeat
                     for (uint32_t j = 0; j < rep; j++) sm.lens[have + j] = (uint8_t)val;
                     have += rep;
                 }
             }
+            p = wq * 32u - bc;
             if (!err && sm.lens[256] == 0) err = 1;  // invalid code -- missing end-of-block
             if (!err) {
                 // distance lengths follow the literal/length lengths: move them to lens[288..]
