@@ -86,7 +86,7 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 namespace ppinf {
 
 // ---- phase timers (thread 0's clock, summed over all CTAs; read with pp_internal_phase_cycles) ----
-enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_COUNT };  // PH_R_EXPAND is folded into PH_R_GATHER
+enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_H_PARSE, PH_H_LIT, PH_COUNT };  // PH_R_EXPAND is folded into PH_R_GATHER
 #if defined(PP_HOST_EMU)
 #define PP_PHASE(ph)
 #else
@@ -486,21 +486,30 @@ PP_DEV int build_table(const Sm &sm, uint32_t *tbl, int root, int cap, int nsym,
     PP_END_T
     PP_SYNC();
     if (maxlen <= root) return 0;
-    // 5. sub-table geometry (thread 0): prefix p owns the length-l codes in
-    //    [p << (l-root), (p+1) << (l-root)); long codes sit at the top of the code space.
+    // 5. sub-table geometry: prefix p owns the length-l codes in [p << (l-root), (p+1) << (l-root));
+    //    long codes sit at the top of the code space.  Every prefix finds its own sub-table size in
+    //    parallel (scratch: the resolve tile buffer, idle here); thread 0 only hands out the offsets.
+    int pmin = nprim;
+    for (int l = root + 1; l <= maxlen; l++)
+        if (sm.count[l]) { pmin = (int)(sm.first[l] >> (l - root)); break; }
+    uint8_t *subs = reinterpret_cast<uint8_t *>(sm.res);  // [nprim] sub-table index bits per prefix (0: none)
+    PP_FOR_T(t)
+    for (int p = pmin + t; p < nprim; p += T) {
+        int sub = 0;
+        for (int l = maxlen; l > root; l--) {
+            const uint32_t lo = (uint32_t)p << (l - root), hi = ((uint32_t)p + 1u) << (l - root);
+            const uint32_t f = sm.first[l], e = f + sm.count[l];
+            if (sm.count[l] && lo < e && hi > f) { sub = l - root; break; }
+        }
+        subs[p] = (uint8_t)sub;
+    }
+    PP_END_T
+    PP_SYNC();
     PP_T0_BEGIN
     {
         int used = nprim, err = 0;
-        int pmin = nprim;
-        for (int l = root + 1; l <= maxlen; l++)
-            if (sm.count[l]) { pmin = (int)(sm.first[l] >> (l - root)); break; }
         for (int p = pmin; p < nprim; p++) {
-            int sub = 0;
-            for (int l = maxlen; l > root; l--) {
-                const uint32_t lo = (uint32_t)p << (l - root), hi = ((uint32_t)p + 1u) << (l - root);
-                const uint32_t f = sm.first[l], e = f + sm.count[l];
-                if (sm.count[l] && lo < e && hi > f) { sub = l - root; break; }
-            }
+            const int sub = subs[p];
             if (sub) {
                 if (used + (1 << sub) > cap) { err = 1; break; }
                 tbl[bitrev((uint32_t)p, root)] =
@@ -651,7 +660,9 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
     const int nlen = (int)sm.u[3], ndist = (int)sm.u[4];
     *pos_out = sm.u[5];
     PP_SYNC();
+    PP_PHASE(PH_H_PARSE);
     int rc = build_table(sm, sm.lit, kRootL, kLitCap, nlen, 0, 0);
+    PP_PHASE(PH_H_LIT);
     if (rc) return rc;
     return build_table(sm, sm.dist, kRootD, kDistCap, ndist, 288, 1);
 }

@@ -26,7 +26,7 @@ L.pp_internal_phase_cycles(ph, 16)
 for _ in range(iters):
     info = job.run(gz)
 n = L.pp_internal_phase_cycles(ph, 16)
-names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other", "r.expand", "r.gather", "r.chase"]
+names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other", "r.expand", "r.gather", "r.chase", "h.parse", "h.lit"]
 tot = sum(ph[i] for i in range(n)) or 1
 print("phase share of CTA time:", ", ".join(f"{names[i]} {100*ph[i]/tot:.1f}%" for i in range(n)),
       f"| cycles/iter/CTA-sum {tot/iters:.3e}")
