@@ -327,3 +327,38 @@ def test_on_device_base_histogram(device):
     assert np.array_equal(h, want)
     assert int(h.sum()) == len(seq) and int(h[ord("A")]) > 0
     job.free()
+
+
+def test_empty_chunk_range_and_threaded_callers(device):
+    """A rank that gets no chunks (more GPUs than chunks) and callers on thread-pool threads
+    (BatchedFASTQ.cs:62 spawns tasks; README.md:50 asks for thread safety)."""
+    import threading
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(9000, fixed=150)
+    gz = corpus.gz_member(fq, 6)
+    ix = pp.Core.BuildDeflateIndex(gz, 1000)
+    nchunks = ix.Count - 1
+    j = pp.Job(device, ix, gz.size, nchunks, 0)
+    info = j.run(gz)
+    assert (info.status, info.n_chunks, info.total_records, info.total_bytes) == (0, 0, 0, 0)
+    j.free()
+    results, errors = {}, []
+
+    def work(first, n):
+        try:
+            jb = pp.Job(device, ix, gz.size, first, n)
+            i = jb.run(gz)
+            results[first] = (i.status, i.total_records, jb.all_bytes().tobytes())
+            jb.free()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+    half = nchunks // 2
+    ts = [threading.Thread(target=work, args=a) for a in ((0, half), (half, nchunks - half))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors
+    assert results[0][0] == 0 and results[half][0] == 0
+    assert results[0][2] + results[half][2] == fq
+    assert results[0][1] + results[half][1] >= 9000
