@@ -403,6 +403,18 @@ def main():
             line["cpu_baseline"] = {"value": nbytes / dt / 1e9, "unit": "GB/s", "reads_per_s": recs / dt,
                                     "cores": cores, "kind": "port",
                                     "sample": "whole workload, 2 timed passes after 1 warm-up (oracle thread pool)"}
+            # the reference's serial baseline (SimpleDecompressor: GZipStream + line parser), one thread,
+            # on a bounded prefix of the same file (a truncated stream ends in an error: only the bytes
+            # it got through are used)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            sample = gz_np[: min(gz_np.size, 192 << 20)]
+            t0 = time.perf_counter()
+            _, nb = O.naive_count(sample)
+            dtn = time.perf_counter() - t0
+            line["cpu_baseline"]["naive_serial"] = {
+                "value": nb / dtn / 1e9, "unit": "GB/s", "reads_per_s": nb / dtn / (U / R), "cores": 1, "kind": "port",
+                "sample": f"first {sample.size >> 20} MiB of the compressed file ({nb} bytes inflated and parsed)"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
