@@ -850,8 +850,46 @@ PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t t
     return r;
 }
 
+// Bit position right after the symbol whose output makes a segment's byte count reach `target`
+// (target >= 1); one thread, once per chunk: zlib stops as soon as the wanted bytes are out
+// (Core.cs:187), so the input it needed ends there and not at the end of the window.
+PP_DEV uint32_t seg_pos_at_output(const Sm &sm, uint32_t start, uint32_t limit, uint32_t target)
+{
+    const uint32_t *cw = sm.cw;
+    uint32_t wp = start >> 5;
+    const uint32_t sh = start & 31u;
+    uint64_t buf = ((uint64_t)cw[wp] | ((uint64_t)cw[wp + 1] << 32)) >> sh;
+    uint32_t cnt = 64u - sh;
+    wp += 2;
+    uint32_t out = 0;
+    while (wp * 32u - cnt < limit && out < target) {
+        if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+        uint32_t lo = (uint32_t)buf;
+        uint32_t e = sm.lit[lo & ((1u << kRootL) - 1u)];
+        if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
+        const uint32_t kind = e_kind(e), tot = e_tot(e);
+        if (kind != K_LIT && kind != K_BASE) break;  // EOB / invalid: the caller has already seen it
+        uint32_t n = 1;
+        if (kind == K_BASE) n = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
+        buf >>= tot;
+        cnt -= tot;
+        if (kind == K_BASE) {
+            if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+            lo = (uint32_t)buf;
+            uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
+            if (e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
+            const uint32_t dtot = e_tot(d);
+            buf >>= dtot;
+            cnt -= dtot;
+        }
+        out += n;
+    }
+    return wp * 32u - cnt;
+}
+
 struct WindowOut {
     uint32_t next_bit;   // window-relative bit after the last symbol used
+    uint32_t need_bit;   // window-relative bit up to which the compressed input was really needed
     uint32_t produced;   // output bytes (clipped to the room left)
     uint32_t flag;       // F_EOB: the block ended; F_BAD: invalid data; F_NONE: window or output exhausted
     uint32_t rounds;     // SYNC rounds (statistics)
@@ -1153,8 +1191,17 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     uint32_t produced = nlive < (uint32_t)T ? sm.outc[nlive] : total;
     const uint32_t next_bit = sm.end[nlive - 1u];
     uint32_t flag = (f < (uint32_t)T && nlive == f + 1u) ? sm.flag[f] : (uint32_t)F_NONE;
+    PP_T0_BEGIN
+    sm.u[23] = next_bit;  // every symbol of the window was needed ...
+    PP_T0_END
+    PP_SYNC();
     if (produced >= room) {
         // Core.cs:187: the loop ends as soon as the wanted bytes are there (zlib stops mid-block)
+        // ... except here: the input is needed only up to the symbol that completes the output
+        PP_FOR_T(t)
+        if ((uint32_t)t == nlive - 1u)
+            sm.u[23] = seg_pos_at_output(sm, sm.start[t], s0 + (uint32_t)(t + 1) * kSubBits, room - sm.outc[t]);
+        PP_END_T
         produced = room;
         if (flag == F_BAD) flag = F_NONE;
     }
@@ -1180,6 +1227,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_PHASE(PH_RESOLVE);
     WindowOut w;
     w.next_bit = next_bit;
+    w.need_bit = sm.u[23];
     w.produced = produced;
     w.flag = flag;
     w.rounds = rounds;
@@ -1276,12 +1324,15 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
             else if (type == 2u) rc = dynamic_tables(sm, s0, &s0);
             else rc = -3;  // invalid block type
             if (rc) { status = rc; break; }
+            if (base_byte * 8u + s0 > d.in_limit * 8u) { status = -3; break; }  // the header itself ran past the input
             PP_PHASE(PH_HEADER);
             need_header = false;
         }
         const WindowOut w = huffman_window(sm, s0, tok, idx, mapcap, out + produced, out_len - produced);
         produced += w.produced;
         bit = base_byte * 8u + w.next_bit;
+        // Core.cs:174: the reference throws DATA_ERROR when zlib wants input past the end of fileBuffer
+        if (base_byte * 8u + w.need_bit > d.in_limit * 8u) { status = -3; break; }
 #ifdef PP_HOST_EMU
         g_stat[0]++;
         g_stat[1] += w.rounds;

@@ -362,3 +362,43 @@ def test_empty_chunk_range_and_threaded_callers(device):
     assert results[0][0] == 0 and results[half][0] == 0
     assert results[0][2] + results[half][2] == fq
     assert results[0][1] + results[half][1] >= 9000
+
+
+def test_bit_flips_agree_with_zlib(device):
+    """Random bit flips in a chunk's compressed bytes: wherever zlib (the oracle's restatement of
+    Core.ExtractDeflateIndex) produces bytes the GPU produces the same bytes, wherever the reference
+    would throw ZException(DATA_ERROR) — invalid data, or input exhausted before `len` bytes are out
+    (Core.cs:174) — the GPU path raises it too."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(7)
+    fq = corpus.fastq(4000, fixed=150, seed=2)
+    gz = corpus.gz_member(fq, 6)
+    ox = O.OracleIndex.build(gz, 700)
+    ix = pp.Core.BuildDeflateIndex(gz, 700)
+    outs, ins = ox.outputs(), ox.inputs()
+    n_err = n_ok = 0
+    for _ in range(30):
+        k = int(rng.integers(0, ox.count - 1))
+        bad = gz.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(ins[k] + 1, ins[k + 1] - 1))
+            bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        try:
+            ref = O.extract(bad, ox, k)
+        except RuntimeError:
+            ref = None
+        fb = bad[ins[k] - 1: ins[k + 1]]
+        buf = np.zeros(outs[k + 1] - outs[k], np.uint8)
+        try:
+            n = pp.Core.ExtractDeflateIndex(fb, ix, k, buf, device)
+            got = buf[:n]
+        except pp.ZException as e:
+            assert e.Code == -3
+            got = None
+        if ref is None:
+            assert got is None, f"chunk {k}: zlib reports a data error, the GPU path does not"
+            n_err += 1
+        else:
+            assert got is not None and got.size == ref.size and np.array_equal(got, ref), f"chunk {k}"
+            n_ok += 1
+    assert n_err > 0 and n_err + n_ok == 30
