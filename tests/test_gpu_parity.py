@@ -402,3 +402,71 @@ def test_bit_flips_agree_with_zlib(device):
             assert got is not None and got.size == ref.size and np.array_equal(got, ref), f"chunk {k}"
             n_ok += 1
     assert n_err > 0 and n_err + n_ok == 30
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_parse_fuzz(device, seed):
+    """Random line structures (empty lines, NULs, CRs, missing final newline, arbitrary prepend split)
+    through Parsing.Parse on the GPU against the oracle's literal restatement of Parsing.cs."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(1000 + seed)
+    alphabet = np.frombuffer(b"\n\n\n@+ACGT?\r", np.uint8)
+    for trial in range(60):
+        n = int(rng.integers(0, 4000))
+        body = alphabet[rng.integers(0, alphabet.size, n)].copy()
+        if n and rng.random() < 0.3:  # a NUL somewhere: the reference stops there
+            body[int(rng.integers(0, n))] = 0
+        if rng.random() < 0.5:        # mostly well-formed records with noise lines in between
+            recs = []
+            for i in range(int(rng.integers(1, 40))):
+                L = int(rng.integers(0, 60))
+                recs.append(b"@r%d\n" % i + bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8)) + b"\n+\n" + b"?" * L + b"\n")
+                if rng.random() < 0.1:
+                    recs.append(bytes(body[: int(rng.integers(0, 8))]))
+            body = np.frombuffer(b"".join(recs), np.uint8)
+        data = body.tobytes()
+        cut = int(rng.integers(0, len(data) + 1))
+        _parse_both(pp, device, data[:cut], data[cut:])
+
+
+def test_decompress_all_with_irregular_records(device):
+    """DecompressAll over a stream the fast parser must NOT trust: NUL bytes inside chunks (the
+    reference stops there, Parsing.cs:16,60), empty id / '+' lines (first byte skipped unchecked,
+    :19,:30), CRLF line ends.  Such chunks are routed through the exact parser; everything is
+    compared with the oracle chunk by chunk."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(6000):
+        L = int(rng.integers(20, 200))
+        seq = bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8))
+        r = b"@read%d\n" % i + seq + b"\n+\n" + b"?" * L + b"\n"
+        x = rng.random()
+        if x < 0.002:
+            r = r.replace(b"?", b"\x00", 1)           # NUL inside a quality line
+        elif x < 0.004:
+            r = b"\n" + seq + b"\n+\n" + b"?" * L + b"\n"  # empty id line
+        elif x < 0.006:
+            r = b"@read%d\n" % i + seq + b"\n\n" + b"?" * L + b"\n"  # empty '+' line
+        elif x < 0.02:
+            r = r.replace(b"\n", b"\r\n")
+        recs.append(r)
+    data = b"".join(recs)
+    gz = corpus.gz_member(data, 6, flush_every=90000)
+    ox = O.OracleIndex.build(gz, 300)
+    ix = pp.Core.BuildDeflateIndex(gz, 300)
+    job = pp.Job(device, ix, gz.size)
+    info = job.run(gz)
+    assert info.status == 0 and info.n_chunks == ox.count - 1 and info.exact_chunks > 0
+    l0, l1, l2, l3 = job.line_starts()
+    total = 0
+    for k in range(info.n_chunks):
+        n, recs_o, buf, _ = O.chunk(gz, ox, k)
+        c = job.chunk(k)
+        assert np.array_equal(job.chunk_bytes(k), buf)
+        assert c.records == n, f"chunk {k}: {c.records} != {n}"
+        s = slice(c.record_base, c.record_base + c.records)
+        assert np.array_equal(pp.fields_from_line_starts(l0[s], l1[s], l2[s], l3[s], c.parse_end), recs_o), f"chunk {k}"
+        total += n
+    assert total == info.total_records
+    job.free()
