@@ -57,11 +57,14 @@ def test_fuzz_random_streams(seed):
         assert st == 0 and np.array_equal(got, ref_all[outs[k]: outs[k] + want]), (seed, k, want)
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(6))
 def test_fuzz_bit_flips(seed):
     rng = np.random.default_rng(100 + seed)
     fq = corpus.fastq(4000, fixed=150, seed=seed)
-    gz = corpus.gz_member(fq, int(rng.choice([1, 6, 9])))
+    # seeds 4 and 5: fixed-Huffman blocks (invalid symbols 286/287 and distance codes 30/31 exist
+    # there) and sync-flushed streams (stored blocks whose LEN/NLEN can be hit)
+    kw = dict(strategy=zlib.Z_FIXED) if seed == 4 else dict(flush_every=30000) if seed == 5 else {}
+    gz = corpus.gz_member(fq, int(rng.choice([1, 6, 9])), **kw)
     ox = O.OracleIndex.build(gz, 700)
     ins = ox.inputs()
     agree_err = agree_ok = 0
