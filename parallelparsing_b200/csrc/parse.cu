@@ -271,6 +271,572 @@ return true;
 }
 
 
+
+// ---- v2: newline positions are COMPACTED into shared memory by tile-local ordinal, then every
+// thread emits whole records' worth of line starts with all lanes busy ----------------------------
+constexpr uint32_t kPosCap = 4096;  // newline positions per emission round (a 64 KB tile of 150 bp reads has ~700)
+
+// 16 flag bits (bit i = byte i is '\n') of one 16-byte vector
+__device__ __forceinline__ uint32_t nl_mask16(const uint4 x)
+{
+    // two words per multiply: flags of the first at bits 0,8,16,24, of the second at 4,12,20,28
+    const uint32_t u = (nl_bytes(x.x) >> 7) | (nl_bytes(x.y) >> 3);
+    const uint32_t v = (nl_bytes(x.z) >> 7) | (nl_bytes(x.w) >> 3);
+    return ((u * 0x01020408u) >> 24) | (((v * 0x01020408u) >> 24) << 8);
+}
+
+__device__ __forceinline__ bool pp_parse_tile2(const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc, int n,
+                                               const uint32_t *__restrict__ tile_base, uint32_t tk, int order,
+                                               uint32_t *__restrict__ lines, int64_t stride, ParseOut *__restrict__ pout,
+                                               unsigned long long *tile_state, uint32_t *warp_tot, uint32_t *pos_sh,
+                                               uint32_t *s_before_p, int lane, int warp)
+{
+    int k;
+    uint32_t ti;
+    if (order) {
+        k = (int)(tk % (uint32_t)n);
+        ti = tk / (uint32_t)n;
+        if (ti >= tile_base[k + 1] - tile_base[k]) return false;
+    } else {
+        int lo = 0, hi = n - 1;  // last chunk whose tile_base <= tk
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_base[mid] <= tk) lo = mid; else hi = mid - 1;
+        }
+        k = lo;
+        ti = tk - tile_base[k];
+    }
+    const ParseDesc d = pdesc[k];
+    if (d.exact) return false;  // handled by pp_exact_emit_kernel
+    const uint8_t *data = slots + d.data_off;
+    const uint32_t total = d.total;
+    const uint32_t head = (uint32_t)((uintptr_t)data & 15u);  // bytes before `data` in its first vector
+    const uint4 *vec0 = reinterpret_cast<const uint4 *>(data - head);
+    const uint32_t span = head + total;                       // bytes from vec0 to the end
+    const uint32_t t0 = ti * (uint32_t)kTileBytesP;
+    if (t0 >= span) return false;  // the chunk produced less than planned: nothing here, nothing after
+    const uint32_t tile = tile_base[k] + ti;                  // slot of this tile in tile_state
+    const uint32_t rec_total = d.rec_count + d.skip;          // records in the chunk before skipping
+    uint32_t *const l_base = lines + d.rec_base;
+    if (threadIdx.x == 0 && ti == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
+
+    // the byte right after the tile, fetched with the tile's loads: is it a newline?
+    uint32_t after_pos = 0xffffffffu;  // combined-memory index of that byte when it is one
+    {
+        const uint32_t nxt = t0 + (uint32_t)kTileBytesP;
+        if (threadIdx.x == kParseThreads - 1 && nxt >= head && nxt < span && data[nxt - head] == '\n') after_pos = nxt - head;
+    }
+    // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
+    uint32_t m[kTileIters][kRows];
+    const uint32_t last_vec = (span - 1u) >> 4;  // loads past the end are clamped to the last vector and masked out
+    const bool edge = t0 == 0u || t0 + (uint32_t)kTileBytesP > span;  // block-uniform
+    const uint32_t toff = t0 + (uint32_t)warp * kWarpBytes + (uint32_t)lane * 16u;  // (it, r) adds it * 16 KB + r * 512
+#pragma unroll
+    for (int half = 0; half < kTileIters; half += 2) {
+        uint4 v[2][kRows];
+#pragma unroll
+        for (int i2 = 0; i2 < 2; i2++) {
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const uint32_t vi = (toff + (uint32_t)(half + i2) * kIterBytes + (uint32_t)r * 512u) >> 4;
+                v[i2][r] = ld_stream(vec0 + (vi < last_vec ? vi : last_vec));
+            }
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 2; i2++) {
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                uint32_t mask = nl_mask16(v[i2][r]);
+                // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
+                if (edge) {
+                    const uint32_t off = toff + (uint32_t)(half + i2) * kIterBytes + (uint32_t)r * 512u;
+                    if (off >= span) mask = 0;
+                    if (off < head) mask &= 0xffffu << (head - off);
+                    if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
+                }
+                m[half + i2][r] = mask;
+            }
+        }
+    }
+    // 2. per-row counts, packed two per register, inclusive warp scans
+    uint32_t s01[kTileIters], s23[kTileIters];
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        s01[it] = __popc(m[it][0]) | (__popc(m[it][1]) << 16);
+        s23[it] = __popc(m[it][2]) | (__popc(m[it][3]) << 16);
+    }
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+#pragma unroll
+        for (int it = 0; it < kTileIters; it++) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, s01[it], sft), b = __shfl_up_sync(0xffffffffu, s23[it], sft);
+            if (lane >= sft) { s01[it] += a; s23[it] += b; }
+        }
+    }
+    uint32_t t01[kTileIters], t23[kTileIters];
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        t01[it] = __shfl_sync(0xffffffffu, s01[it], 31);
+        t23[it] = __shfl_sync(0xffffffffu, s23[it], 31);
+        if (lane == 0)
+            warp_tot[it * kParseWarps + warp] = (t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16);
+        // inclusive -> exclusive (no borrow between the halves: every field only shrinks to >= 0)
+        s01[it] -= __popc(m[it][0]) | (__popc(m[it][1]) << 16);
+        s23[it] -= __popc(m[it][2]) | (__popc(m[it][3]) << 16);
+    }
+    __syncthreads();
+    // newlines of the tile before this warp's block of step `it`: one warp scan over the 32 block totals
+    uint32_t before[kTileIters], all;
+    {
+        static_assert(kTileIters * kParseWarps == 32, "one total per lane");
+        const uint32_t mine = warp_tot[lane];
+        uint32_t inc = mine;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc, sft);
+            if (lane >= sft) inc += a;
+        }
+        all = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int it = 0; it < kTileIters; it++) before[it] = __shfl_sync(0xffffffffu, inc - mine, it * kParseWarps + warp);
+    }
+    volatile unsigned long long *st = tile_state;
+    if (threadIdx.x == 0) st[tile] = (ti == 0 ? kFlagPrefix : kFlagAgg) | all;  // successors can go on
+    uint32_t flags = 0, run = 0;
+    uint32_t lo = 0;
+    do {  // one round unless the tile holds more than kPosCap newlines
+        if (lo) __syncthreads();  // the previous round's positions have been consumed
+        // 3. compaction: position of newline `o` of the tile -> pos_sh[o - lo]  (slot kPosCap = first of the next round)
+#pragma unroll
+        for (int it = 0; it < kTileIters; it++) {
+            // tile-local ordinal of the first newline of each of this lane's vectors
+            const uint32_t tot0 = t01[it] & 0xffffu, tot1 = t01[it] >> 16, tot2 = t23[it] & 0xffffu;
+            const uint32_t bef = before[it] - lo;
+            uint32_t ex[kRows];
+            ex[0] = bef + (s01[it] & 0xffffu);
+            ex[1] = bef + tot0 + (s01[it] >> 16);
+            ex[2] = bef + tot0 + tot1 + (s23[it] & 0xffffu);
+            ex[3] = bef + tot0 + tot1 + tot2 + (s23[it] >> 16);
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                uint32_t mask = m[it][r];
+                uint32_t o = ex[r];
+                const uint32_t off = toff + (uint32_t)it * kIterBytes + (uint32_t)r * 512u - head;  // wraps only for masked-out bytes
+                while (mask) {
+                    const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+                    mask &= mask - 1u;
+                    if (o <= kPosCap) pos_sh[o] = off + b;
+                    o++;
+                }
+            }
+        }
+        if (threadIdx.x == kParseThreads - 1 && all - lo <= kPosCap) pos_sh[all - lo] = after_pos;
+        // 4. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
+        if (lo == 0 && warp == 0) {
+            uint32_t excl = 0;
+            if (ti != 0) {
+                const int64_t first = (int64_t)tile_base[k];
+                int64_t j = (int64_t)tile - 1;
+                for (;;) {
+                    const int64_t idx = j - lane;
+                    unsigned long long v;
+                    uint32_t ready, pfx;
+                    do {
+                        v = idx >= first ? st[idx] : kFlagPrefix;  // before the chunk: prefix 0
+                        ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
+                        pfx = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+                        // lanes 0..p are needed, p = nearest tile holding a prefix (all 32 if none)
+                    } while ((ready | ~(pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu)) != 0xffffffffu);
+                    const uint32_t need = pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu;
+                    uint32_t val = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
+                    excl += val;
+                    if (pfx) break;
+                    j -= 32;
+                }
+                if (lane == 0) st[tile] = kFlagPrefix | (unsigned long long)(excl + all);
+            }
+            if (lane == 0) {
+                *s_before_p = excl;
+                if (t0 + (uint32_t)kTileBytesP >= span) pout[k].newlines = excl + all;
+            }
+        }
+        __syncthreads();
+        if (lo == 0) run = *s_before_p;
+        // 5. newline `o` of the chunk ends line o: line L = o + 1 starts right after it
+        const uint32_t cnt = all - lo < kPosCap ? all - lo : kPosCap;
+        for (uint32_t j = threadIdx.x; j < cnt; j += (uint32_t)kParseThreads) {
+            const uint32_t pos = pos_sh[j], nxt = pos_sh[j + 1];
+            const uint32_t L = run + lo + j + 1u;
+            const uint32_t rec = L >> 2, f = L & 3u;
+            // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
+            if (nxt == pos + 1u && (L & 1u) == 0u && rec < rec_total) flags |= 1u;
+            if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
+            if (rec >= d.skip) {
+                if (rec < rec_total) l_base[(int64_t)f * stride + (rec - d.skip)] = pos + 1u;
+                else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
+            }
+        }
+        lo += kPosCap;
+    } while (lo < all);
+    if (flags) atomicOr(&pout[k].flags, flags);
+    return true;
+}
+
+__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel2(const uint8_t *__restrict__ slots,
+                                                                  const ParseDesc *__restrict__ pdesc, int n,
+                                                                  const uint32_t *__restrict__ tile_base,
+                                                                  uint32_t n_tickets, int order,
+                                                                  uint32_t *__restrict__ lines, int64_t stride,
+                                                                  ParseOut *__restrict__ pout,
+                                                                  const ScanTotals *__restrict__ totals,
+                                                                  unsigned long long *tile_state, uint32_t *ticket)
+{
+    __shared__ uint32_t warp_tot[kTileIters * kParseWarps];
+    __shared__ uint32_t pos_sh[kPosCap + 1];
+    __shared__ uint32_t s_ticket, s_before;
+    if (totals->overflow) return;
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    if (threadIdx.x == 32) s_ticket = atomicAdd(ticket, 1u);
+    for (;;) {
+        __syncthreads();  // s_ticket published; previous tile is done with the shared variables
+        const uint32_t tk = s_ticket;
+        if (tk >= n_tickets) break;
+        __syncthreads();  // everyone has read s_ticket
+        uint32_t next_ticket = 0;
+        if (threadIdx.x == 32) next_ticket = atomicAdd(ticket, 1u);
+        pp_parse_tile2(slots, pdesc, n, tile_base, tk, order, lines, stride, pout, tile_state, warp_tot, pos_sh, &s_before, lane, warp);
+        if (threadIdx.x == 32) s_ticket = next_ticket;
+    }
+}
+
+
+// ---- v3: warp-specialised.  A producer warp draws tickets and streams the tile into a 4 x 16 KB
+// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), one tile ahead of
+// the eight consumer warps, so no register holds bytes in flight and HBM latency is off the
+// consumers' path. ------------------------------------------------------------------------------
+constexpr int kConsumers = kParseThreads;                   // 8 warps
+constexpr int kParseThreads3 = kConsumers + 32;             // + producer warp
+constexpr uint32_t kPosCap3 = 2048;                         // newline positions per emission round (150 bp reads: ~700 per tile)
+struct TileMsg {
+    uint64_t data_off;
+    int64_t rec_base;
+    uint32_t total, rec_count, skip, k, ti, tile, first_tile, done;
+};
+struct ParseSm {
+    uint4 stage[kTileIters][kIterBytes / 16];
+    uint32_t pos[kPosCap3 + 4];
+    uint16_t tr[kParseWarps][kWarpBytes / 16];  // per warp: the 16-bit masks of one step, by vector number
+    uint32_t warp_tot[kTileIters * kParseWarps];
+    TileMsg msg[4];
+    unsigned long long full[kTileIters], empty[kTileIters];
+    uint32_t before;
+};
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ppinf::smem_u32(bar)) : "memory");
+}
+// try_wait sleeps in hardware for up to `hint_ns` per attempt, so a waiting warp issues almost nothing
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, uint32_t hint_ns)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(ppinf::smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a transfer that never lands must not hang the GPU
+    }
+}
+
+// ticket -> tile; false when the ticket names nothing to do
+__device__ __forceinline__ bool ticket_to_tile(const ParseDesc *__restrict__ pdesc, int n, const uint32_t *__restrict__ tile_base,
+                                               uint32_t tk, int order, TileMsg &g)
+{
+    int k;
+    uint32_t ti;
+    if (order) {
+        k = (int)(tk % (uint32_t)n);
+        ti = tk / (uint32_t)n;
+        if (ti >= tile_base[k + 1] - tile_base[k]) return false;
+    } else {
+        int lo = 0, hi = n - 1;  // last chunk whose tile_base <= tk
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_base[mid] <= tk) lo = mid; else hi = mid - 1;
+        }
+        k = lo;
+        ti = tk - tile_base[k];
+    }
+    const ParseDesc d = pdesc[k];
+    if (d.exact) return false;  // handled by pp_exact_emit_kernel
+    const uint32_t head = (uint32_t)(d.data_off & 15u);
+    if ((uint64_t)ti * kTileBytesP >= (uint64_t)head + d.total) return false;  // the chunk produced less than planned
+    g.data_off = d.data_off;
+    g.rec_base = d.rec_base;
+    g.total = d.total;
+    g.rec_count = d.rec_count;
+    g.skip = d.skip;
+    g.k = (uint32_t)k;
+    g.ti = ti;
+    g.first_tile = tile_base[k];
+    g.tile = g.first_tile + ti;
+    g.done = 0;
+    return true;
+}
+
+__device__ __forceinline__ void parse_producer(ParseSm &sm, const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc,
+                                               int n, const uint32_t *__restrict__ tile_base, uint32_t n_tickets, int order,
+                                               uint32_t *ticket)
+{
+    uint32_t tile_no = 0;
+    uint32_t tk = atomicAdd(ticket, 1u);
+    while (tk < n_tickets) {
+        const uint32_t next = atomicAdd(ticket, 1u);  // in flight while this tile is set up
+        TileMsg g;
+        if (ticket_to_tile(pdesc, n, tile_base, tk, order, g)) {
+            // slot tile_no & 3 was last used by tile_no - 4: every consumer left that tile before it
+            // released the last stage of tile_no - 3, which the loads of tile_no - 2 waited for
+            sm.msg[tile_no & 3u] = g;
+            const uint32_t head = (uint32_t)(g.data_off & 15u);
+            const uint8_t *src = slots + g.data_off - head + (uint64_t)g.ti * kTileBytesP;
+            const uint32_t span16 = (head + g.total + 15u) & ~15u;
+            const uint32_t t0 = g.ti * (uint32_t)kTileBytesP;
+#pragma unroll
+            for (int it = 0; it < kTileIters; it++) {
+                mbar_wait_or_trap(&sm.empty[it], (tile_no & 1u) ^ 1u, 20000u);
+                const uint32_t o = t0 + (uint32_t)it * kIterBytes;
+                const uint32_t bytes = o >= span16 ? 0u : (span16 - o < (uint32_t)kIterBytes ? span16 - o : (uint32_t)kIterBytes);
+                if (bytes) {
+                    ppinf::mbar_expect_tx(&sm.full[it], bytes);
+                    ppinf::tma_load(sm.stage[it], src + (uint32_t)it * kIterBytes, bytes, &sm.full[it]);
+                } else {
+                    mbar_arrive(&sm.full[it]);
+                }
+            }
+            tile_no++;
+        }
+        tk = next;
+    }
+    sm.msg[tile_no & 3u].done = 1u;
+    mbar_wait_or_trap(&sm.empty[0], (tile_no & 1u) ^ 1u, 20000u);
+    mbar_arrive(&sm.full[0]);
+}
+
+// positions of the newlines of this lane's 64-byte blocks -> sm.pos[tile-local ordinal - lo]
+template <bool kChecked>
+__device__ __forceinline__ void compact_positions(ParseSm &sm, const uint32_t (&mlo)[kTileIters], const uint32_t (&mhi)[kTileIters],
+                                                  const uint32_t (&ex)[kTileIters / 2], const uint32_t (&before)[kTileIters],
+                                                  uint32_t rel, uint32_t lo)
+{
+#pragma unroll
+    for (int it = 0; it < kTileIters; it++) {
+        uint32_t o = before[it] - lo + ((ex[it >> 1] >> ((it & 1) * 16)) & 0xffffu);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t mask = h ? mhi[it] : mlo[it];
+            const uint32_t off = rel + (uint32_t)it * kIterBytes + (uint32_t)h * 32u;  // wraps only for masked-out bytes
+            while (mask) {
+                const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                if (!kChecked || o <= kPosCap3) sm.pos[o] = off + b;
+                o++;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint8_t *__restrict__ slots,
+                                                                   const ParseDesc *__restrict__ pdesc, int n,
+                                                                   const uint32_t *__restrict__ tile_base,
+                                                                   uint32_t n_tickets, int order,
+                                                                   uint32_t *__restrict__ lines, int64_t stride,
+                                                                   ParseOut *__restrict__ pout,
+                                                                   const ScanTotals *__restrict__ totals,
+                                                                   unsigned long long *tile_state, uint32_t *ticket)
+{
+    extern __shared__ __align__(128) uint8_t parse_smem_raw[];
+    ParseSm &sm = *reinterpret_cast<ParseSm *>(parse_smem_raw);
+    if (totals->overflow) return;
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kTileIters; i++) {
+            ppinf::mbar_init(&sm.full[i], 1);
+            ppinf::mbar_init(&sm.empty[i], kParseWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kParseWarps) {  // producer
+        if (lane == 0) parse_producer(sm, slots, pdesc, n, tile_base, n_tickets, order, ticket);
+        return;
+    }
+    volatile unsigned long long *st = tile_state;
+    for (uint32_t tile_no = 0;; tile_no++) {
+        const uint32_t par = tile_no & 1u;
+        mbar_wait_or_trap(&sm.full[0], par, 2000u);
+        const volatile TileMsg *g = &sm.msg[tile_no & 3u];
+        if (g->done) break;
+        const uint64_t data_off = g->data_off;
+        const uint32_t total = g->total, skip = g->skip, k = g->k, ti = g->ti, tile = g->tile;
+        const uint32_t rec_total = g->rec_count + skip;  // records in the chunk before skipping
+        uint32_t *const l_base = lines + g->rec_base;
+        const int64_t first = (int64_t)g->first_tile;
+        const uint8_t *data = slots + data_off;
+        const uint32_t head = (uint32_t)(data_off & 15u);  // bytes before `data` in its first vector
+        const uint32_t span = head + total;                  // bytes from the first vector to the end
+        const uint32_t t0 = ti * (uint32_t)kTileBytesP;
+        if (threadIdx.x == 0 && ti == 0 && rec_total > skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
+        // the byte right after the tile: is it a newline?
+        uint32_t after_pos = 0xffffffffu;  // combined-memory index of that byte when it is one
+        {
+            const uint32_t nxt = t0 + (uint32_t)kTileBytesP;
+            if (threadIdx.x == kConsumers - 1 && nxt < span && data[nxt - head] == '\n') after_pos = nxt - head;
+        }
+        // 1. newline masks from the staged bytes: 16 bits per vector, then regrouped through shared memory so
+        //    that every lane holds the 64-bit mask of 64 CONSECUTIVE bytes (one count, one loop per step)
+        uint32_t mlo[kTileIters], mhi[kTileIters];
+        const bool edge = t0 == 0u || t0 + (uint32_t)kTileBytesP > span;  // block-uniform
+        const uint32_t toff = t0 + (uint32_t)warp * kWarpBytes + (uint32_t)lane * 16u;  // (it, r) adds it * 16 KB + r * 512
+        uint16_t *const tr = sm.tr[warp];
+#pragma unroll
+        for (int it = 0; it < kTileIters; it++) {
+            if (it) mbar_wait_or_trap(&sm.full[it], par, 2000u);
+            uint4 v[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; r++) v[r] = sm.stage[it][warp * (kWarpBytes / 16) + r * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                uint32_t mask = nl_mask16(v[r]);
+                // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
+                if (edge) {
+                    const uint32_t off = toff + (uint32_t)it * kIterBytes + (uint32_t)r * 512u;
+                    if (off >= span) mask = 0;
+                    if (off < head) mask &= 0xffffu << (head - off);
+                    if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
+                }
+                tr[r * 32 + lane] = (uint16_t)mask;
+            }
+            __syncwarp();
+            const uint2 mm = *reinterpret_cast<const uint2 *>(tr + lane * 4);  // vectors 4*lane .. 4*lane+3
+            mlo[it] = mm.x;
+            mhi[it] = mm.y;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[it]);  // this warp is done with the stage
+        }
+        // 2. per-step counts, packed two per register, inclusive warp scans
+        uint32_t cnt2[kTileIters / 2], ex[kTileIters / 2];
+#pragma unroll
+        for (int h = 0; h < kTileIters / 2; h++) {
+            cnt2[h] = (uint32_t)(__popc(mlo[2 * h]) + __popc(mhi[2 * h])) |
+                      ((uint32_t)(__popc(mlo[2 * h + 1]) + __popc(mhi[2 * h + 1])) << 16);
+            ex[h] = cnt2[h];
+        }
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+#pragma unroll
+            for (int h = 0; h < kTileIters / 2; h++) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, ex[h], sft);
+                if (lane >= sft) ex[h] += a;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < kTileIters / 2; h++) {
+            const uint32_t t = __shfl_sync(0xffffffffu, ex[h], 31);
+            if (lane == 0) {
+                sm.warp_tot[(2 * h) * kParseWarps + warp] = t & 0xffffu;
+                sm.warp_tot[(2 * h + 1) * kParseWarps + warp] = t >> 16;
+            }
+            ex[h] -= cnt2[h];  // inclusive -> exclusive (no borrow between the halves)
+        }
+        consumer_sync();
+        // newlines of the tile before this warp's block of step `it`: one warp scan over the 32 block totals
+        uint32_t before[kTileIters], all;
+        {
+            static_assert(kTileIters * kParseWarps == 32, "one total per lane");
+            const uint32_t mine = sm.warp_tot[lane];
+            uint32_t inc = mine;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, inc, sft);
+                if (lane >= sft) inc += a;
+            }
+            all = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+            for (int it = 0; it < kTileIters; it++) before[it] = __shfl_sync(0xffffffffu, inc - mine, it * kParseWarps + warp);
+        }
+        if (threadIdx.x == 0) st[tile] = (ti == 0 ? kFlagPrefix : kFlagAgg) | all;  // successors can go on
+        uint32_t flags = 0, run = 0;
+        uint32_t lo = 0;
+        do {  // one round unless the tile holds more than kPosCap3 newlines
+            if (lo) consumer_sync();  // the previous round's positions have been consumed
+            // 3. compaction (slot kPosCap3 = first position of the next round)
+            const uint32_t rel = t0 + (uint32_t)warp * kWarpBytes + (uint32_t)lane * 64u - head;
+            if (all <= kPosCap3) compact_positions<false>(sm, mlo, mhi, ex, before, rel, 0u);
+            else compact_positions<true>(sm, mlo, mhi, ex, before, rel, lo);
+            if (threadIdx.x == kConsumers - 1 && all - lo <= kPosCap3) sm.pos[all - lo] = after_pos;
+            // 4. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
+            if (lo == 0 && warp == 0) {
+                uint32_t excl = 0;
+                if (ti != 0) {
+                    int64_t j = (int64_t)tile - 1;
+                    for (;;) {
+                        const int64_t idx = j - lane;
+                        unsigned long long v;
+                        uint32_t ready, pfx;
+                        do {
+                            v = idx >= first ? st[idx] : kFlagPrefix;  // before the chunk: prefix 0
+                            ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
+                            pfx = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+                            // lanes 0..p are needed, p = nearest tile holding a prefix (all 32 if none)
+                        } while ((ready | ~(pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu)) != 0xffffffffu);
+                        const uint32_t need = pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu;
+                        uint32_t val = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
+                        excl += val;
+                        if (pfx) break;
+                        j -= 32;
+                    }
+                    if (lane == 0) st[tile] = kFlagPrefix | (unsigned long long)(excl + all);
+                }
+                if (lane == 0) {
+                    sm.before = excl;
+                    if (t0 + (uint32_t)kTileBytesP >= span) pout[k].newlines = excl + all;
+                }
+            }
+            consumer_sync();
+            if (lo == 0) run = sm.before;
+            // 5. newline `o` of the chunk ends line o: line L = o + 1 starts right after it
+            const uint32_t cnt = all - lo < kPosCap3 ? all - lo : kPosCap3;
+            for (uint32_t j = threadIdx.x; j < cnt; j += (uint32_t)kConsumers) {
+                const uint32_t pos = sm.pos[j], nxt = sm.pos[j + 1];
+                const uint32_t L = run + lo + j + 1u;
+                const uint32_t rec = L >> 2, f = L & 3u;
+                // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
+                if (nxt == pos + 1u && (L & 1u) == 0u && rec < rec_total) flags |= 1u;
+                if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
+                if (rec >= skip) {
+                    if (rec < rec_total) l_base[(int64_t)f * stride + (rec - skip)] = pos + 1u;
+                    else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
+                }
+            }
+            lo += kPosCap3;
+        } while (lo < all);
+        if (flags) atomicOr(&pout[k].flags, flags);
+    }
+}
+
 // order 0: ticket = global tile number (tile_base[k] + i); order 1: ticket = i * n + k
 __global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel(const uint8_t *__restrict__ slots,
                                                                  const ParseDesc *__restrict__ pdesc, int n,
@@ -591,6 +1157,25 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
     const uint32_t n_tickets = order ? (uint32_t)rr : total_tiles;
     const uint32_t resident = (uint32_t)sm_count * (2048u / kParseThreads);
     const uint32_t grid = n_tickets < resident ? n_tickets : resident;
+    static const int ver = getenv("PPB200_PARSE_V") ? atoi(getenv("PPB200_PARSE_V")) : 3;
+    if (ver == 3) {
+        static int per_sm = 0;
+        if (!per_sm) {
+            e = cudaFuncSetAttribute(pp_parse_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSm));
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_parse_kernel3, kParseThreads3, sizeof(ParseSm));
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        }
+        // the look-back needs every CTA of the grid resident
+        const uint32_t res3 = (uint32_t)sm_count * (uint32_t)per_sm;
+        const uint32_t grid3 = n_tickets < res3 ? n_tickets : res3;
+        pp_parse_kernel3<<<grid3, kParseThreads3, sizeof(ParseSm), st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines,
+                                                                         line_stride, pout, totals, work, ticket);
+    } else if (ver == 2)
+        pp_parse_kernel2<<<grid, kParseThreads, 0, st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
+                                                         pout, totals, work, ticket);
+    else
     pp_parse_kernel<<<grid, kParseThreads, 0, st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
                                                     pout, totals, work, ticket);
     return cudaGetLastError();
