@@ -21,28 +21,23 @@
 
 namespace pp {
 
-constexpr int kParseThreads = 256;
-constexpr int kParseWarps = kParseThreads / 32;
-constexpr int kRows = 4;                                   // 16-byte vectors per lane per iteration
-constexpr int kWarpBytes = 32 * 16 * kRows;                // 2 KB per warp per iteration
-constexpr int kIterBytes = kWarpBytes * kParseWarps;       // 16 KB per CTA per iteration
+constexpr int kConsumers = 256;                            // eight consumer warps
+constexpr int kParseWarps = kConsumers / 32;
+constexpr int kParseThreads = kConsumers + 32;             // + the producer warp
+constexpr int kRows = 4;                                   // 16-byte vectors per lane per step
+constexpr int kWarpBytes = 32 * 16 * kRows;                // 2 KB per warp per step
+constexpr int kIterBytes = kWarpBytes * kParseWarps;       // 16 KB per CTA per step = one ring stage
 
-// 0x80 in every byte of w that equals '\n'
+// 0x80 in every byte of w that equals '\n' (exact for any byte values), three instructions:
+// per byte, ((b & 0x7f) ^ 0x0a) + 0x7f has bit 7 set iff the low seven bits differ from 0x0a
+// (no carry leaves the byte), and bit 7 of b itself must be clear
 __device__ __forceinline__ uint32_t nl_bytes(uint32_t w)
 {
-    const uint32_t x = w ^ 0x0a0a0a0au;
-    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
-}
-// gather bits 7,15,23,31 into a nibble
-__device__ __forceinline__ uint32_t nibble(uint32_t t) { return ((t >> 7) * 0x01020408u) >> 24 & 15u; }
-
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
-{
-    uint4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
+    uint32_t x, t;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(x) : "r"(w), "r"(0x7f7f7f7fu), "r"(0x0a0a0a0au));  // (w & A) ^ B
+    x += 0x7f7f7f7fu;
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(t) : "r"(x), "r"(w), "r"(0x80808080u));  // ~(x | w) & C
+    return t;
 }
 
 // Tile-parallel: the combined memory of every chunk is cut into 64 KB tiles and the tiles of
@@ -53,472 +48,35 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 // prefix).  Tickets go round-robin over the chunks (tile r of every chunk, then tile r+1 ...),
 // so the predecessor of a running tile has normally finished long ago and the look-back is one
 // step.  One pass over the bytes, no second read.
+//
+// The CTA is warp-specialised.  A producer warp draws the tickets and streams each tile into a
+// 4 x 16 KB shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), one
+// tile ahead of the eight consumer warps, so no register holds bytes in flight and HBM latency is
+// off the consumers' path.  The consumers turn every 16-byte vector into a 16-bit newline mask
+// (SWAR), regroup the masks through shared memory so that each lane owns 64 CONSECUTIVE bytes (one
+// count to scan and one short loop per step instead of four), rank the newlines with warp/block
+// scans, write their positions into a shared array by tile-local ordinal, and then emit the line
+// starts with all lanes busy: thread j handles newline j, consecutive lanes write consecutive
+// records.  (The first version let every lane walk its own mask bits and store straight to global
+// memory: five of 32 lanes active, 134 warp instructions per 512 bytes; this one needs ~70.)
 // lines: four arrays of `stride` u32 each (line 0..3), record r of the chunk at rec_base + r.
 constexpr int kTileIters = 4;                               // 16 KB steps per tile
 constexpr int kTileBytesP = kIterBytes * kTileIters;        // 64 KB
 #define kFlagAgg (1ull << 32)
 #define kFlagPrefix (2ull << 32)
 
-__device__ __forceinline__ bool pp_parse_tile(const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc, int n,
-                                              const uint32_t *__restrict__ tile_base, uint32_t tk, int order,
-                                              uint32_t *__restrict__ lines, int64_t stride, ParseOut *__restrict__ pout,
-                                              unsigned long long *tile_state, uint32_t (*warp_tot)[kParseWarps],
-                                              uint32_t *s_before_p, int lane, int warp)
-{
-    int k;
-    uint32_t ti;
-    if (order) {
-        k = (int)(tk % (uint32_t)n);
-        ti = tk / (uint32_t)n;
-        if (ti >= tile_base[k + 1] - tile_base[k]) return false;
-    } else {
-        int lo = 0, hi = n - 1;  // last chunk whose tile_base <= tk
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_base[mid] <= tk) lo = mid; else hi = mid - 1;
-        }
-        k = lo;
-        ti = tk - tile_base[k];
-    }
-    const ParseDesc d = pdesc[k];
-    if (d.exact) return false;  // handled by pp_exact_emit_kernel
-    const uint8_t *data = slots + d.data_off;
-    const uint32_t total = d.total;
-    const uint32_t head = (uint32_t)((uintptr_t)data & 15u);  // bytes before `data` in its first vector
-    const uint4 *vec0 = reinterpret_cast<const uint4 *>(data - head);
-    const uint32_t span = head + total;                       // bytes from vec0 to the end
-    const uint32_t t0 = ti * (uint32_t)kTileBytesP;
-    if (t0 >= span) return false;  // the chunk produced less than planned: nothing here, nothing after
-    const uint32_t tile = tile_base[k] + ti;                  // slot of this tile in tile_state
-    const uint32_t rec_total = d.rec_count + d.skip;          // records in the chunk before skipping
-    uint32_t *const l_base = lines + d.rec_base;
-    if (threadIdx.x == 0 && ti == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
-
-    // the byte right after the tile (successor of its last vector), fetched with the tile's loads
-    uint32_t tile_next = 0;
-    {
-        const uint32_t nxt = t0 + (uint32_t)kTileBytesP;
-        if (warp == kParseWarps - 1 && lane == 31 && nxt >= head && nxt < span) tile_next = data[nxt - head];
-    }
-    // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
-    uint32_t m[kTileIters][kRows];
-    const uint32_t last_vec = (span - 1u) >> 4;  // loads past the end are clamped to the last vector and masked out
-    const bool edge = t0 == 0u || t0 + (uint32_t)kTileBytesP > span;  // block-uniform
-#pragma unroll
-    for (int half = 0; half < kTileIters; half += 2) {
-        uint4 v[2][kRows];
-#pragma unroll
-        for (int i2 = 0; i2 < 2; i2++) {
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                const uint32_t off = t0 + (uint32_t)(half + i2) * kIterBytes + (uint32_t)warp * kWarpBytes +
-                                     (uint32_t)r * 512u + (uint32_t)lane * 16u;
-                const uint32_t vi = off >> 4;
-                v[i2][r] = ld_stream(vec0 + (vi < last_vec ? vi : last_vec));
-            }
-        }
-#pragma unroll
-        for (int i2 = 0; i2 < 2; i2++) {
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                const uint32_t off = t0 + (uint32_t)(half + i2) * kIterBytes + (uint32_t)warp * kWarpBytes +
-                                     (uint32_t)r * 512u + (uint32_t)lane * 16u;
-                const uint4 x = v[i2][r];
-                uint32_t mask = nibble(nl_bytes(x.x)) | (nibble(nl_bytes(x.y)) << 4) | (nibble(nl_bytes(x.z)) << 8) |
-                                (nibble(nl_bytes(x.w)) << 12);
-                // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
-                if (edge) {
-                    if (off >= span) mask = 0;
-                    if (off < head) mask &= 0xffffu << (head - off);
-                    if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
-                }
-                m[half + i2][r] = mask;
-            }
-        }
-    }
-    // 2. per-row counts, packed two per register, inclusive warp scans
-    uint32_t c01[kTileIters], c23[kTileIters], s01[kTileIters], s23[kTileIters];
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        c01[it] = __popc(m[it][0]) | (__popc(m[it][1]) << 16);
-        c23[it] = __popc(m[it][2]) | (__popc(m[it][3]) << 16);
-        s01[it] = c01[it];
-        s23[it] = c23[it];
-    }
-#pragma unroll
-    for (int sft = 1; sft < 32; sft <<= 1) {
-#pragma unroll
-        for (int it = 0; it < kTileIters; it++) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, s01[it], sft), b = __shfl_up_sync(0xffffffffu, s23[it], sft);
-            if (lane >= sft) { s01[it] += a; s23[it] += b; }
-        }
-    }
-    uint32_t t01[kTileIters], t23[kTileIters];
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        t01[it] = __shfl_sync(0xffffffffu, s01[it], 31);
-        t23[it] = __shfl_sync(0xffffffffu, s23[it], 31);
-        // bit 31: the block's first byte is a newline (the successor bit of the block before it)
-        if (lane == 0)
-            warp_tot[it][warp] = ((t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16)) |
-                                 ((m[it][0] & 1u) << 31);
-    }
-    __syncthreads();
-    uint32_t before[kTileIters], all = 0;
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        before[it] = all;
-#pragma unroll
-        for (int w = 0; w < kParseWarps; w++) {
-            const uint32_t t = warp_tot[it][w] & 0x7fffffffu;
-            if (w < warp) before[it] += t;
-            all += t;
-        }
-    }
-    // 3. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
-    if (warp == 0) {
-        volatile unsigned long long *st = tile_state;
-        uint32_t excl = 0;
-        if (ti == 0) {
-            if (lane == 0) st[tile] = kFlagPrefix | all;
-        } else {
-            if (lane == 0) st[tile] = kFlagAgg | all;
-            const int64_t first = (int64_t)tile_base[k];
-            int64_t j = (int64_t)tile - 1;
-            for (;;) {
-                const int64_t idx = j - lane;
-                unsigned long long v;
-                uint32_t ready, pfx;
-                do {
-                    v = idx >= first ? st[idx] : kFlagPrefix;  // before the chunk: prefix 0
-                    ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
-                    pfx = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
-                    // lanes 0..p are needed, p = nearest tile holding a prefix (all 32 if none)
-                } while ((ready | ~(pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu)) != 0xffffffffu);
-                const uint32_t need = pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu;
-                uint32_t val = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
-                excl += val;
-                if (pfx) break;
-                j -= 32;
-            }
-            if (lane == 0) st[tile] = kFlagPrefix | (unsigned long long)(excl + all);
-        }
-        if (lane == 0) {
-            *s_before_p = excl;
-            if (t0 + (uint32_t)kTileBytesP >= span) pout[k].newlines = excl + all;
-        }
-    }
-    __syncthreads();
-    const uint32_t run = *s_before_p;
-    // 4. every newline knows its ordinal: line L = ordinal + 1 starts right after it
-    uint32_t flags = 0;
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        const uint32_t wbase = t0 + (uint32_t)it * kIterBytes + (uint32_t)warp * kWarpBytes;
-        if (wbase >= span) break;
-        // successor bit of every vector: is the byte right after it a newline?
-        uint32_t fb = 0;
-#pragma unroll
-        for (int r = 0; r < kRows; r++) fb |= (m[it][r] & 1u) << r;
-        uint32_t nfb = __shfl_down_sync(0xffffffffu, fb, 1);
-        const uint32_t fb0 = __shfl_sync(0xffffffffu, fb, 0);
-        if (lane == 31) {
-            nfb = fb0 >> 1;  // rows 0..2 continue at lane 0 of the next row
-            // first byte after this warp's block: the next warp's block, the next step's first
-            // block, or (last block of the tile) the byte fetched above
-            uint32_t nb;
-            if (warp + 1 < kParseWarps) nb = warp_tot[it][warp + 1] >> 31;
-            else if (it + 1 < kTileIters) nb = warp_tot[it + 1][0] >> 31;
-            else nb = tile_next == '\n';
-            nfb |= nb << (kRows - 1);
-        }
-        const uint32_t tot0 = t01[it] & 0xffffu, tot1 = t01[it] >> 16, tot2 = t23[it] & 0xffffu;
-        const uint32_t bef = run + before[it];
-        uint32_t ex[kRows];
-        ex[0] = bef + (s01[it] & 0xffffu) - (c01[it] & 0xffffu);
-        ex[1] = bef + tot0 + (s01[it] >> 16) - (c01[it] >> 16);
-        ex[2] = bef + tot0 + tot1 + (s23[it] & 0xffffu) - (c23[it] & 0xffffu);
-        ex[3] = bef + tot0 + tot1 + tot2 + (s23[it] >> 16) - (c23[it] >> 16);
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            uint32_t mask = m[it][r];
-            if (mask == 0) continue;
-            const uint32_t off = wbase + (uint32_t)r * 512u + (uint32_t)lane * 16u;
-            // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
-            const uint32_t mm = mask | (((nfb >> r) & 1u) << 16);
-            const uint32_t pairs = mm & (mm >> 1) & 0xffffu;
-            uint32_t ord = ex[r];
-            while (mask) {
-                const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
-                mask &= mask - 1u;
-                const uint32_t pos = off + b - head;  // combined-memory index of this '\n'
-                const uint32_t L = ord + 1u;          // the line that starts at pos + 1
-                const uint32_t rec = L >> 2, f = L & 3u;
-                if (((pairs >> b) & 1u) && (L & 1u) == 0u && rec < rec_total) flags |= 1u;
-                if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
-                if (rec >= d.skip) {
-                    if (rec < rec_total) l_base[(int64_t)f * stride + (rec - d.skip)] = pos + 1u;
-                    else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
-                }
-                ord++;
-            }
-        }
-    }
-    if (flags) atomicOr(&pout[k].flags, flags);
-return true;
-}
-
-
-
-// ---- v2: newline positions are COMPACTED into shared memory by tile-local ordinal, then every
-// thread emits whole records' worth of line starts with all lanes busy ----------------------------
-constexpr uint32_t kPosCap = 4096;  // newline positions per emission round (a 64 KB tile of 150 bp reads has ~700)
-
-// 16 flag bits (bit i = byte i is '\n') of one 16-byte vector
+// 16 flag bits (bit i = byte i is '\n') of one 16-byte vector in the LOW HALF of the result; the high
+// half is not defined
 __device__ __forceinline__ uint32_t nl_mask16(const uint4 x)
 {
-    // two words per multiply: flags of the first at bits 0,8,16,24, of the second at 4,12,20,28
-    const uint32_t u = (nl_bytes(x.x) >> 7) | (nl_bytes(x.y) >> 3);
-    const uint32_t v = (nl_bytes(x.z) >> 7) | (nl_bytes(x.w) >> 3);
-    return ((u * 0x01020408u) >> 24) | (((v * 0x01020408u) >> 24) << 8);
+    // two words per multiply: the flags of the first word at bits 8j+3, of the second at bits 8j+7;
+    // times 2^21 + 2^14 + 2^7 + 1 they land, in order and without any carry, in bits 24..31
+    const uint32_t u = (nl_bytes(x.x) >> 4) | nl_bytes(x.y);
+    const uint32_t v = (nl_bytes(x.z) >> 4) | nl_bytes(x.w);
+    return __byte_perm(u * 0x00204081u, v * 0x00204081u, 0x0073);
 }
 
-__device__ __forceinline__ bool pp_parse_tile2(const uint8_t *__restrict__ slots, const ParseDesc *__restrict__ pdesc, int n,
-                                               const uint32_t *__restrict__ tile_base, uint32_t tk, int order,
-                                               uint32_t *__restrict__ lines, int64_t stride, ParseOut *__restrict__ pout,
-                                               unsigned long long *tile_state, uint32_t *warp_tot, uint32_t *pos_sh,
-                                               uint32_t *s_before_p, int lane, int warp)
-{
-    int k;
-    uint32_t ti;
-    if (order) {
-        k = (int)(tk % (uint32_t)n);
-        ti = tk / (uint32_t)n;
-        if (ti >= tile_base[k + 1] - tile_base[k]) return false;
-    } else {
-        int lo = 0, hi = n - 1;  // last chunk whose tile_base <= tk
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_base[mid] <= tk) lo = mid; else hi = mid - 1;
-        }
-        k = lo;
-        ti = tk - tile_base[k];
-    }
-    const ParseDesc d = pdesc[k];
-    if (d.exact) return false;  // handled by pp_exact_emit_kernel
-    const uint8_t *data = slots + d.data_off;
-    const uint32_t total = d.total;
-    const uint32_t head = (uint32_t)((uintptr_t)data & 15u);  // bytes before `data` in its first vector
-    const uint4 *vec0 = reinterpret_cast<const uint4 *>(data - head);
-    const uint32_t span = head + total;                       // bytes from vec0 to the end
-    const uint32_t t0 = ti * (uint32_t)kTileBytesP;
-    if (t0 >= span) return false;  // the chunk produced less than planned: nothing here, nothing after
-    const uint32_t tile = tile_base[k] + ti;                  // slot of this tile in tile_state
-    const uint32_t rec_total = d.rec_count + d.skip;          // records in the chunk before skipping
-    uint32_t *const l_base = lines + d.rec_base;
-    if (threadIdx.x == 0 && ti == 0 && rec_total > d.skip) l_base[0] = 0;  // record 0 starts at 0 (when not skipped)
-
-    // the byte right after the tile, fetched with the tile's loads: is it a newline?
-    uint32_t after_pos = 0xffffffffu;  // combined-memory index of that byte when it is one
-    {
-        const uint32_t nxt = t0 + (uint32_t)kTileBytesP;
-        if (threadIdx.x == kParseThreads - 1 && nxt >= head && nxt < span && data[nxt - head] == '\n') after_pos = nxt - head;
-    }
-    // 1. all loads of the tile in flight together; newline masks, 16 bits per vector
-    uint32_t m[kTileIters][kRows];
-    const uint32_t last_vec = (span - 1u) >> 4;  // loads past the end are clamped to the last vector and masked out
-    const bool edge = t0 == 0u || t0 + (uint32_t)kTileBytesP > span;  // block-uniform
-    const uint32_t toff = t0 + (uint32_t)warp * kWarpBytes + (uint32_t)lane * 16u;  // (it, r) adds it * 16 KB + r * 512
-#pragma unroll
-    for (int half = 0; half < kTileIters; half += 2) {
-        uint4 v[2][kRows];
-#pragma unroll
-        for (int i2 = 0; i2 < 2; i2++) {
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                const uint32_t vi = (toff + (uint32_t)(half + i2) * kIterBytes + (uint32_t)r * 512u) >> 4;
-                v[i2][r] = ld_stream(vec0 + (vi < last_vec ? vi : last_vec));
-            }
-        }
-#pragma unroll
-        for (int i2 = 0; i2 < 2; i2++) {
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                uint32_t mask = nl_mask16(v[i2][r]);
-                // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
-                if (edge) {
-                    const uint32_t off = toff + (uint32_t)(half + i2) * kIterBytes + (uint32_t)r * 512u;
-                    if (off >= span) mask = 0;
-                    if (off < head) mask &= 0xffffu << (head - off);
-                    if (off + 16u > span && off < span) mask &= 0xffffu >> (off + 16u - span);
-                }
-                m[half + i2][r] = mask;
-            }
-        }
-    }
-    // 2. per-row counts, packed two per register, inclusive warp scans
-    uint32_t s01[kTileIters], s23[kTileIters];
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        s01[it] = __popc(m[it][0]) | (__popc(m[it][1]) << 16);
-        s23[it] = __popc(m[it][2]) | (__popc(m[it][3]) << 16);
-    }
-#pragma unroll
-    for (int sft = 1; sft < 32; sft <<= 1) {
-#pragma unroll
-        for (int it = 0; it < kTileIters; it++) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, s01[it], sft), b = __shfl_up_sync(0xffffffffu, s23[it], sft);
-            if (lane >= sft) { s01[it] += a; s23[it] += b; }
-        }
-    }
-    uint32_t t01[kTileIters], t23[kTileIters];
-#pragma unroll
-    for (int it = 0; it < kTileIters; it++) {
-        t01[it] = __shfl_sync(0xffffffffu, s01[it], 31);
-        t23[it] = __shfl_sync(0xffffffffu, s23[it], 31);
-        if (lane == 0)
-            warp_tot[it * kParseWarps + warp] = (t01[it] & 0xffffu) + (t01[it] >> 16) + (t23[it] & 0xffffu) + (t23[it] >> 16);
-        // inclusive -> exclusive (no borrow between the halves: every field only shrinks to >= 0)
-        s01[it] -= __popc(m[it][0]) | (__popc(m[it][1]) << 16);
-        s23[it] -= __popc(m[it][2]) | (__popc(m[it][3]) << 16);
-    }
-    __syncthreads();
-    // newlines of the tile before this warp's block of step `it`: one warp scan over the 32 block totals
-    uint32_t before[kTileIters], all;
-    {
-        static_assert(kTileIters * kParseWarps == 32, "one total per lane");
-        const uint32_t mine = warp_tot[lane];
-        uint32_t inc = mine;
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, inc, sft);
-            if (lane >= sft) inc += a;
-        }
-        all = __shfl_sync(0xffffffffu, inc, 31);
-#pragma unroll
-        for (int it = 0; it < kTileIters; it++) before[it] = __shfl_sync(0xffffffffu, inc - mine, it * kParseWarps + warp);
-    }
-    volatile unsigned long long *st = tile_state;
-    if (threadIdx.x == 0) st[tile] = (ti == 0 ? kFlagPrefix : kFlagAgg) | all;  // successors can go on
-    uint32_t flags = 0, run = 0;
-    uint32_t lo = 0;
-    do {  // one round unless the tile holds more than kPosCap newlines
-        if (lo) __syncthreads();  // the previous round's positions have been consumed
-        // 3. compaction: position of newline `o` of the tile -> pos_sh[o - lo]  (slot kPosCap = first of the next round)
-#pragma unroll
-        for (int it = 0; it < kTileIters; it++) {
-            // tile-local ordinal of the first newline of each of this lane's vectors
-            const uint32_t tot0 = t01[it] & 0xffffu, tot1 = t01[it] >> 16, tot2 = t23[it] & 0xffffu;
-            const uint32_t bef = before[it] - lo;
-            uint32_t ex[kRows];
-            ex[0] = bef + (s01[it] & 0xffffu);
-            ex[1] = bef + tot0 + (s01[it] >> 16);
-            ex[2] = bef + tot0 + tot1 + (s23[it] & 0xffffu);
-            ex[3] = bef + tot0 + tot1 + tot2 + (s23[it] >> 16);
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                uint32_t mask = m[it][r];
-                uint32_t o = ex[r];
-                const uint32_t off = toff + (uint32_t)it * kIterBytes + (uint32_t)r * 512u - head;  // wraps only for masked-out bytes
-                while (mask) {
-                    const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
-                    mask &= mask - 1u;
-                    if (o <= kPosCap) pos_sh[o] = off + b;
-                    o++;
-                }
-            }
-        }
-        if (threadIdx.x == kParseThreads - 1 && all - lo <= kPosCap) pos_sh[all - lo] = after_pos;
-        // 4. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
-        if (lo == 0 && warp == 0) {
-            uint32_t excl = 0;
-            if (ti != 0) {
-                const int64_t first = (int64_t)tile_base[k];
-                int64_t j = (int64_t)tile - 1;
-                for (;;) {
-                    const int64_t idx = j - lane;
-                    unsigned long long v;
-                    uint32_t ready, pfx;
-                    do {
-                        v = idx >= first ? st[idx] : kFlagPrefix;  // before the chunk: prefix 0
-                        ready = __ballot_sync(0xffffffffu, (v >> 32) != 0ull);
-                        pfx = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
-                        // lanes 0..p are needed, p = nearest tile holding a prefix (all 32 if none)
-                    } while ((ready | ~(pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu)) != 0xffffffffu);
-                    const uint32_t need = pfx ? ((pfx & (0u - pfx)) << 1) - 1u : 0xffffffffu;
-                    uint32_t val = ((need >> lane) & 1u) ? (uint32_t)v : 0u;
-#pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
-                    excl += val;
-                    if (pfx) break;
-                    j -= 32;
-                }
-                if (lane == 0) st[tile] = kFlagPrefix | (unsigned long long)(excl + all);
-            }
-            if (lane == 0) {
-                *s_before_p = excl;
-                if (t0 + (uint32_t)kTileBytesP >= span) pout[k].newlines = excl + all;
-            }
-        }
-        __syncthreads();
-        if (lo == 0) run = *s_before_p;
-        // 5. newline `o` of the chunk ends line o: line L = o + 1 starts right after it
-        const uint32_t cnt = all - lo < kPosCap ? all - lo : kPosCap;
-        for (uint32_t j = threadIdx.x; j < cnt; j += (uint32_t)kParseThreads) {
-            const uint32_t pos = pos_sh[j], nxt = pos_sh[j + 1];
-            const uint32_t L = run + lo + j + 1u;
-            const uint32_t rec = L >> 2, f = L & 3u;
-            // an empty line 0 or 2 is where Parsing.cs:19,30 diverge from "every '\n' ends a line"
-            if (nxt == pos + 1u && (L & 1u) == 0u && rec < rec_total) flags |= 1u;
-            if (pos == 0u) flags |= 1u;  // the chunk starts with an empty id line
-            if (rec >= d.skip) {
-                if (rec < rec_total) l_base[(int64_t)f * stride + (rec - d.skip)] = pos + 1u;
-                else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
-            }
-        }
-        lo += kPosCap;
-    } while (lo < all);
-    if (flags) atomicOr(&pout[k].flags, flags);
-    return true;
-}
-
-__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel2(const uint8_t *__restrict__ slots,
-                                                                  const ParseDesc *__restrict__ pdesc, int n,
-                                                                  const uint32_t *__restrict__ tile_base,
-                                                                  uint32_t n_tickets, int order,
-                                                                  uint32_t *__restrict__ lines, int64_t stride,
-                                                                  ParseOut *__restrict__ pout,
-                                                                  const ScanTotals *__restrict__ totals,
-                                                                  unsigned long long *tile_state, uint32_t *ticket)
-{
-    __shared__ uint32_t warp_tot[kTileIters * kParseWarps];
-    __shared__ uint32_t pos_sh[kPosCap + 1];
-    __shared__ uint32_t s_ticket, s_before;
-    if (totals->overflow) return;
-    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
-    if (threadIdx.x == 32) s_ticket = atomicAdd(ticket, 1u);
-    for (;;) {
-        __syncthreads();  // s_ticket published; previous tile is done with the shared variables
-        const uint32_t tk = s_ticket;
-        if (tk >= n_tickets) break;
-        __syncthreads();  // everyone has read s_ticket
-        uint32_t next_ticket = 0;
-        if (threadIdx.x == 32) next_ticket = atomicAdd(ticket, 1u);
-        pp_parse_tile2(slots, pdesc, n, tile_base, tk, order, lines, stride, pout, tile_state, warp_tot, pos_sh, &s_before, lane, warp);
-        if (threadIdx.x == 32) s_ticket = next_ticket;
-    }
-}
-
-
-// ---- v3: warp-specialised.  A producer warp draws tickets and streams the tile into a 4 x 16 KB
-// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), one tile ahead of
-// the eight consumer warps, so no register holds bytes in flight and HBM latency is off the
-// consumers' path. ------------------------------------------------------------------------------
-constexpr int kConsumers = kParseThreads;                   // 8 warps
-constexpr int kParseThreads3 = kConsumers + 32;             // + producer warp
-constexpr uint32_t kPosCap3 = 2048;                         // newline positions per emission round (150 bp reads: ~700 per tile)
+constexpr uint32_t kPosCap = 2048;  // newline positions per emission round (a tile of 150 bp reads holds ~700)
 struct TileMsg {
     uint64_t data_off;
     int64_t rec_base;
@@ -526,7 +84,7 @@ struct TileMsg {
 };
 struct ParseSm {
     uint4 stage[kTileIters][kIterBytes / 16];
-    uint32_t pos[kPosCap3 + 4];
+    uint32_t pos[kPosCap + 4];
     uint16_t tr[kParseWarps][kWarpBytes / 16];  // per warp: the 16-bit masks of one step, by vector number
     uint32_t warp_tot[kTileIters * kParseWarps];
     TileMsg msg[4];
@@ -648,14 +206,14 @@ __device__ __forceinline__ void compact_positions(ParseSm &sm, const uint32_t (&
             while (mask) {
                 const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
                 mask &= mask - 1u;
-                if (!kChecked || o <= kPosCap3) sm.pos[o] = off + b;
+                if (!kChecked || o <= kPosCap) sm.pos[o] = off + b;
                 o++;
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint8_t *__restrict__ slots,
+__global__ void __launch_bounds__(kParseThreads, 3) pp_parse_kernel(const uint8_t *__restrict__ slots,
                                                                    const ParseDesc *__restrict__ pdesc, int n,
                                                                    const uint32_t *__restrict__ tile_base,
                                                                    uint32_t n_tickets, int order,
@@ -720,6 +278,7 @@ __global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint
                 uint32_t mask = nl_mask16(v[r]);
                 // bytes outside [head, span) are not part of the chunk (only a chunk's first and last tile)
                 if (edge) {
+                    mask &= 0xffffu;
                     const uint32_t off = toff + (uint32_t)it * kIterBytes + (uint32_t)r * 512u;
                     if (off >= span) mask = 0;
                     if (off < head) mask &= 0xffffu << (head - off);
@@ -778,13 +337,13 @@ __global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint
         if (threadIdx.x == 0) st[tile] = (ti == 0 ? kFlagPrefix : kFlagAgg) | all;  // successors can go on
         uint32_t flags = 0, run = 0;
         uint32_t lo = 0;
-        do {  // one round unless the tile holds more than kPosCap3 newlines
+        do {  // one round unless the tile holds more than kPosCap newlines
             if (lo) consumer_sync();  // the previous round's positions have been consumed
-            // 3. compaction (slot kPosCap3 = first position of the next round)
+            // 3. compaction (slot kPosCap = first position of the next round)
             const uint32_t rel = t0 + (uint32_t)warp * kWarpBytes + (uint32_t)lane * 64u - head;
-            if (all <= kPosCap3) compact_positions<false>(sm, mlo, mhi, ex, before, rel, 0u);
+            if (all <= kPosCap) compact_positions<false>(sm, mlo, mhi, ex, before, rel, 0u);
             else compact_positions<true>(sm, mlo, mhi, ex, before, rel, lo);
-            if (threadIdx.x == kConsumers - 1 && all - lo <= kPosCap3) sm.pos[all - lo] = after_pos;
+            if (threadIdx.x == kConsumers - 1 && all - lo <= kPosCap) sm.pos[all - lo] = after_pos;
             // 4. decoupled look-back over the earlier tiles of this chunk (warp 0, 32 tiles per step)
             if (lo == 0 && warp == 0) {
                 uint32_t excl = 0;
@@ -818,7 +377,7 @@ __global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint
             consumer_sync();
             if (lo == 0) run = sm.before;
             // 5. newline `o` of the chunk ends line o: line L = o + 1 starts right after it
-            const uint32_t cnt = all - lo < kPosCap3 ? all - lo : kPosCap3;
+            const uint32_t cnt = all - lo < kPosCap ? all - lo : kPosCap;
             for (uint32_t j = threadIdx.x; j < cnt; j += (uint32_t)kConsumers) {
                 const uint32_t pos = sm.pos[j], nxt = sm.pos[j + 1];
                 const uint32_t L = run + lo + j + 1u;
@@ -831,38 +390,9 @@ __global__ void __launch_bounds__(kParseThreads3, 3) pp_parse_kernel3(const uint
                     else if (L == rec_total * 4u) pout[k].parse_end = pos + 1u;
                 }
             }
-            lo += kPosCap3;
+            lo += kPosCap;
         } while (lo < all);
         if (flags) atomicOr(&pout[k].flags, flags);
-    }
-}
-
-// order 0: ticket = global tile number (tile_base[k] + i); order 1: ticket = i * n + k
-__global__ void __launch_bounds__(kParseThreads, 4) pp_parse_kernel(const uint8_t *__restrict__ slots,
-                                                                 const ParseDesc *__restrict__ pdesc, int n,
-                                                                 const uint32_t *__restrict__ tile_base,
-                                                                 uint32_t n_tickets, int order,
-                                                                 uint32_t *__restrict__ lines, int64_t stride,
-                                                                 ParseOut *__restrict__ pout,
-                                                                 const ScanTotals *__restrict__ totals,
-                                                                 unsigned long long *tile_state, uint32_t *ticket)
-{
-    __shared__ uint32_t warp_tot[kTileIters][kParseWarps];
-    __shared__ uint32_t s_ticket, s_before;
-    if (totals->overflow) return;
-    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
-    // the ticket of the NEXT tile is drawn while the current one is processed (thread 32 holds it in
-    // a register until the end of the iteration), so its round trip never sits in front of the loads
-    if (threadIdx.x == 32) s_ticket = atomicAdd(ticket, 1u);
-    for (;;) {
-        __syncthreads();  // s_ticket published; previous tile is done with the shared variables
-        const uint32_t tk = s_ticket;
-        if (tk >= n_tickets) break;
-        __syncthreads();  // everyone has read s_ticket
-        uint32_t next_ticket = 0;
-        if (threadIdx.x == 32) next_ticket = atomicAdd(ticket, 1u);
-        if (pp_parse_tile(slots, pdesc, n, tile_base, tk, order, lines, stride, pout, tile_state, warp_tot, &s_before, lane, warp)) {}
-        if (threadIdx.x == 32) s_ticket = next_ticket;
     }
 }
 
@@ -1155,29 +685,23 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
     int order = rr <= 4ull * total_tiles && rr < 0xffffffffull ? 1 : 0;
     if (const char *e = getenv("PPB200_PARSE_ORDER")) order = atoi(e) ? order : 0;  // 0 forces linear tickets
     const uint32_t n_tickets = order ? (uint32_t)rr : total_tiles;
-    const uint32_t resident = (uint32_t)sm_count * (2048u / kParseThreads);
+    static int per_sm_of[64];  // per device: the attribute lives in the device's context
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int &per_sm = per_sm_of[dev & 63];
+    if (!per_sm) {
+        e = cudaFuncSetAttribute(pp_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSm));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_parse_kernel, kParseThreads, sizeof(ParseSm));
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    // the look-back needs every CTA of the grid resident
+    const uint32_t resident = (uint32_t)sm_count * (uint32_t)per_sm;
     const uint32_t grid = n_tickets < resident ? n_tickets : resident;
-    static const int ver = getenv("PPB200_PARSE_V") ? atoi(getenv("PPB200_PARSE_V")) : 3;
-    if (ver == 3) {
-        static int per_sm = 0;
-        if (!per_sm) {
-            e = cudaFuncSetAttribute(pp_parse_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSm));
-            if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_parse_kernel3, kParseThreads3, sizeof(ParseSm));
-            if (e != cudaSuccess) return e;
-            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        }
-        // the look-back needs every CTA of the grid resident
-        const uint32_t res3 = (uint32_t)sm_count * (uint32_t)per_sm;
-        const uint32_t grid3 = n_tickets < res3 ? n_tickets : res3;
-        pp_parse_kernel3<<<grid3, kParseThreads3, sizeof(ParseSm), st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines,
-                                                                         line_stride, pout, totals, work, ticket);
-    } else if (ver == 2)
-        pp_parse_kernel2<<<grid, kParseThreads, 0, st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
-                                                         pout, totals, work, ticket);
-    else
-    pp_parse_kernel<<<grid, kParseThreads, 0, st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
-                                                    pout, totals, work, ticket);
+    pp_parse_kernel<<<grid, kParseThreads, sizeof(ParseSm), st>>>(slots, pdesc, n, tile_base, n_tickets, order, lines, line_stride,
+                                                                  pout, totals, work, ticket);
     return cudaGetLastError();
 }
 cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
