@@ -561,110 +561,148 @@ PP_DEV int fixed_tables(const Sm &sm)
 }
 
 // Dynamic block header at window-relative bit `pos` (just past the 3 block-type bits):
-// HLIT/HDIST/HCLEN, the code-length code and the run-length coded lengths (thread 0),
-// then both tables (all threads).  On success *pos_out is the first symbol's bit.
+// HLIT/HDIST/HCLEN, the code-length code, the run-length coded lengths, then both tables.
+// On success *pos_out is the first symbol's bit.
+//
+// The run-length coded lengths are a serial bit stream (every symbol's position depends on
+// the one before), and one GPU thread needs ~140 cycles per symbol for "refill, look up,
+// shift, store".  So the lookups are done SPECULATIVELY for every bit position by all threads
+// (node[p] = bits consumed | repeat count | symbol of the symbol that would start at p), and
+// thread 0 only follows the chain p -> p + bits(node[p]): one dependent shared-memory load per
+// symbol.  It records (first index, repeat, value) per symbol; all threads then expand the runs.
+// Scratch: sm.lit (the table it is about to build), sm.dist[0..127], sm.wsum.
 PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 {
-    PP_T0_BEGIN
-    {
-        int err = 0;
-        const uint32_t nlen = peek_bits(sm.cw, pos, 5) + 257u;
-        const uint32_t ndist = peek_bits(sm.cw, pos + 5, 5) + 1u;
-        const uint32_t ncode = peek_bits(sm.cw, pos + 10, 4) + 4u;
-        uint32_t p = pos + 14;
-        if (nlen > 286u || ndist > 30u) err = 1;  // too many length or distance symbols
-        // code-length code: 19 symbols with 3-bit lengths.  7-bit direct lookup table kept in
-        // sm.dist (free at this point): entry = sym | len << 8, 0 = invalid
-        uint8_t cl[19];
-        for (int i = 0; i < 19; i++) cl[i] = 0;
-        for (uint32_t i = 0; i < ncode; i++) { cl[kClOrder[i]] = (uint8_t)peek_bits(sm.cw, p, 3); p += 3; }
-        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nxt[8];
-        for (int i = 0; i < 19; i++) cnt[cl[i]]++;
-        int left = 1;
-        for (int l = 1; l <= 7; l++) {
-            left <<= 1;
-            left -= (int)cnt[l];
-            if (left < 0) err = 1;
-        }
-        if (left > 0) err = 1;  // zlib: the code-length code must be complete
-        if (!err) {
-            uint32_t code = 0;
-            for (int l = 1; l <= 7; l++) {
-                code = (code + (l > 1 ? cnt[l - 1] : 0u)) << 1;
-                nxt[l] = code;
-            }
-            for (int i = 0; i < 128; i++) sm.dist[i] = 0;
-            for (uint32_t s = 0; s < 19; s++) {
-                const uint32_t l = cl[s];
-                if (!l) continue;
-                const uint32_t base = bitrev(nxt[l]++, (int)l);
-                for (uint32_t j = base; j < 128u; j += 1u << l) sm.dist[j] = s | (l << 8) | 0x8000u;
-            }
-            uint32_t have = 0;
-            const uint32_t total = nlen + ndist;
-            // bit buffer in registers: one table lookup per code-length symbol on the critical path
-            uint32_t wq = p >> 5;
-            uint64_t bb = ((uint64_t)sm.cw[wq] | ((uint64_t)sm.cw[wq + 1] << 32)) >> (p & 31u);
-            uint32_t bc = 64u - (p & 31u);
-            wq += 2;
-            while (have < total && !err) {
-                if (bc < 32u) { bb |= (uint64_t)sm.cw[wq] << bc; bc += 32u; wq++; }
-                const uint32_t e = sm.dist[(uint32_t)bb & 127u];
-                if (!e) { err = 1; break; }
-                const uint32_t l = (e >> 8) & 15u;
-                bb >>= l;
-                bc -= l;
-                const uint32_t sym = e & 255u;
-                if (sym < 16u) {
-                    sm.lens[have++] = (uint8_t)sym;
-                } else {
-                    uint32_t rep, val = 0, xb;
-                    if (sym == 16u) {
-                        if (have == 0) { err = 1; break; }  // invalid bit length repeat
-                        val = sm.lens[have - 1];
-                        rep = 3u + ((uint32_t)bb & 3u);
-                        xb = 2;
-                    } else if (sym == 17u) {
-                        rep = 3u + ((uint32_t)bb & 7u);
-                        xb = 3;
-                    } else {
-                        rep = 11u + ((uint32_t)bb & 127u);
-                        xb = 7;
-                    }
-                    bb >>= xb;
-                    bc -= xb;
-                    if (have + rep > total) { err = 1; break; }  // invalid bit length repeat
-                    for (uint32_t j = 0; j < rep; j++) sm.lens[have + j] = (uint8_t)val;
-                    have += rep;
-                }
-            }
-            p = wq * 32u - bc;
-            if (!err && sm.lens[256] == 0) err = 1;  // invalid code -- missing end-of-block
-            if (!err) {
-                // distance lengths follow the literal/length lengths: move them to lens[288..]
-                uint8_t tmp[32];
-                for (uint32_t i = 0; i < ndist; i++) tmp[i] = sm.lens[nlen + i];
-                for (uint32_t i = 0; i < ndist; i++) sm.lens[288 + i] = tmp[i];
-                for (uint32_t i = nlen; i < 288u; i++) sm.lens[i] = 0;
-                for (uint32_t i = 288u + ndist; i < 320u; i++) sm.lens[i] = 0;
-            }
-        }
-        sm.u[0] = (uint32_t)err;
-        sm.u[3] = nlen;
-        sm.u[4] = ndist;
-        sm.u[5] = p;
+    uint32_t *const chain = sm.lit;        // [320] symbols on the true path: first index | repeat << 9 | value << 17
+    uint32_t *const node = sm.lit + 512;   // [T] one round of speculative decodes
+    uint32_t *const clv = sm.wsum;         // [19] lengths of the code-length code
+    const uint32_t nlen = peek_bits(sm.cw, pos, 5) + 257u;
+    const uint32_t ndist = peek_bits(sm.cw, pos + 5, 5) + 1u;
+    const uint32_t ncode = peek_bits(sm.cw, pos + 10, 4) + 4u;
+    const uint32_t total = nlen + ndist;
+    const uint32_t p0 = pos + 14u + 3u * ncode;
+    PP_FOR_T(t)
+    for (int i = t; i < 320; i += PP_NT) sm.lens[i] = 0;
+    for (int i = t; i < 128; i += PP_NT) sm.dist[i] = 0;
+    if (t < 19) clv[kClOrder[t]] = (uint32_t)t < ncode ? peek_bits(sm.cw, pos + 14u + 3u * (uint32_t)t, 3) : 0u;
+    if (t == 0) {
+        sm.u[0] = (nlen > 286u || ndist > 30u) ? 1u : 0u;  // too many length or distance symbols
+        sm.u[3] = 0;   // lengths produced
+        sm.u[4] = 0;   // chain entries
+        sm.u[5] = p0;  // bit position of the walk
+        sm.u[6] = 0;   // previous length (for symbol 16)
     }
-    PP_T0_END
+    PP_END_T
+    PP_SYNC();
+    // code-length code: 7-bit direct lookup table in sm.dist: entry = sym | len << 8 | 0x8000, 0 = invalid.
+    // One thread per symbol: its canonical code is first[len] + (symbols before it with the same length).
+    PP_FOR_T(t)
+    if (t < 19) {
+        const uint32_t l = clv[t];
+        uint64_t cnt = 0;  // eight 8-bit counters, one per length
+        uint32_t rank = 0;
+        for (int i = 0; i < 19; i++) {
+            const uint32_t li = clv[i];
+            cnt += 1ull << (8u * li);
+            if (i < t && li == l) rank++;
+        }
+        int left = 1, bad = 0;
+        uint32_t code = 0, prev = 0, mine = 0;
+        for (uint32_t k = 1; k <= 7u; k++) {
+            const uint32_t c = (uint32_t)(cnt >> (8u * k)) & 255u;
+            left = (left << 1) - (int)c;
+            if (left < 0) bad = 1;
+            code = (code + prev) << 1;
+            if (k == l) mine = code + rank;
+            prev = c;
+        }
+        if (left > 0) bad = 1;  // zlib: the code-length code must be complete
+        if (bad) {
+            if (t == 0) sm.u[0] = 1;
+        } else if (l) {
+            for (uint32_t j = bitrev(mine, (int)l); j < 128u; j += 1u << l) sm.dist[j] = (uint32_t)t | (l << 8) | 0x8000u;
+        }
+    }
+    PP_END_T
     PP_SYNC();
     if (sm.u[0]) { PP_SYNC(); return -3; }
-    const int nlen = (int)sm.u[3], ndist = (int)sm.u[4];
+    const uint32_t pmax = p0 + 4440u;  // 316 symbols of at most 14 bits: the true path never gets here
+    for (uint32_t base = p0;; base += (uint32_t)PP_NT) {
+        PP_FOR_T(t)
+        {
+            const uint32_t q = base + (uint32_t)t;
+            uint32_t nd = 0;
+            if (q < pmax) {
+                const uint32_t bits = peek_bits(sm.cw, q, 14);
+                const uint32_t e = sm.dist[bits & 127u];
+                if (e) {
+                    const uint32_t l = (e >> 8) & 15u, sym = e & 255u, x = bits >> l;
+                    uint32_t n = l, rep = 1;
+                    if (sym == 16u) { rep = 3u + (x & 3u); n += 2u; }
+                    else if (sym == 17u) { rep = 3u + (x & 7u); n += 3u; }
+                    else if (sym == 18u) { rep = 11u + (x & 127u); n += 7u; }
+                    nd = n | (rep << 4) | (sym << 12) | 0x80000000u;
+                }
+            }
+            node[t] = nd;
+        }
+        PP_END_T
+        PP_SYNC();
+        PP_T0_BEGIN
+        {
+            uint32_t q = sm.u[5], have = sm.u[3], k = sm.u[4], last = sm.u[6], err = 0;
+            const uint32_t lim = base + (uint32_t)PP_NT;
+            while (have < total && q < lim) {
+                const uint32_t nd = node[q - base];
+                if (!nd) { err = 1; break; }  // invalid code
+                const uint32_t rep = (nd >> 4) & 255u, sym = (nd >> 12) & 31u;
+                uint32_t val = 0;
+                if (sym < 16u) {
+                    val = sym;
+                    last = sym;
+                } else if (sym == 16u) {
+                    if (have == 0) { err = 1; break; }  // invalid bit length repeat
+                    val = last;
+                } else {
+                    last = 0;
+                }
+                if (have + rep > total) { err = 1; break; }  // invalid bit length repeat
+                chain[k++] = have | (rep << 9) | (val << 17);
+                have += rep;
+                q += nd & 15u;
+            }
+            sm.u[5] = q;
+            sm.u[3] = have;
+            sm.u[4] = k;
+            sm.u[6] = last;
+            if (err) sm.u[0] = 1;
+            sm.u[7] = (err || have >= total) ? 1u : 0u;
+        }
+        PP_T0_END
+        PP_SYNC();
+        if (sm.u[7]) break;
+    }
+    if (sm.u[0]) { PP_SYNC(); return -3; }
+    const uint32_t nch = sm.u[4];
+    // runs -> lens: lit/len lengths at 0, distance lengths (they follow in the stream) at 288
+    PP_FOR_T(t)
+    for (uint32_t k = (uint32_t)t; k < nch; k += (uint32_t)PP_NT) {
+        const uint32_t c = chain[k], val = c >> 17;
+        if (val) {
+            const uint32_t h0 = c & 511u, h1 = h0 + ((c >> 9) & 255u);
+            for (uint32_t h = h0; h < h1; h++) sm.lens[h < nlen ? h : h + 288u - nlen] = (uint8_t)val;
+        }
+    }
+    PP_END_T
+    PP_SYNC();
+    if (sm.lens[256] == 0) { PP_SYNC(); return -3; }  // invalid code -- missing end-of-block
     *pos_out = sm.u[5];
     PP_SYNC();
     PP_PHASE(PH_H_PARSE);
-    int rc = build_table(sm, sm.lit, kRootL, kLitCap, nlen, 0, 0);
+    int rc = build_table(sm, sm.lit, kRootL, kLitCap, (int)nlen, 0, 0);
     PP_PHASE(PH_H_LIT);
     if (rc) return rc;
-    return build_table(sm, sm.dist, kRootD, kDistCap, ndist, 288, 1);
+    return build_table(sm, sm.dist, kRootD, kDistCap, (int)ndist, 288, 1);
 }
 
 // ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
