@@ -46,8 +46,13 @@ def ensure_built():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, d)])
 
 
+LONG = {"mean": 0.0, "sigma": 0.0, "cap": 0}  # --lognormal / --cap (BASELINE config 4: long reads)
+
+
 def corpus_paths(reads, fixed, seed, chunk):
     key = f"gen_s{seed}_r{reads}_L{fixed}_gz6"
+    if LONG["mean"]:
+        key += f"_ln{LONG['mean']:g}_{LONG['sigma']:g}_cap{LONG['cap']}"
     d = os.path.join(CACHE, key)
     return d, os.path.join(d, "reads.fastq.gz"), os.path.join(d, f"chunk{chunk}.gzi"), os.path.join(d, "meta.json")
 
@@ -61,7 +66,11 @@ def make_corpus(reads, fixed, seed, chunk):
         t = time.time()
         tmp = gz_path + f".tmp{os.getpid()}"
         gen = [os.path.join(ROOT, "tools", "_build", "ppgen"), str(reads), "--seed", str(seed)]
-        if fixed:
+        if LONG["mean"]:
+            gen += ["--lognormal", str(LONG["mean"]), str(LONG["sigma"])]
+            if LONG["cap"]:
+                gen += ["--cap", str(LONG["cap"])]
+        elif fixed:
             gen += ["--fixed", str(fixed)]
         p1 = subprocess.Popen(gen, stdout=subprocess.PIPE)
         p2 = subprocess.Popen([os.path.join(ROOT, "tools", "_build", "ppgzip"), "-l", "6", "-", tmp], stdin=p1.stdout)
@@ -72,7 +81,9 @@ def make_corpus(reads, fixed, seed, chunk):
         log(f"[bench] corpus {reads} reads -> {os.path.getsize(gz_path)/1e6:.1f} MB gz in {time.time()-t:.1f}s")
     if not os.path.exists(idx_path):
         t = time.time()
-        ix = pp.Core.BuildDeflateIndex(gz_path, chunk)
+        # records longer than 32 768 B make the reference's CreateIndex throw (quirk H2): lifted only for
+        # uncapped long reads, a documented extension
+        ix = pp.Core.BuildDeflateIndex(gz_path, chunk, lift_record_cap=bool(LONG["mean"]) and not LONG["cap"])
         tmp = idx_path + f".tmp{os.getpid()}"
         pp.IndexIO.Serialize(ix, tmp)
         os.replace(tmp, idx_path)
@@ -201,13 +212,22 @@ def main():
     ap.add_argument("--fixed-len", type=int, default=150)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lognormal", type=float, nargs=2, metavar=("MEAN", "SIGMA"),
+                    help="read lengths lognormal with this mean (BASELINE config 4: --lognormal 10000 0.5 --chunk 1000)")
+    ap.add_argument("--cap", type=int, default=0, help="clamp read lengths (16000 keeps records reference-legal, H2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = (f"Generator seed {args.seed}, {args.reads} reads x {args.fixed_len}bp single-end, gzip -6 "
+    if args.lognormal:
+        LONG.update(mean=args.lognormal[0], sigma=args.lognormal[1], cap=args.cap)
+        args.fixed_len = 0
+    lens = (f"lognormal lengths (mean {LONG['mean']:g} bp, sigma {LONG['sigma']:g}"
+            f"{', capped at ' + str(LONG['cap']) if LONG['cap'] else ', uncapped: record cap lifted'})"
+            if LONG["mean"] else f"{args.fixed_len}bp")
+    workload = (f"Generator seed {args.seed}, {args.reads} reads x {lens} single-end, gzip -6 "
                 f"(one member), chunk {args.chunk}")
     cores = os.cpu_count() or 1
 
