@@ -1090,8 +1090,8 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
         PP_END_W
         PP_SYNC();
         PP_PHASE(PH_R_GATHER);
-        // CHASE + store
-        PP_FOR_T(t)
+        // CHASE: follow in-tile sources through shared memory (published pointer jumping, no barrier)
+        PP_FOR_W(t)
         {
             const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
             const uint32_t pb = qb;
@@ -1115,21 +1115,54 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
                     }
                 }
             }
-            // every entry is 0x8000|byte now: '\n' is 0x800a, NUL is the smallest possible value 0x8000
-            uint32_t nl = 0, mn = 0xffffu;
-#pragma unroll
-            for (int j = 0; j < kTileB; j++) {
-                const uint32_t v = tb + qb + (uint32_t)j * 32u;
-                if (v - a < total) {  // a <= v < vend
-                    vbase[v] = (uint8_t)e[j];
-                    nl += (e[j] == 0x800au);
-                    mn = e[j] < mn ? e[j] : mn;
-                }
-            }
-            sm.nl[t] += nl;
-            sm.nul[t] |= (mn == 0x8000u);
         }
-        PP_END_T
+        // STORE: every entry of the warp's 512 bytes is 0x8000|byte in shared memory now; thread t takes
+        // the group it expanded (bytes 16 t .. 16 t + 15 of the tile) and writes it with one 16-byte store
+        PP_WARP_SPLIT(t)
+        {
+            const uint32_t q0 = (uint32_t)t * kTileB;
+            const uint32_t v0 = tb + q0;
+            uint32_t lo = v0 < a ? a - v0 : 0u;
+            uint32_t hi = v0 < vend ? (vend - v0 < (uint32_t)kTileB ? vend - v0 : (uint32_t)kTileB) : 0u;
+            if (lo > hi) lo = hi;
+            if (lo < hi) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(sm.res + q0);
+                const uint4 r0 = src[0], r1 = src[1];
+                uint32_t w[4];
+#ifdef PP_HOST_EMU
+#define PP_PACK(x, y) (((x) & 0xffu) | (((x) >> 8) & 0xff00u) | (((y) & 0xffu) << 16) | (((y) << 8) & 0xff000000u))
+#else
+#define PP_PACK(x, y) __byte_perm((x), (y), 0x6420)
+#endif
+                w[0] = PP_PACK(r0.x, r0.y); w[1] = PP_PACK(r0.z, r0.w);
+                w[2] = PP_PACK(r1.x, r1.y); w[3] = PP_PACK(r1.z, r1.w);
+#undef PP_PACK
+                uint32_t nl = 0, nul = 0;
+                if (hi - lo == (uint32_t)kTileB) {
+                    uint32_t nz = 0x80808080u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t x = ((w[j] & 0x7f7f7f7fu) ^ 0x0a0a0a0au) + 0x7f7f7f7fu;
+                        nl += popc32(~(x | w[j]) & 0x80808080u);                 // bytes equal to '\n'
+                        nz &= ((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w[j];        // bit 7 of a byte survives iff it is not NUL
+                    }
+                    nul = nz != 0x80808080u;
+                    uint4 o;
+                    o.x = w[0]; o.y = w[1]; o.z = w[2]; o.w = w[3];
+                    *reinterpret_cast<uint4 *>(vbase + v0) = o;
+                } else {  // first / last group of the window
+                    for (uint32_t j = lo; j < hi; j++) {
+                        const uint32_t byte = (uint32_t)res[q0 + j] & 0xffu;
+                        vbase[v0 + j] = (uint8_t)byte;
+                        nl += (byte == 0x0au);
+                        nul |= (byte == 0u);
+                    }
+                }
+                sm.nl[t] += nl;
+                sm.nul[t] |= nul;
+            }
+        }
+        PP_END_W
         PP_SYNC();  // stores visible to the next tile's gathers; res free again
         PP_PHASE(PH_R_CHASE);
     }
