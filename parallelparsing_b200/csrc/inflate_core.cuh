@@ -796,18 +796,19 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
 }
 
 // GUESS / SYNC walk of one segment with CHECKPOINTS.  Slot c (c = 0..kCkpt-1) of a thread is the
-// first symbol boundary at or after bit tgt0 + c * kCkptStep of its sub-sequence, stored as
-// {position, output bytes from there to the end of the segment}.  A decoder that restarts at a
-// corrected bit falls back onto the old path's boundaries after a few symbols; as soon as it
+// first symbol boundary at or after bit tgt0 + c * kCkptStep of its sub-sequence, stored as one
+// word: position relative to `base` (the sub-sequence's first bit; < 2048) | output bytes from
+// there to the end of the segment << 11 (a segment emits < 128 Ki bytes).  A decoder that restarts
+// at a corrected bit falls back onto the old path's boundaries after a few symbols; as soon as it
 // stands exactly on the old path's boundary for the slot it is passing, the rest of the segment is
 // already known: it stops there and reuses the stored suffix (end, flag and later slots are
-// unchanged), so a SYNC round costs a fraction of a full pass.  cp: [2 * kCkpt][T] words,
-// positions first, then suffixes (aliases the resolve tile buffer, which is idle while decoding).
-constexpr int kCkpt = 3;
+// unchanged), so a SYNC round costs a fraction of a full pass.  cp: [kCkpt][T] words (aliases the
+// resolve tile buffer, which is idle while decoding).
+constexpr int kCkpt = 7;
 constexpr uint32_t kCkptStep = (uint32_t)kSubBits / (kCkpt + 1);
 constexpr uint32_t kNoCkpt = 0xffffffffu;
 
-PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t tgt0, uint32_t *cp, uint32_t T,
+PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t base, uint32_t *cp, uint32_t T,
                         uint32_t t, bool have_old, uint32_t old_end, uint32_t old_flag)
 {
     const uint32_t *cw = sm.cw;
@@ -817,21 +818,19 @@ PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t t
     uint32_t cnt = 64u - sh;
     wp += 2;
     uint32_t out = 0, flag = F_NONE;
-    uint32_t c = 0, next_t = tgt0;
-    uint32_t npos0 = kNoCkpt, npos1 = kNoCkpt, npos2 = kNoCkpt, ncum0 = 0, ncum1 = 0, ncum2 = 0;
+    uint32_t c = 0, next_t = base + kCkptStep;
     bool reused = false;
     for (;;) {
         const uint32_t pos = wp * 32u - cnt;
         if (pos >= limit) break;
         if (pos >= next_t && c < (uint32_t)kCkpt) {
-            if (have_old && cp[c * T + t] == pos) {  // on the old path: the rest is known
-                out += cp[((uint32_t)kCkpt + c) * T + t];
+            const uint32_t old = cp[c * T + t];
+            if (have_old && old != kNoCkpt && (old & 2047u) == pos - base) {  // on the old path: the rest is known
+                out += old >> 11;
                 reused = true;
                 break;
             }
-            if (c == 0) { npos0 = pos; ncum0 = out; }
-            else if (c == 1) { npos1 = pos; ncum1 = out; }
-            else { npos2 = pos; ncum2 = out; }
+            cp[c * T + t] = (pos - base) | (out << 11);  // bytes BEFORE the boundary for now; turned into the suffix below
             c++;
             next_t += kCkptStep;
         }
@@ -882,9 +881,10 @@ PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t t
     r.out = out;
     r.ntok = 0;
     // slots passed on the way (before the reuse point, or all of them) now describe the new path
-    if (c > 0) { cp[0 * T + t] = npos0; cp[((uint32_t)kCkpt + 0) * T + t] = out - ncum0; }
-    if (c > 1) { cp[1 * T + t] = npos1; cp[((uint32_t)kCkpt + 1) * T + t] = out - ncum1; }
-    if (c > 2) { cp[2 * T + t] = npos2; cp[((uint32_t)kCkpt + 2) * T + t] = out - ncum2; }
+    for (uint32_t j = 0; j < c; j++) {
+        const uint32_t w = cp[j * T + t];
+        cp[j * T + t] = (w & 2047u) | ((out - (w >> 11)) << 11);
+    }
     return r;
 }
 
@@ -1179,7 +1179,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_FOR_T(t)
     {
         const uint32_t st = s0 + (uint32_t)t * kSubBits;
-        const Seg r = decode_count(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, st + kCkptStep, cp, (uint32_t)T, (uint32_t)t,
+        const Seg r = decode_count(sm, st, s0 + (uint32_t)(t + 1) * kSubBits, st, cp, (uint32_t)T, (uint32_t)t,
                                    false, 0, 0);
         sm.start[t] = st;
         sm.end[t] = r.end;
@@ -1220,7 +1220,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
                     r.end = ns; r.out = 0; r.flag = F_NONE; r.ntok = 0;
                     for (int j = 0; j < kCkpt; j++) cp[(uint32_t)j * (uint32_t)T + (uint32_t)t] = kNoCkpt;  // no path left to reuse
                 }
-                else r = decode_count(sm, ns, lim, s0 + (uint32_t)t * kSubBits + kCkptStep, cp, (uint32_t)T, (uint32_t)t, true,
+                else r = decode_count(sm, ns, lim, s0 + (uint32_t)t * kSubBits, cp, (uint32_t)T, (uint32_t)t, true,
                                       sm.end[t], sm.flag[t]);
                 sm.start[t] = ns;
                 sm.end[t] = r.end;
