@@ -86,3 +86,39 @@ def test_fuzz_bit_flips(seed):
             assert st == 0 and got.size == ref.size and np.array_equal(got, ref), (seed, k)
             agree_ok += 1
     assert agree_err + agree_ok == 40 and agree_err > 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_bit_flips_in_block_headers(seed):
+    """Flips aimed at the dynamic block header every chunk starts with (HLIT/HDIST/HCLEN, the
+    code-length code, the run-length coded lengths): over-subscribed or incomplete codes, repeats
+    with no previous length, repeats past the end, a missing end-of-block code.  zlib's verdict
+    (inflate_table / 'invalid bit length repeat' / 'missing end-of-block') is the reference's."""
+    rng = np.random.default_rng(900 + seed)
+    fq = corpus.fastq(3000, fixed=int(rng.choice([50, 150])), seed=seed)
+    gz = corpus.gz_member(fq, int(rng.choice([1, 6, 9])), strategy=zlib.Z_DEFAULT_STRATEGY if seed < 3 else zlib.Z_RLE)
+    ox = O.OracleIndex.build(gz, 300)
+    ins = ox.inputs()
+    agree_err = agree_ok = 0
+    for _ in range(80):
+        k = int(rng.integers(0, ox.count - 1))
+        bad = gz.copy()
+        # a chunk starts at a block boundary, so its first ~90 bytes are a block header
+        span = min(90, ins[k + 1] - ins[k] - 2)
+        if span < 8:
+            continue
+        for _ in range(int(rng.integers(1, 3))):
+            pos = int(ins[k] + rng.integers(0, span))
+            bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        try:
+            ref = O.extract(bad, ox, k)
+        except RuntimeError:
+            ref = None
+        st, got, _, _, _ = _emu_chunk(bad, ox, k, T=int(rng.choice([32, 64, 128])))
+        if ref is None:
+            assert st == -3, (seed, k, "zlib reports a data error, the kernel logic does not")
+            agree_err += 1
+        else:
+            assert st == 0 and got.size == ref.size and np.array_equal(got, ref), (seed, k)
+            agree_ok += 1
+    assert agree_err > 10

@@ -404,6 +404,47 @@ def test_bit_flips_agree_with_zlib(device):
     assert n_err > 0 and n_err + n_ok == 30
 
 
+def test_bit_flips_in_block_headers_agree_with_zlib(device):
+    """Flips aimed at the dynamic block header every chunk starts with (code-length code, run-length
+    coded lengths): the kernel decodes those speculatively in parallel, zlib serially; the verdicts
+    (bytes, or DATA_ERROR for an over-subscribed / incomplete code, a bad repeat, a missing
+    end-of-block) must agree."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(11)
+    fq = corpus.fastq(3000, fixed=150, seed=5)
+    gz = corpus.gz_member(fq, 6)
+    ox = O.OracleIndex.build(gz, 300)
+    ix = pp.Core.BuildDeflateIndex(gz, 300)
+    outs, ins = ox.outputs(), ox.inputs()
+    n_err = n_ok = 0
+    for _ in range(60):
+        k = int(rng.integers(0, ox.count - 1))
+        span = min(90, ins[k + 1] - ins[k] - 2)
+        if span < 8:
+            continue
+        bad = gz.copy()
+        for _ in range(int(rng.integers(1, 3))):
+            bad[int(ins[k] + rng.integers(0, span))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        try:
+            ref = O.extract(bad, ox, k)
+        except RuntimeError:
+            ref = None
+        buf = np.zeros(outs[k + 1] - outs[k], np.uint8)
+        try:
+            n = pp.Core.ExtractDeflateIndex(bad[ins[k] - 1: ins[k + 1]], ix, k, buf, device)
+            got = buf[:n]
+        except pp.ZException as e:
+            assert e.Code == -3
+            got = None
+        if ref is None:
+            assert got is None, f"chunk {k}: zlib reports a data error, the GPU path does not"
+            n_err += 1
+        else:
+            assert got is not None and got.size == ref.size and np.array_equal(got, ref), f"chunk {k}"
+            n_ok += 1
+    assert n_err > 10
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_parse_fuzz(device, seed):
     """Random line structures (empty lines, NULs, CRs, missing final newline, arbitrary prepend split)
