@@ -145,6 +145,21 @@ def test_parse_large_random_lines(device):
         _parse_both(pp, device, data[:cut], data[cut:])
 
 
+def test_parse_short_records_many_newlines_per_tile(device):
+    """Records of ~10 bytes: a 64 KB tile then holds >20 000 newlines, far beyond the 2048 positions the
+    parse kernel keeps in shared memory per emission round (the multi-round path)."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(9)
+    body = bytearray()
+    for i in range(40000):
+        L = int(rng.integers(1, 4))
+        body += b"@%d\n" % (i % 10) + bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8)) + b"\n+\n" + b"?" * L + b"\n"
+    data = bytes(body)
+    for cut in (0, 7, 65536, 70001):
+        n = _parse_both(pp, device, data[:cut], data[cut:])
+        assert n == 40000
+
+
 def test_strict_drops_h1_duplicate(device):
     """Extension: PP_JOB_STRICT removes the duplicate record quirk H1 creates."""
     import parallelparsing_b200 as pp
