@@ -201,6 +201,13 @@ int pp_job_device_ptrs(const pp_job *job, const uint8_t **slots, const uint64_t 
  * structure-of-arrays line starts.  Only the 256 counters cross PCIe.  Needs pp_job_download first.
  */
 int pp_job_base_histogram(pp_job *job, uint64_t counts[256]);
+/*
+ * On-device consumer for the reference benchmark's pattern search (Benchmark/Naive.cs:167-180:
+ * `if (record.Sequence.Contains(pattern)) count++`, ordinal comparison): the number of records
+ * whose SEQUENCE line contains `pattern` (any length; an empty pattern matches every record, as
+ * string.Contains("") does).  Only the pattern and one counter cross PCIe.  Needs pp_job_download first.
+ */
+int pp_job_count_pattern(pp_job *job, const uint8_t *pattern, int32_t pattern_len, uint64_t *count);
 void pp_job_free(pp_job *job);
 
 /* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */

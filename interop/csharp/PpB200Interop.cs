@@ -51,6 +51,7 @@ internal static class LibPpB200
     [DllImport(L)] public static unsafe extern int pp_job_fetch_bytes(IntPtr job, byte* dst, long cap);
     [DllImport(L)] public static extern int pp_job_device_ptrs(IntPtr job, out IntPtr slots, out IntPtr chunkDataOff, out IntPtr l0, out IntPtr l1, out IntPtr l2, out IntPtr l3);
     [DllImport(L)] public static unsafe extern int pp_job_base_histogram(IntPtr job, ulong* counts256);
+    [DllImport(L)] public static unsafe extern int pp_job_count_pattern(IntPtr job, byte* pattern, int patternLen, out ulong count);
     [DllImport(L)] public static extern void pp_job_free(IntPtr job);
     [DllImport(L)] public static unsafe extern int pp_decompress_all(IntPtr ctx, IntPtr index, byte* gz, nuint gzLen, int firstChunk, int nChunks, uint flags, out IntPtr job);
 }

@@ -287,6 +287,14 @@ class Job:
         check(lib().pp_job_base_histogram(self.h, _ptr(out)), "pp_job_base_histogram")
         return out
 
+    def count_pattern(self, pattern: bytes) -> int:
+        """On-device consumer: records whose Sequence contains `pattern` (Benchmark/Naive.cs:167-180)."""
+        pat = np.frombuffer(bytes(pattern), np.uint8)
+        out = np.zeros(1, np.uint64)
+        check(lib().pp_job_count_pattern(self.h, _ptr(pat) if pat.size else None, int(pat.size), _ptr(out)),
+              "pp_job_count_pattern")
+        return int(out[0])
+
     def chunk_bytes(self, k):
         c = self.chunk(k)
         out = np.zeros(max(c.inflated, 1), np.uint8)

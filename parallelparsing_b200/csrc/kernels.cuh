@@ -62,6 +62,9 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
                          cudaStream_t st);
 cudaError_t launch_base_histogram(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
                                   int64_t line_stride, unsigned long long *counts, int sm_count, cudaStream_t st);
+cudaError_t launch_pattern_count(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
+                                 int64_t line_stride, const uint8_t *pattern, int plen, unsigned long long *count,
+                                 int sm_count, cudaStream_t st);
 cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
                                const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st);
 cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,

@@ -642,6 +642,58 @@ __global__ void __launch_bounds__(256) pp_base_histogram_kernel(const uint8_t *_
         if (s_hist[i]) atomicAdd(&counts[i], (unsigned long long)s_hist[i]);
 }
 
+// ---- on-device consumer: records whose sequence line contains a pattern -----------------------
+// One warp per record (grid-stride over chunks): lane i tests the start positions a+i, a+i+32, ...
+// of the sequence line against the pattern (held in shared memory up to 256 bytes).  Replaces the host loop of
+// Benchmark/Naive.cs:167-180 (`record.Sequence.Contains(pattern)`, ordinal).
+constexpr int kMaxPattern = 256;
+__global__ void __launch_bounds__(256) pp_pattern_count_kernel(const uint8_t *__restrict__ slots,
+                                                               const ParseDesc *__restrict__ pdesc, int n,
+                                                               const uint32_t *__restrict__ lines, int64_t stride,
+                                                               const uint8_t *__restrict__ pattern, int plen,
+                                                               unsigned long long *__restrict__ count)
+{
+    __shared__ uint8_t s_pat[kMaxPattern];
+    const bool in_smem = plen <= kMaxPattern;  // longer patterns are compared straight from global memory
+    if (in_smem)
+        for (int i = (int)threadIdx.x; i < plen; i += (int)blockDim.x) s_pat[i] = pattern[i];
+    __syncthreads();
+    const uint8_t *pat = in_smem ? s_pat : pattern;
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5), nwarps = (int)(blockDim.x >> 5);
+    unsigned long long hits = 0;
+    for (int k = (int)blockIdx.x; k < n; k += (int)gridDim.x) {
+        const ParseDesc d = pdesc[k];
+        const uint8_t *data = slots + d.data_off;
+        const uint32_t *l1 = lines + stride + d.rec_base, *l2 = lines + 2 * stride + d.rec_base;
+        for (uint32_t r = (uint32_t)warp; r < d.rec_count; r += (uint32_t)nwarps) {
+            const uint32_t a = l1[r], b = l2[r] - 1u;  // sequence = [l1, l2 - 1): without its '\n'
+            bool found = false;
+            if (b - a >= (uint32_t)plen) {
+                const uint32_t last = b - (uint32_t)plen;  // last start position
+                for (uint32_t s = a + (uint32_t)lane; s <= last && !found; s += 32u) {
+                    int j = 0;
+                    while (j < plen && data[s + (uint32_t)j] == pat[j]) j++;
+                    found = j == plen;
+                }
+            }
+            if (__any_sync(0xffffffffu, found) && lane == 0) hits++;
+        }
+    }
+    if (lane == 0 && hits) atomicAdd(count, hits);
+}
+
+cudaError_t launch_pattern_count(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
+                                 int64_t line_stride, const uint8_t *pattern, int plen, unsigned long long *count,
+                                 int sm_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess || n <= 0) return e;
+    if (plen < 1) return cudaErrorInvalidValue;
+    const int grid = n < sm_count * 8 ? n : sm_count * 8;
+    pp_pattern_count_kernel<<<grid, 256, 0, st>>>(slots, pdesc, n, lines, line_stride, pattern, plen, count);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_base_histogram(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
                                   int64_t line_stride, unsigned long long *counts, int sm_count, cudaStream_t st)
 {

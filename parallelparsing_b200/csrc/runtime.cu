@@ -661,6 +661,27 @@ int pp_job_base_histogram(pp_job *j, uint64_t counts[256])
     return PP_OK;
 }
 
+int pp_job_count_pattern(pp_job *j, const uint8_t *pattern, int32_t pattern_len, uint64_t *count)
+{
+    if (!j || !j->ctx || !count || !j->have_results || pattern_len < 0 || (pattern_len && !pattern))
+        return PP_E_ARG;
+    if (pattern_len == 0) {  // string.Contains("") is true for every record
+        *count = (uint64_t)j->h_totals->total_records;
+        return PP_OK;
+    }
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    DevBuf d;
+    CK(d.alloc((size_t)pattern_len + sizeof(unsigned long long)));
+    uint8_t *d_pat = d.as<uint8_t>() + sizeof(unsigned long long);
+    CK(cudaMemcpyAsync(d_pat, pattern, (size_t)pattern_len, cudaMemcpyHostToDevice, j->ctx->stream));
+    CK(launch_pattern_count(j->d_slots, j->d_pdesc, j->n, j->d_lines, j->rec_cap, d_pat, pattern_len,
+                            d.as<unsigned long long>(), j->ctx->sm_count, j->ctx->stream));
+    CK(cudaMemcpyAsync(count, d.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, j->ctx->stream));
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
 int pp_job_device_ptrs(const pp_job *j, const uint8_t **slots, const uint64_t **chunk_data_off, const uint32_t **l0,
                        const uint32_t **l1, const uint32_t **l2, const uint32_t **l3)
 {

@@ -344,6 +344,27 @@ def test_on_device_base_histogram(device):
     job.free()
 
 
+def test_on_device_pattern_count(device):
+    """On-device consumer for the reference benchmark's pattern search (Benchmark/Naive.cs:167-180):
+    records whose Sequence contains the pattern, counted on the GPU, equal Python's `in` over the
+    generator's sequences — for short, long, absent, full-line and empty patterns."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(20000)  # native U[128,512) lengths
+    gz = corpus.gz_member(fq, 6)
+    ix = pp.Core.BuildDeflateIndex(gz, 3000)
+    job = pp.Job(device, ix, gz.size, strict=True)
+    info = job.run(gz)
+    assert info.status == 0 and info.total_records == 20000
+    seqs = fq.split(b"\n")[1::4]
+    pats = [b"GTTATACACTGC", b"ACGT", b"A", b"GATTACA", seqs[17][:40], seqs[123][-25:], seqs[5], seqs[9] + b"A",
+            b"N", b"", b"ACGTACGTACGTACGTACGTACGTACGT"]
+    for pat in pats:
+        want = sum(1 for q in seqs if pat in q)
+        assert job.count_pattern(pat) == want, pat
+    assert job.count_pattern(b"ACGT") > 0 and job.count_pattern(seqs[5]) >= 1
+    job.free()
+
+
 def test_empty_chunk_range_and_threaded_callers(device):
     """A rank that gets no chunks (more GPUs than chunks) and callers on thread-pool threads
     (BatchedFASTQ.cs:62 spawns tasks; README.md:50 asks for thread safety)."""
