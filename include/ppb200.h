@@ -90,6 +90,13 @@ int pp_index_add(pp_index *ix, int32_t bits, int64_t input, int64_t output, cons
 /* IndexIO.Serialize / Deserialize — Common/IndexIO.cs:7-27 / :29-53 (same bytes on disk) */
 int pp_index_serialize(const pp_index *ix, const char *path);
 int pp_index_deserialize(const char *path, pp_index **out);
+/*
+ * Extension: IndexIO file version 1.  The leading int32 of the file — reserved, written as 0 and
+ * ignored on read by the reference (Common/IndexIO.cs:12,34) — is 1 and every 32 KB window is stored
+ * zlib-compressed (`winLen` = compressed length).  pp_index_deserialize reads both versions; files
+ * the reference itself must read have to stay version 0 (pp_index_serialize).
+ */
+int pp_index_serialize_v1(const pp_index *ix, const char *path);
 /* Index.Count, Index.ChunkMaxBytes, Index[i] — Common/Index.cs:9,20,21 */
 int32_t pp_index_count(const pp_index *ix);
 int32_t pp_index_chunk_max_bytes(const pp_index *ix);

@@ -22,6 +22,7 @@ internal static class LibPpB200
     [DllImport(L)] public static unsafe extern int pp_index_add_point(IntPtr index, int bits, long input, long output, uint left, byte* window, byte* offset, int offsetLen);
     [DllImport(L, CharSet = CharSet.Ansi)] public static extern int pp_index_serialize(IntPtr index, string path);
     [DllImport(L, CharSet = CharSet.Ansi)] public static extern int pp_index_deserialize(string path, out IntPtr index);
+    [DllImport(L, CharSet = CharSet.Ansi)] public static extern int pp_index_serialize_v1(IntPtr index, string path);   // extension: file version 1, compressed windows
     [DllImport(L)] public static extern int pp_index_count(IntPtr index);
     [DllImport(L)] public static extern int pp_index_chunk_max_bytes(IntPtr index);
     [DllImport(L)] public static extern int pp_index_point(IntPtr index, int i, out pp_point p);

@@ -56,6 +56,7 @@ SYMBOLS = [
     ("pp_index_add_point", C.c_int, [_p, _i32, _i64, _i64, _u32, _p, _p, _i32]),
     ("pp_index_add", C.c_int, [_p, _i32, _i64, _i64, _p, _p, _i32]),
     ("pp_index_serialize", C.c_int, [_p, C.c_char_p]),
+    ("pp_index_serialize_v1", C.c_int, [_p, C.c_char_p]),
     ("pp_index_deserialize", C.c_int, [C.c_char_p, _PP]),
     ("pp_index_count", _i32, [_p]),
     ("pp_index_chunk_max_bytes", _i32, [_p]),

@@ -128,8 +128,11 @@ class IndexIO:
     """Common/IndexIO.cs:7-53 — same bytes on disk."""
 
     @staticmethod
-    def Serialize(index: Index, path: str):
-        check(lib().pp_index_serialize(index.h, str(path).encode()), "IndexIO.Serialize")
+    def Serialize(index: Index, path: str, compact: bool = False):
+        """compact=True writes file version 1 (extension: zlib-compressed windows; this library's
+        Deserialize reads both versions, the reference only version 0)."""
+        f = lib().pp_index_serialize_v1 if compact else lib().pp_index_serialize
+        check(f(index.h, str(path).encode()), "IndexIO.Serialize")
 
     @staticmethod
     def Deserialize(path: str) -> Index:

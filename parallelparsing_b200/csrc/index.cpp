@@ -279,7 +279,13 @@ int pp_index_create_file(const char *gz_path, uint32_t chunksize, uint32_t flags
 // IndexIO.Serialize — Common/IndexIO.cs:7-27.  Layout (little endian, the code
 // not the stale comment at :5-6): int32 0 | int32 ChunkMaxBytes | int32 Count |
 // Count x { int64 Output | int64 Input | int32 Bits | int32 winLen | win | int32 offLen | off }.
-int pp_index_serialize(const pp_index *ix, const char *path)
+//
+// version 1 (extension, pp_index_serialize_v1): the leading int32 — reserved, written as 0 and
+// ignored on read by the reference (IndexIO.cs:12,34) — is 1, and every window is stored
+// zlib-compressed: `winLen` is the compressed length, the bytes inflate to exactly 32768.  The
+// windows are the bulk of an index (32 KB per point; 27.6 % of the .gz size at chunk 1000), and
+// they are FASTQ text.  Files the reference must read stay version 0.
+static int serialize_index(const pp_index *ix, const char *path, int version)
 {
     if (!ix || !path) return PP_E_ARG;
     FILE *f = fopen(path, "wb");
@@ -287,15 +293,29 @@ int pp_index_serialize(const pp_index *ix, const char *path)
     bool ok = true;
     auto put32 = [&](int32_t v) { ok = ok && fwrite(&v, 4, 1, f) == 1; };
     auto put64 = [&](int64_t v) { ok = ok && fwrite(&v, 8, 1, f) == 1; };
-    put32(0);
+    std::vector<uint8_t> packed;
+    try {
+        if (version == 1) packed.resize(compressBound(PP_WINSIZE));
+    } catch (...) {
+        fclose(f);
+        return PP_MEM_ERROR;
+    }
+    put32(version);
     put32(ix->chunk_max_bytes);
     put32(ix->count());
     for (int32_t i = 0; i < ix->count() && ok; i++) {
         put64(ix->output[(size_t)i]);
         put64(ix->input[(size_t)i]);
         put32(ix->bits[(size_t)i]);
-        put32(PP_WINSIZE);
-        ok = ok && fwrite(ix->window(i), 1, PP_WINSIZE, f) == PP_WINSIZE;
+        if (version == 1) {
+            uLongf n = (uLongf)packed.size();
+            ok = ok && compress2(packed.data(), &n, ix->window(i), PP_WINSIZE, 6) == Z_OK;
+            put32((int32_t)n);
+            ok = ok && fwrite(packed.data(), 1, (size_t)n, f) == (size_t)n;
+        } else {
+            put32(PP_WINSIZE);
+            ok = ok && fwrite(ix->window(i), 1, PP_WINSIZE, f) == PP_WINSIZE;
+        }
         const int32_t ol = ix->off_len[(size_t)i];
         put32(ol);
         if (ol) ok = ok && fwrite(ix->offset(i), 1, (size_t)ol, f) == (size_t)ol;
@@ -303,6 +323,8 @@ int pp_index_serialize(const pp_index *ix, const char *path)
     ok = (fclose(f) == 0) && ok;
     return ok ? PP_OK : PP_E_IO;
 }
+int pp_index_serialize(const pp_index *ix, const char *path) { return serialize_index(ix, path, 0); }
+int pp_index_serialize_v1(const pp_index *ix, const char *path) { return serialize_index(ix, path, 1); }
 
 // IndexIO.Deserialize — Common/IndexIO.cs:29-53.  As in the reference the stored
 // ChunkMaxBytes is read and discarded (:35,52): the new Index(points) has 0.
@@ -318,13 +340,29 @@ int pp_index_deserialize(const char *path, pp_index **out)
     int32_t hdr[3];
     if (fread(hdr, 4, 3, f) != 3 || hdr[2] < 0) rc = PP_E_FORMAT;
     try {
-        std::vector<uint8_t> win(PP_WINSIZE), off;
+        const bool v1 = rc == PP_OK && hdr[0] == 1;  // any other value: version 0, as the reference reads it
+        std::vector<uint8_t> win(PP_WINSIZE), off, packed(v1 ? compressBound(PP_WINSIZE) : 0);
         for (int32_t i = 0; rc == PP_OK && i < hdr[2]; i++) {
             int64_t output, input;
             int32_t bits, winlen, ol;
             if (fread(&output, 8, 1, f) != 1 || fread(&input, 8, 1, f) != 1 || fread(&bits, 4, 1, f) != 1 ||
-                fread(&winlen, 4, 1, f) != 1 || winlen != PP_WINSIZE ||
-                fread(win.data(), 1, PP_WINSIZE, f) != PP_WINSIZE || fread(&ol, 4, 1, f) != 1 || ol < 0) {
+                fread(&winlen, 4, 1, f) != 1) {
+                rc = PP_E_FORMAT;
+                break;
+            }
+            if (v1) {
+                uLongf n = PP_WINSIZE;
+                if (winlen <= 0 || (size_t)winlen > packed.size() ||
+                    fread(packed.data(), 1, (size_t)winlen, f) != (size_t)winlen ||
+                    uncompress(win.data(), &n, packed.data(), (uLong)winlen) != Z_OK || n != PP_WINSIZE) {
+                    rc = PP_E_FORMAT;
+                    break;
+                }
+            } else if (winlen != PP_WINSIZE || fread(win.data(), 1, PP_WINSIZE, f) != PP_WINSIZE) {
+                rc = PP_E_FORMAT;
+                break;
+            }
+            if (fread(&ol, 4, 1, f) != 1 || ol < 0) {
                 rc = PP_E_FORMAT;
                 break;
             }

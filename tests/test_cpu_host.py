@@ -90,6 +90,35 @@ def test_index_io_golden_bytes(tmp_path):
     _assert_same_index(pp.IndexIO.Deserialize(out), O.OracleIndex.deserialize(out))
 
 
+def test_index_io_version1_compact_windows(tmp_path):
+    """Extension: IndexIO file version 1 (leading reserved int32 = 1, windows zlib-compressed).  Same
+    points back, a much smaller file, version 0 files unchanged, damaged files rejected."""
+    import parallelparsing_b200 as pp
+    gz = corpus.gz_member(corpus.fastq(8000, fixed=150), 6)
+    ix = pp.Core.BuildDeflateIndex(gz, 500)
+    v0, v1 = str(tmp_path / "v0.gzi"), str(tmp_path / "v1.gzi")
+    pp.IndexIO.Serialize(ix, v0)
+    pp.IndexIO.Serialize(ix, v1, compact=True)
+    b0, b1 = open(v0, "rb").read(), open(v1, "rb").read()
+    assert b0[:4] == b"\0\0\0\0" and b1[:4] == b"\1\0\0\0" and b0[4:12] == b1[4:12]
+    assert len(b1) * 2 < len(b0)
+    a, b = pp.IndexIO.Deserialize(v0), pp.IndexIO.Deserialize(v1)
+    assert a.Count == b.Count == ix.Count
+    for i in range(ix.Count):
+        p, q, r = ix[i], a[i], b[i]
+        assert (p.Output, p.Input, p.Bits) == (q.Output, q.Input, q.Bits) == (r.Output, r.Input, r.Bits)
+        assert np.array_equal(p.Window, q.Window) and np.array_equal(p.Window, r.Window)
+        assert np.array_equal(p.offset, q.offset) and np.array_equal(p.offset, r.offset)
+    _assert_same_index(a, O.OracleIndex.deserialize(v0))  # the oracle (version 0 only) still reads what we wrote
+    # truncated / corrupted version-1 files are format errors, not crashes
+    for bad in (b1[: len(b1) // 2], b1[:40] + bytes([b1[40] ^ 0xff]) + b1[41:]):
+        pth = str(tmp_path / "bad.gzi")
+        open(pth, "wb").write(bad)
+        with pytest.raises(pp.ZException) as e:
+            pp.IndexIO.Deserialize(pth)
+        assert e.value.Code == -105
+
+
 def test_index_errors():
     import parallelparsing_b200 as pp
     gz = corpus.gz_member(corpus.fastq(12, fixed=20000), 6)
