@@ -381,13 +381,40 @@ class PairedFASTQ:
     requiring both files to cut their chunks at the same records (checkpoints sit on deflate block
     boundaries, which differ between the files).  Quirk H1 (a duplicate record when a checkpoint
     falls on a record boundary) would shift the ordinals of one file only, so both jobs run with
-    PP_JOB_STRICT.  Iteration yields (FastqRecord, FastqRecord) pairs."""
+    PP_JOB_STRICT.  Iteration yields (FastqRecord, FastqRecord) pairs.
 
-    def __init__(self, index1, gzip1, index2, gzip2, device=None):
-        self._a = BatchedFASTQ(index1, gzip1, device=device, strict=True)
-        self._b = BatchedFASTQ(index2, gzip2, device=device, strict=True)
+    The two jobs run CONCURRENTLY: R2 gets its own context (stream) on the same GPU and its own host
+    thread, so its CTAs fill the SMs the last, thin wave of R1's chunks leaves idle (DESIGN.md §4.1,
+    wave quantisation) and the other way round."""
+
+    def __init__(self, index1, gzip1, index2, gzip2, device=None, concurrent=True):
+        dev = device or Device.default()
+        self._dev2 = Device(dev.ordinal) if concurrent else None
+        self._a = BatchedFASTQ(index1, gzip1, device=dev, strict=True)
+        self._b = BatchedFASTQ(index2, gzip2, device=self._dev2 or dev, strict=True)
+
+    def _run_both(self):
+        if self._dev2 is None or (self._a._job is not None and self._b._job is not None):
+            self._a._run()
+            self._b._run()
+            return
+        import threading
+        err = []
+
+        def work(x):
+            try:
+                x._run()
+            except BaseException as e:  # re-raised on the caller's thread
+                err.append(e)
+        th = threading.Thread(target=work, args=(self._b,))
+        th.start()
+        work(self._a)
+        th.join()
+        if err:
+            raise err[0]
 
     def Count(self):
+        self._run_both()
         n1, n2 = self._a.Count(), self._b.Count()
         if n1 != n2:
             raise ValueError(f"R1 holds {n1} records, R2 holds {n2}: not a paired-end pair of files")
@@ -400,3 +427,6 @@ class PairedFASTQ:
     def Dispose(self):
         self._a.Dispose()
         self._b.Dispose()
+        if self._dev2 is not None:
+            self._dev2.close()
+            self._dev2 = None
