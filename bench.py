@@ -408,7 +408,10 @@ def main():
                          "peak": peak, "unit": "GB/s", "frac": b_parse / t_parse / 1e9 / peak,
                          "traffic": traffic.get("pp_parse_kernel"),
                          "algorithmic_bytes": b_parse, "ms": t_parse * 1e3, "peak_source": peak_src,
-                         "timing": "CUDA events on the library stream around the kernel, last timed step"},
+                         "timing": "CUDA events on the library stream around the kernel, last timed step",
+                         "peak_kind": "device COPY bandwidth (read + write); this kernel reads ~25x more than it "
+                                      "writes, and a read-only stream can run above that figure (long reads: "
+                                      "frac > 1)"},
             "inflate": {"kernel": "pp_inflate_kernel",
                         "bound": "instruction issue / shared-memory latency (Huffman decode + LZ77 resolve), not HBM",
                         "decompressed_gbs": U / t_inflate / 1e9, "ms": t_inflate * 1e3,
