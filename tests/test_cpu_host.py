@@ -227,3 +227,33 @@ def test_two_rank_partition_over_gloo():
     assert c0 == c1 and sum(c0) == G["total_records"] and tb0 == G["index"]["end_output"]
     assert b0 == 0 and b1 == c0[0]
     assert c0[0] == sum(c["records"] for c in G["chunks"][:n0])
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary as a P/Invoke binding sees it: tests/c_abi/harness.c (C99, include/ppb200.h only)
+    builds an index from a .gz file, writes and reads both index file versions, walks the points, and
+    gets a loud PP_E_NO_DEVICE from pp_open on a machine without a GPU.  Its numbers must equal the
+    Python mirror's."""
+    import subprocess
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "harness")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_abi", "harness.c"), "-o", exe,
+                           "-L", libdir, "-lppb200", f"-Wl,-rpath,{libdir}"])
+    gz = corpus.gz_member(corpus.fastq(6000, fixed=150), 6)
+    gz_path = str(tmp_path / "r.fastq.gz")
+    gz.tofile(gz_path)
+    out = subprocess.run([exe, gz_path, "700", str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    kv = dict(line.split(" ", 1) for line in out.stdout.strip().splitlines())
+    ix = pp.Core.BuildDeflateIndex(gz, 700)
+    assert int(kv["points"]) == ix.Count == int(kv["rebuilt_points"])
+    assert int(kv["chunk_max_bytes"]) == ix.ChunkMaxBytes
+    want = sum(ix[i].Output * 31 + ix[i].Input * 7 + ix[i].Bits for i in range(ix.Count)) & 0xFFFFFFFFFFFFFFFF
+    assert int(kv["point_sum"]) == want
+    import torch
+    code = int(kv["open"].split()[0])
+    assert code == (0 if torch.cuda.is_available() else -101), kv["open"]
