@@ -45,7 +45,7 @@ def test_fuzz_random_streams(seed):
     ref_all = np.frombuffer(data, np.uint8)
     outs = ox.outputs()
     for k in range(ox.count - 1):
-        st, got, nl, mb, _ = _emu_chunk(gz, ox, k, T=int(rng.choice([32, 64, 128])))
+        st, got, nl, mb, _ = _emu_chunk(gz, ox, k, T=int(rng.choice([32, 64, 128, 512])))
         ref = ref_all[outs[k]: outs[k + 1]]
         assert st == 0 and np.array_equal(got, ref), (seed, k)
         assert nl == int((ref == 10).sum())
