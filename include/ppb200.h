@@ -147,7 +147,10 @@ int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const
 
 /* flags for pp_job_create */
 #define PP_JOB_STRICT 1u      /* extension: drop the duplicate record of quirk H1 */
-#define PP_JOB_ZEROCOPY 2u    /* kernels pull compressed bytes/windows straight from pinned host memory */
+/* kernels pull compressed bytes/windows straight from pinned host memory.  `gz` handed to
+ * pp_job_upload must then be device-accessible pinned memory (pp_host_alloc, or any buffer passed
+ * through pp_host_register); exactly gz_len bytes are readable, nothing behind them is touched. */
+#define PP_JOB_ZEROCOPY 2u
 
 typedef struct pp_job_info {
     int32_t first_chunk, n_chunks;
@@ -198,7 +201,9 @@ int pp_job_fetch_line_starts(pp_job *job, uint32_t *l0, uint32_t *l1, uint32_t *
 int pp_job_fetch_chunk(pp_job *job, int32_t chunk, uint8_t *dst, int64_t cap);
 /* Inflated bytes of all chunks, concatenated (dst capacity >= total_bytes). */
 int pp_job_fetch_bytes(pp_job *job, uint8_t *dst, int64_t cap);
-/* Device pointers for on-device consumers (valid until the job is freed). */
+/* Device pointers for on-device consumers.  Take them AFTER pp_job_download: the download may
+ * re-allocate the line-start arrays when a corpus has more records than first provisioned.
+ * Valid until the next pp_job_download / pp_job_free. */
 int pp_job_device_ptrs(const pp_job *job, const uint8_t **slots, const uint64_t **chunk_data_off,
                        const uint32_t **l0, const uint32_t **l1, const uint32_t **l2, const uint32_t **l3);
 /*
@@ -215,6 +220,22 @@ int pp_job_base_histogram(pp_job *job, uint64_t counts[256]);
  * string.Contains("") does).  Only the pattern and one counter cross PCIe.  Needs pp_job_download first.
  */
 int pp_job_count_pattern(pp_job *job, const uint8_t *pattern, int32_t pattern_len, uint64_t *count);
+/*
+ * Per-chunk integrity digests computed on the GPU (n_chunks entries each; either pointer may be NULL),
+ * so that a whole DecompressAll can be checked against an independent implementation with two
+ * integers per chunk crossing PCIe instead of every byte and record.  With
+ *   mix(x) = splitmix64 finaliser: z = x + 0x9E3779B97F4A7C15; z = (z ^ z>>30) * 0xBF58476D1CE4E5B9;
+ *            z = (z ^ z>>27) * 0x94D049BB133111EB; z ^ z>>31
+ * and all arithmetic modulo 2^64:
+ *   bytes_digest[k]  = mix(n) + sum_i mix(i) * (W_i + 1) over the n bytes Core.ExtractDeflateIndex
+ *                      produced for chunk k (Core.cs:133-192), W_i = little-endian u64 of bytes
+ *                      [8i, 8i+8), zero padded;
+ *   fields_digest[k] = sum_r sum_{f<9} mix(9r + f) * (field_{r,f} + 1) over the chunk's records r and
+ *                      the nine integers Parsing.Parse computes per record (Parsing.cs:20-39: start,
+ *                      idnFrom, idnLen, seqFrom, seqLen, plsFrom, plsLen, qltFrom, qltLen).
+ * Needs pp_job_download first.
+ */
+int pp_job_digests(pp_job *job, uint64_t *bytes_digest, uint64_t *fields_digest);
 void pp_job_free(pp_job *job);
 
 /* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */

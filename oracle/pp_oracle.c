@@ -611,6 +611,140 @@ int64_t ora_naive_count(const uint8_t *gz, size_t gz_len, int64_t *bytes_out)
     return bad ? -1 : records;
 }
 
+/*
+ * SimpleDecompressor/Parsing.cs:9-49 record for record — the INDEPENDENT second restatement used to
+ * pin the hot-path parser: on well-formed input both parsers must cut the same four fields out of
+ * the same byte stream.  `data` is the whole inflated stream followed by the zero tail the last
+ * 64 KB buffer carries (SimpleDecompressor.cs:19-24).  For every record emits 8 int64 into `recs`
+ * (capacity `cap` records): idnFrom, idnLen, seqFrom, seqLen, plsFrom, plsLen, qltFrom, qltLen as
+ * offsets into the stream (the strings :26-31 build are data[from, from+len)).  '\r' or '\n' ends
+ * a line (:48) and exactly one byte is consumed after it (:44).  Returns the record count, or -1
+ * where the reference throws (:24,29: a record not starting with '@' / '+').
+ */
+int64_t ora_naive_records(const uint8_t *data, int64_t n, int64_t *recs, int64_t cap)
+{
+    int64_t pos = 0, count = 0;
+    while (pos < n) {                      /* :15 !raw.IsAtEnd */
+        if (data[pos] == 0) break;         /* :18 */
+        if (data[pos++] != '@') return -1; /* :24 */
+        int64_t f[8];
+        for (int line = 0; line < 4; line++) {
+            if (line == 2) {               /* :28-29 skip + */
+                if (pos >= n || data[pos++] != '+') return -1;
+            }
+            int64_t from = pos;
+            while (pos < n && data[pos] != '\n' && data[pos] != '\r') pos++; /* :40-43 */
+            f[2 * line] = from;
+            f[2 * line + 1] = pos - from;
+            if (pos < n) pos++;            /* :46 consume \n */
+        }
+        if (recs && count < cap) memcpy(recs + 8 * count, f, sizeof f);
+        count++;
+    }
+    return count;
+}
+
+/* ------------------------------------------------------------ digests ------- */
+
+/*
+ * Order-sensitive, parallel-friendly digests (sums mod 2^64 of position-keyed terms) that the GPU
+ * library computes per chunk (pp_job_digests, include/ppb200.h) so that parity at BASELINE sizes
+ * needs only a few integers per chunk to cross PCIe.  The oracle computes the same function over
+ * ITS OWN bytes / records; equality of digests is the comparison.
+ *   mix(x)            splitmix64 finaliser
+ *   bytes:  mix(n) + sum_i mix(i) * (W_i + 1),  W_i = little-endian u64 of bytes [8i, 8i+8), zero padded
+ *   fields: sum_r sum_{f<9} mix(9r+f) * (field_{r,f} + 1) over the nine integers of Parsing.cs:20-39
+ */
+static inline uint64_t ora_mix64(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+uint64_t ora_digest_bytes(const uint8_t *p, int64_t n)
+{
+    uint64_t d = ora_mix64((uint64_t)n);
+    int64_t nw = n / 8;
+    for (int64_t i = 0; i < nw; i++) {
+        uint64_t w;
+        memcpy(&w, p + 8 * i, 8);
+        d += ora_mix64((uint64_t)i) * (w + 1);
+    }
+    if (n & 7) {
+        uint64_t w = 0;
+        memcpy(&w, p + 8 * nw, (size_t)(n & 7));
+        d += ora_mix64((uint64_t)nw) * (w + 1);
+    }
+    return d;
+}
+uint64_t ora_digest_fields(const int64_t *recs, int64_t n)
+{
+    uint64_t d = 0;
+    for (int64_t r = 0; r < n; r++)
+        for (int f = 0; f < 9; f++) d += ora_mix64((uint64_t)(9 * r + f)) * ((uint64_t)recs[9 * r + f] + 1);
+    return d;
+}
+
+/*
+ * Every chunk of [first, first+n) through ora_chunk on `threads` workers, keeping only what a
+ * size-independent comparison needs per chunk: out4[4k..4k+3] = inflated length, record count,
+ * bytes digest, fields digest.  Test infrastructure for the BASELINE-size parity gates.
+ * Returns 0 or the first negative chunk status.
+ */
+typedef struct {
+    const uint8_t *gz; size_t gz_len; const ora_index *ix;
+    int first, last; int next; pthread_mutex_t mu; uint64_t *out4; int err;
+} dig_job;
+
+static void *dig_worker(void *arg)
+{
+    dig_job *j = (dig_job *)arg;
+    int64_t maxlen = 0, maxoff = 0;
+    for (int k = j->first; k < j->last; k++) {
+        int64_t l = j->ix->pts[k + 1]->output - j->ix->pts[k]->output;
+        if (l > maxlen) maxlen = l;
+        if (j->ix->pts[k]->offset_len > maxoff) maxoff = j->ix->pts[k]->offset_len;
+    }
+    uint8_t *buf = (uint8_t *)malloc((size_t)ora_rent_size(maxlen) + 16);
+    int64_t cap = (maxlen + maxoff) / 4 + 16;
+    int64_t *recs = (int64_t *)malloc(sizeof(int64_t) * 9 * (size_t)cap);
+    for (;;) {
+        pthread_mutex_lock(&j->mu);
+        int k = j->next < j->last ? j->next++ : -1;
+        pthread_mutex_unlock(&j->mu);
+        if (k < 0) break;
+        int64_t produced = 0;
+        int64_t n = ora_chunk(j->gz, j->gz_len, j->ix, k, buf, recs, cap, NULL, &produced, 0);
+        if (n < 0) { j->err = (int)n; break; }
+        uint64_t *o = j->out4 + 4 * (size_t)(k - j->first);
+        o[0] = (uint64_t)produced;
+        o[1] = (uint64_t)n;
+        o[2] = ora_digest_bytes(buf, produced);
+        o[3] = ora_digest_fields(recs, n);
+    }
+    free(buf);
+    free(recs);
+    return NULL;
+}
+
+int ora_chunk_digests_mt(const uint8_t *gz, size_t gz_len, const ora_index *ix, int first_chunk, int n_chunks,
+                         int threads, uint64_t *out4)
+{
+    dig_job j;
+    memset(&j, 0, sizeof j);
+    j.gz = gz; j.gz_len = gz_len; j.ix = ix; j.out4 = out4;
+    j.first = first_chunk; j.last = first_chunk + n_chunks; j.next = first_chunk;
+    pthread_mutex_init(&j.mu, NULL);
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, dig_worker, &j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    pthread_mutex_destroy(&j.mu);
+    return j.err;
+}
+
 /* Whole-stream inflate (zcat) used by tests for concat(chunks) == stream. */
 int64_t ora_zcat(const uint8_t *gz, size_t gz_len, uint8_t *out, int64_t out_cap)
 {

@@ -7,7 +7,7 @@ interface for that path (see api.py) and the in-tree build driver (build.py).
 """
 from .api import (BatchedFASTQ, Core, Device, FastqRecord, Index, IndexIO, Job, PairedFASTQ, Parsing, Point, ZException,
                   fields_from_line_starts, pinned_copy)
-from ._lib import LIB_PATH, SYMBOLS, lib
+from ._lib import LIB_PATH, SYMBOLS, check, lib
 
 __all__ = ["BatchedFASTQ", "Core", "Device", "FastqRecord", "Index", "IndexIO", "Job", "PairedFASTQ", "Parsing", "Point",
            "ZException", "fields_from_line_starts", "pinned_copy", "LIB_PATH", "SYMBOLS", "lib"]

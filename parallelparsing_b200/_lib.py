@@ -82,6 +82,7 @@ SYMBOLS = [
     ("pp_job_device_ptrs", C.c_int, [_p, _PP, _PP, _PP, _PP, _PP, _PP]),
     ("pp_job_base_histogram", C.c_int, [_p, _p]),
     ("pp_job_count_pattern", C.c_int, [_p, _p, _i32, _p]),
+    ("pp_job_digests", C.c_int, [_p, _p, _p]),
     ("pp_job_free", None, [_p]),
     ("pp_decompress_all", C.c_int, [_p, _p, _p, _sz, _i32, _i32, _u32, _PP]),
 ]

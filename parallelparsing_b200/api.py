@@ -298,6 +298,13 @@ class Job:
               "pp_job_count_pattern")
         return int(out[0])
 
+    def digests(self):
+        """Per-chunk (bytes_digest[n], fields_digest[n]) computed on the GPU (pp_job_digests)."""
+        n = self.info().n_chunks
+        b, f = np.zeros(max(n, 1), np.uint64), np.zeros(max(n, 1), np.uint64)
+        check(lib().pp_job_digests(self.h, _ptr(b), _ptr(f)), "pp_job_digests")
+        return b[:n], f[:n]
+
     def chunk_bytes(self, k):
         c = self.chunk(k)
         out = np.zeros(max(c.inflated, 1), np.uint8)

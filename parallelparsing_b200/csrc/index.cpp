@@ -205,6 +205,18 @@ int pp_index_create(const uint8_t *gz, size_t gz_len, uint32_t chunksize, uint32
                     size_t ats = 0;
                     for (size_t i = 0; i < span_len; i++) ats += (span[i] == 64);
                     size_t keep_from = 0;
+                    // :93 indexes offsetBeforePoint byte by byte: the reference throws as soon as the running
+                    // partial record needs a 32769th byte, even when an '@' follows later in the same span.
+                    // Inside a span only the stretch before its first '@' can get there (a span is <= 32768 B).
+                    if (!lift) {
+                        const uint8_t *first = ats ? (const uint8_t *)memchr(span, 64, span_len) : nullptr;
+                        const size_t head = first ? (size_t)(first - span) : span_len;
+                        if (partial.size() + head > (size_t)PP_WINSIZE) {
+                            rc = PP_E_RECORD_TOO_LONG;
+                            done = true;
+                            break;
+                        }
+                    }
                     if (ats) {
                         records += (int64_t)ats;
                         const uint8_t *last = (const uint8_t *)memrchr(span, 64, span_len);

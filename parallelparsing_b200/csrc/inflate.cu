@@ -43,12 +43,19 @@ extern "C" int pp_internal_phase_cycles(unsigned long long *out, int n)
     return ppinf::PH_COUNT;
 }
 
+// The dynamic shared memory opt-in is a property of the function in the device's context, shared by
+// every pp_ctx on that device: it is set ONCE per context, to the largest configuration, and never
+// changed per launch (two contexts launching different CTA sizes would otherwise race on it).
+cudaError_t inflate_set_max_smem(int threads)
+{
+    return cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)ppinf::sm_bytes_for(threads));
+}
+
 int inflate_max_ctas_per_sm(int threads)
 {
     int nb = 0;
     const size_t smem = ppinf::sm_bytes_for(threads);
-    if (cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pp_inflate_kernel, threads, smem) != cudaSuccess) return 0;
     return nb;
 }
@@ -65,8 +72,6 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);
-    e = cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const int grid = n < cfg.grid ? n : cfg.grid;
     pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
                                                         ppinf::scratch_words_for(cfg.threads), cfg.counter);

@@ -19,8 +19,9 @@
 //           Thread 0 is right by construction, so after k rounds threads 0..k are
 //           exact; with self-synchronisation two or three rounds settle all of them;
 //  SCAN     block-wide prefix sum of the bytes each sub-sequence produces;
-//  EMIT     every thread decodes its (now exact) sub-sequence once more and writes a
-//           SOURCE MAP: one u16 per output byte, "literal v" or "copy from d+1 back";
+//  EMIT     every thread decodes its (now exact) sub-sequence once more and writes one 32-bit
+//           TOKEN per symbol (literal byte, or match length + distance) into its row of the
+//           CTA's global scratch, plus a group index entry per 16 output bytes;
 //  RESOLVE  the CTA walks the window's output in tiles of 16 bytes per thread: sources
 //           in front of the tile are gathered from global memory (all loads in flight
 //           together), sources inside the tile are settled in shared memory by pointer
@@ -323,15 +324,20 @@ PP_DEV void tma_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsig
 PP_DEV bool stage_window(const Sm &sm, const uint8_t *comp, uint64_t comp_bytes, uint64_t byte_off, uint32_t words,
                          uint32_t &phase)
 {
-    uint64_t avail = byte_off < comp_bytes ? comp_bytes - byte_off : 0;
-    avail &= ~(uint64_t)15;
+    // comp_bytes is the TRUE readable extent of the buffer (it may be a caller's pinned host
+    // buffer with nothing behind it): whole 16-byte units go through TMA, a ragged tail of
+    // fewer than 16 bytes is fetched with byte loads, everything past the end reads as zero
+    const uint64_t avail = byte_off < comp_bytes ? comp_bytes - byte_off : 0;
     const uint32_t want = words * 4u;
-    const uint32_t nbytes = avail < want ? (uint32_t)avail : want;
+    const uint32_t have = avail < want ? (uint32_t)avail : want;   // bytes that exist
+    const uint32_t nbytes = have & ~15u;                            // bulk-copied part
+    const uint32_t tail = have - nbytes;                            // < 16
     PP_SYNC();  // every thread is done with the previous contents of cw
 #ifdef PP_HOST_EMU
-    if (nbytes) memcpy(sm.cw, comp + byte_off, nbytes);
-    memset((uint8_t *)sm.cw + nbytes, 0, want - nbytes);
+    if (have) memcpy(sm.cw, comp + byte_off, have);
+    memset((uint8_t *)sm.cw + have, 0, want - have);
     (void)phase;
+    (void)tail;
     return true;
 #else
     if (threadIdx.x == 0 && nbytes) {
@@ -341,7 +347,12 @@ PP_DEV bool stage_window(const Sm &sm, const uint8_t *comp, uint64_t comp_bytes,
             tma_load((uint8_t *)sm.cw + o, comp + byte_off + o, n, sm.bar);
         }
     }
-    for (uint32_t i = nbytes / 4u + threadIdx.x; i < words; i += blockDim.x) sm.cw[i] = 0;
+    if (nbytes < want) {
+        // the 16-byte unit holding the ragged tail (threads 0..15, one byte each), zeros behind it
+        if (threadIdx.x < 16u)
+            ((uint8_t *)sm.cw)[nbytes + threadIdx.x] = threadIdx.x < tail ? comp[byte_off + nbytes + threadIdx.x] : (uint8_t)0;
+        for (uint32_t i = nbytes / 4u + 4u + threadIdx.x; i < words; i += blockDim.x) sm.cw[i] = 0;
+    }
     bool ok = true;
     if (nbytes) {
         ok = mbar_wait(sm.bar, phase & 1u);

@@ -47,6 +47,7 @@ struct InflateLaunch {
     int *counter = nullptr;  // chunk counter the CTAs pull work from
 };
 int inflate_max_ctas_per_sm(int threads);
+cudaError_t inflate_set_max_smem(int threads);
 size_t inflate_scratch_bytes(int threads, int grid);
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                            const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st);
@@ -59,7 +60,8 @@ uint32_t parse_tile_bytes();
 cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *tile_base,
                          uint32_t total_tiles, uint32_t max_tiles, uint32_t *lines, int64_t line_stride,
                          ParseOut *pout, const ScanTotals *totals, unsigned long long *work, int sm_count,
-                         cudaStream_t st);
+                         int per_sm, cudaStream_t st);
+int parse_max_ctas_per_sm();
 cudaError_t launch_base_histogram(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
                                   int64_t line_stride, unsigned long long *counts, int sm_count, cudaStream_t st);
 cudaError_t launch_pattern_count(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *lines,
@@ -69,5 +71,8 @@ cudaError_t launch_exact_count(const uint8_t *slots, const ChunkDesc *descs, con
                                const ParseOut *pout, int n, int64_t *exact_counts, cudaStream_t st);
 cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int n, uint32_t *lines,
                               int64_t line_stride, ParseOut *pout, const ScanTotals *totals, cudaStream_t st);
+cudaError_t launch_digests(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
+                           const ParseDesc *pdesc, const ParseOut *pout, int n, const uint32_t *lines,
+                           int64_t line_stride, unsigned long long *out, cudaStream_t st);
 
 }  // namespace pp

@@ -721,14 +721,28 @@ cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, cons
 }
 uint32_t parse_tile_bytes() { return (uint32_t)kTileBytesP; }
 
+// Resident CTAs of the parse kernel per SM on the current device (also opts the kernel into its
+// dynamic shared memory size).  Called once per device context: the attribute lives in the
+// device's primary context, and the answer is kept in the pp_ctx, not in a process-wide cache.
+int parse_max_ctas_per_sm()
+{
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(pp_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSm)) != cudaSuccess)
+        return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_parse_kernel, kParseThreads, sizeof(ParseSm)) != cudaSuccess)
+        return 0;
+    return per_sm;
+}
+
 // tile_base: n+1 entries (device); max_tiles: largest tile count of one chunk;
 // work: total_tiles u64 tile states followed by the u32 ticket
 cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, const uint32_t *tile_base,
                          uint32_t total_tiles, uint32_t max_tiles, uint32_t *lines, int64_t line_stride,
                          ParseOut *pout, const ScanTotals *totals, unsigned long long *work, int sm_count,
-                         cudaStream_t st)
+                         int per_sm, cudaStream_t st)
 {
     if (n <= 0 || total_tiles == 0) return cudaSuccess;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     cudaError_t e = cudaMemsetAsync(work, 0, ((size_t)total_tiles + 1) * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     uint32_t *ticket = reinterpret_cast<uint32_t *>(work + total_tiles);
@@ -737,18 +751,6 @@ cudaError_t launch_parse(const uint8_t *slots, const ParseDesc *pdesc, int n, co
     int order = rr <= 4ull * total_tiles && rr < 0xffffffffull ? 1 : 0;
     if (const char *e = getenv("PPB200_PARSE_ORDER")) order = atoi(e) ? order : 0;  // 0 forces linear tickets
     const uint32_t n_tickets = order ? (uint32_t)rr : total_tiles;
-    static int per_sm_of[64];  // per device: the attribute lives in the device's context
-    int dev = 0;
-    e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    int &per_sm = per_sm_of[dev & 63];
-    if (!per_sm) {
-        e = cudaFuncSetAttribute(pp_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSm));
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_parse_kernel, kParseThreads, sizeof(ParseSm));
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    }
     // the look-back needs every CTA of the grid resident
     const uint32_t resident = (uint32_t)sm_count * (uint32_t)per_sm;
     const uint32_t grid = n_tickets < resident ? n_tickets : resident;

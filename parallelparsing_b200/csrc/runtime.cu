@@ -53,6 +53,7 @@ struct pp_ctx {
     InflateLaunch wide, dense;
     uint32_t *d_map = nullptr;
     int *d_counter = nullptr;
+    int parse_per_sm = 0;  // resident CTAs of the parse kernel per SM (its look-back needs a resident grid)
     const InflateLaunch &inflate_cfg(int n_chunks) const { return n_chunks <= wide.grid ? wide : dense; }
 };
 
@@ -63,6 +64,8 @@ static int ctx_setup_inflate(pp_ctx *c)
         const int v = atoi(e);
         if (v >= 32 && v <= 1024 && v % 32 == 0) t_wide = t_dense = v;
     }
+    // dynamic shared memory opt-in: once per context, for the largest CTA size (never per launch)
+    CK(inflate_set_max_smem(std::max(t_wide, t_dense)));
     const int occ_w = inflate_max_ctas_per_sm(t_wide), occ_d = inflate_max_ctas_per_sm(t_dense);
     if (occ_w <= 0 || occ_d <= 0) {
         fprintf(stderr, "ppb200: inflate kernel does not fit an SM (threads %d/%d)\n", t_wide, t_dense);
@@ -77,6 +80,11 @@ static int ctx_setup_inflate(pp_ctx *c)
     CK(cudaMalloc(&c->d_counter, sizeof(int)));
     c->wide.map = c->dense.map = c->d_map;
     c->wide.counter = c->dense.counter = c->d_counter;
+    c->parse_per_sm = parse_max_ctas_per_sm();
+    if (c->parse_per_sm < 1) {
+        fprintf(stderr, "ppb200: parse kernel does not fit an SM\n");
+        return PP_E_CUDA;
+    }
     return PP_OK;
 }
 
@@ -488,7 +496,7 @@ static int job_parse_stage(pp_job *j, cudaStream_t st, bool with_pout_flags, int
                    j->d_pout, j->d_totals, st));
     CK(cudaEventRecord(j->ev[4], st));
     CK(launch_parse(j->d_slots, j->d_pdesc, n, j->d_tile_base, j->total_tiles, j->max_tiles, j->d_lines, j->rec_cap,
-                    j->d_pout, j->d_totals, j->d_parse_work, j->ctx->sm_count, st));
+                    j->d_pout, j->d_totals, j->d_parse_work, j->ctx->sm_count, j->ctx->parse_per_sm, st));
     CK(cudaEventRecord(j->ev[5], st));
     CK(launch_exact_emit(j->d_slots, j->d_pdesc, n, j->d_lines, j->rec_cap, j->d_pout, j->d_totals, st));
     *launches += n > 0 ? 4 : 1;
@@ -512,7 +520,9 @@ int pp_job_execute(pp_job *j)
         const uint8_t *hl = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
         CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(hl), 0));
         lead = (const uint8_t *)dp;
-        comp_bytes = align_up(j->comp_copy, kTile) + kTile;  // pp_host_alloc keeps spare tiles behind the data
+        // the TRUE extent of what the job may read: nothing behind the caller's buffer is touched, so
+        // any pinned buffer works (pp_host_alloc or pp_host_register); the kernel zero-fills past it
+        comp_bytes = j->comp_copy;
     }
     CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
                       st));
@@ -532,7 +542,11 @@ int pp_job_download(pp_job *j)
     CK(cudaSetDevice(j->ctx->device));
     cudaStream_t st = j->ctx->stream;
     const size_t n = (size_t)std::max(j->n, 1);
-    for (int attempt = 0; attempt < 4; attempt++) {
+    // download, and when the results ask for another parse pass (record arrays too small, or a chunk
+    // the fast parser flagged for the exact parser) run it and download AGAIN: the last action is
+    // always a download, and a job that does not settle is an error, never stale results
+    bool settled = false;
+    for (int attempt = 0; attempt < 5 && !settled; attempt++) {
         CK(cudaEventRecord(j->ev[6], st));
         CK(cudaMemcpyAsync(j->h_results, j->d_results, sizeof(ChunkResult) * n, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(j->h_pdesc, j->d_pdesc, sizeof(ParseDesc) * n, cudaMemcpyDeviceToHost, st));
@@ -542,7 +556,9 @@ int pp_job_download(pp_job *j)
         CK(cudaStreamSynchronize(st));
         bool redo = false;
         if (j->h_totals->overflow) {
-            // more records than the arrays hold: grow to the exact need and parse again
+            // more records than the arrays hold: grow to the exact need and parse again.  (Device
+            // pointers handed out earlier by pp_job_device_ptrs are invalidated by this; callers take
+            // them after pp_job_download, see ppb200.h.)
             int rc = job_alloc_lines(j, j->h_totals->total_records + 16);
             if (rc != PP_OK) return rc;
             redo = true;
@@ -550,11 +566,15 @@ int pp_job_download(pp_job *j)
             for (int k = 0; k < j->n; k++)
                 if ((j->h_pout[k].flags & 1u) && !j->h_pdesc[k].exact) { redo = true; break; }
         }
-        if (!redo) break;
+        if (!redo) { settled = true; break; }
         int launches = 0;
         int rc = job_parse_stage(j, st, true, &launches);
         if (rc != PP_OK) return rc;
         j->info.launches += launches;
+    }
+    if (!settled) {
+        fprintf(stderr, "ppb200: parse stage did not settle after 4 re-runs\n");
+        return PP_E_CUDA;
     }
     pp_job_info &I = j->info;
     I.total_records = j->h_totals->total_records;
@@ -679,6 +699,27 @@ int pp_job_count_pattern(pp_job *j, const uint8_t *pattern, int32_t pattern_len,
                             d.as<unsigned long long>(), j->ctx->sm_count, j->ctx->stream));
     CK(cudaMemcpyAsync(count, d.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, j->ctx->stream));
     CK(cudaStreamSynchronize(j->ctx->stream));
+    return PP_OK;
+}
+
+int pp_job_digests(pp_job *j, uint64_t *bytes_digest, uint64_t *fields_digest)
+{
+    if (!j || !j->ctx || !j->have_results) return PP_E_ARG;
+    if (j->n <= 0) return PP_OK;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    DevBuf d;
+    const size_t words = (size_t)j->n * 2;
+    CK(d.alloc(words * sizeof(unsigned long long)));
+    CK(launch_digests(j->d_slots, j->d_descs, j->d_results, j->d_pdesc, j->d_pout, j->n, j->d_lines, j->rec_cap,
+                      d.as<unsigned long long>(), j->ctx->stream));
+    std::vector<uint64_t> h(words);
+    CK(cudaMemcpyAsync(h.data(), d.p, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, j->ctx->stream));
+    CK(cudaStreamSynchronize(j->ctx->stream));
+    for (int k = 0; k < j->n; k++) {
+        if (bytes_digest) bytes_digest[k] = h[2 * (size_t)k];
+        if (fields_digest) fields_digest[k] = h[2 * (size_t)k + 1];
+    }
     return PP_OK;
 }
 
@@ -814,7 +855,7 @@ int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const
                         pdesc.as<ParseDesc>(), pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess ||
             launch_parse(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, tbase.as<uint32_t>(), tiles0, tiles0,
                          lines.as<uint32_t>(), rec_cap, pout.as<ParseOut>(), totals.as<ScanTotals>(),
-                         work.as<unsigned long long>(), ctx->sm_count, st) != cudaSuccess ||
+                         work.as<unsigned long long>(), ctx->sm_count, ctx->parse_per_sm, st) != cudaSuccess ||
             launch_exact_emit(slot.as<uint8_t>(), pdesc.as<ParseDesc>(), 1, lines.as<uint32_t>(), rec_cap,
                               pout.as<ParseOut>(), totals.as<ScanTotals>(), st) != cudaSuccess)
             return PP_E_CUDA;

@@ -59,6 +59,14 @@ def lib():
         L.ora_decompress_all_mt.argtypes = [p, sz, p, C.c_int, C.c_int, C.c_int, C.POINTER(i64)]
         L.ora_naive_count.restype = i64
         L.ora_naive_count.argtypes = [p, sz, C.POINTER(i64)]
+        L.ora_naive_records.restype = i64
+        L.ora_naive_records.argtypes = [p, i64, p, i64]
+        L.ora_digest_bytes.restype = C.c_uint64
+        L.ora_digest_bytes.argtypes = [p, i64]
+        L.ora_digest_fields.restype = C.c_uint64
+        L.ora_digest_fields.argtypes = [p, i64]
+        L.ora_chunk_digests_mt.restype = C.c_int
+        L.ora_chunk_digests_mt.argtypes = [p, sz, p, C.c_int, C.c_int, C.c_int, p]
         L.ora_zcat.restype = i64
         L.ora_zcat.argtypes = [p, sz, p, i64]
         _lib = L
@@ -186,4 +194,34 @@ def zcat(gz, cap):
     n = lib().ora_zcat(_ptr(gz), gz.size, _ptr(out), cap)
     if n < 0:
         raise RuntimeError(f"zcat failed {n}")
+    return out[:n]
+
+
+def naive_records(data: np.ndarray):
+    """SimpleDecompressor/Parsing.cs:9-49 over the inflated stream (+ zero tail): (count, recs[n,8]) with
+    idnFrom, idnLen, seqFrom, seqLen, plsFrom, plsLen, qltFrom, qltLen as stream offsets; -1 = throws."""
+    cap = data.size // 4 + 4
+    recs = np.zeros((cap, 8), np.int64)
+    n = lib().ora_naive_records(_ptr(data), data.size, _ptr(recs), cap)
+    return n, recs[: max(n, 0)]
+
+
+def digest_bytes(a: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8)
+    return int(lib().ora_digest_bytes(_ptr(a) if a.size else None, a.size))
+
+
+def digest_fields(recs: np.ndarray) -> int:
+    recs = np.ascontiguousarray(recs, np.int64)
+    return int(lib().ora_digest_fields(_ptr(recs) if recs.size else None, recs.shape[0]))
+
+
+def chunk_digests(gz, ix, first=0, n=None, threads=None):
+    """Per chunk (inflated length, records, bytes digest, fields digest) from the oracle, `threads` workers."""
+    import os
+    n = ix.count - 1 - first if n is None else n
+    out = np.zeros((max(n, 1), 4), np.uint64)
+    rc = lib().ora_chunk_digests_mt(_ptr(gz), gz.size, ix.h, first, n, threads or (os.cpu_count() or 1), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle chunk digests failed rc={rc}")
     return out[:n]

@@ -257,3 +257,32 @@ def test_c_abi_from_plain_c(tmp_path):
     import torch
     code = int(kv["open"].split()[0])
     assert code == (0 if torch.cuda.is_available() else -101), kv["open"]
+
+
+def test_record_cap_verdict_matches_oracle_around_the_limit():
+    """Core.cs:93 throws as soon as a partial record needs its 32769th byte — also when an '@' follows in
+    the same inflate span.  CreateIndex and the oracle must give the same verdict for records just
+    below, at and above the limit, wherever the span boundaries fall."""
+    import parallelparsing_b200 as pp
+    rng = np.random.default_rng(3)
+    verdicts = set()
+    for seq_len in (16300, 16350, 16370, 16376, 16377, 16380, 16400, 17000):
+        recs = []
+        for i in range(6):
+            L = seq_len if i == 3 else int(rng.integers(50, 4000))
+            seq = bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8))
+            recs.append(b"@r%d\n" % i + seq + b"\n+\n" + b"?" * L + b"\n")
+        gz = corpus.gz_member(b"".join(recs), 6)
+        try:
+            O.OracleIndex.build(gz, 2)
+            want = 0
+        except RuntimeError:
+            want = -104
+        try:
+            pp.Core.BuildDeflateIndex(gz, 2)
+            got = 0
+        except pp.ZException as e:
+            got = e.Code
+        assert got == want, (seq_len, got, want)
+        verdicts.add(want)
+    assert verdicts == {0, -104}

@@ -166,3 +166,77 @@ def test_parse_stop_rules():
     assert run(b"", b"@a\nAC\n+\n??\n@b\nGG\n") == 1  # trailing partial record dropped
     assert run(b"", b"xa\nAC\nx\n??\n") == 1          # first bytes of lines 0 and 2 are not checked
     assert run(b"", b"") == 0
+
+
+def test_hot_path_parser_equals_naive_parser_on_well_formed_input():
+    """Independent second pin of the PARSE half: the restatement of the hot-path parser
+    (Decompressor/Parsing.cs:11-69, chunk by chunk over CombinedMemory) and the restatement of the
+    Naive parser (SimpleDecompressor/Parsing.cs:9-49, one pass over the whole stream) are two different
+    algorithms of the reference; on well-formed FASTQ they must cut the same four fields out of the
+    same bytes, record for record.  Records are compared in stream coordinates (chunk k's combined
+    memory starts |offset_k| bytes before Output_k); the H1 duplicate (a complete record in
+    Point.offset) is the one documented difference and is dropped before comparing."""
+    fq = corpus.fastq(30000)  # Generator's native U[128,512) lengths
+    gz = corpus.gz_member(fq, 6)
+    data = np.frombuffer(fq, np.uint8)
+    n_naive, naive = O.naive_records(np.concatenate([data, np.zeros(65536, np.uint8)]))
+    assert n_naive == 30000
+    ox = O.OracleIndex.build(gz, 1000)
+    outs = ox.outputs()
+    got = []
+    for k in range(ox.count - 1):
+        n, recs, buf, _ = O.chunk(gz, ox, k)
+        off = ox.point(k)["offset"]
+        base = outs[k] - off.size
+        r = recs.copy()
+        if k > 0 and off.size and off[-1] == 10 and int((off == 10).sum()) == 4:
+            r = r[1:]  # quirk H1: the previous chunk already yielded this record
+        # idnFrom, idnLen, seqFrom, seqLen, plsFrom, plsLen, qltFrom, qltLen in stream coordinates
+        g = r[:, 1:9].copy()
+        g[:, 0::2] += base
+        got.append(g)
+    got = np.concatenate(got)
+    assert got.shape == naive.shape and np.array_equal(got, naive)
+    # and the fields really are the generator's lines
+    lines = fq.split(b"\n")
+    for r in (0, 1, 12345, 29999):
+        f = naive[r]
+        assert fq[f[0]:f[0] + f[1]] == lines[4 * r][1:] and fq[f[2]:f[2] + f[3]] == lines[4 * r + 1]
+        assert fq[f[4]:f[4] + f[5]] == lines[4 * r + 2][1:] and fq[f[6]:f[6] + f[7]] == lines[4 * r + 3]
+
+
+def test_digests_are_order_and_position_sensitive_and_match_numpy():
+    """The oracle's digests (the functions the GPU library restates, pp_job_digests) against a direct
+    numpy evaluation of their definition; swaps and shifts must change them."""
+    def mix(x):
+        x = (x + np.uint64(0x9E3779B97F4A7C15))
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    rng = np.random.default_rng(0)
+    with np.errstate(over="ignore"):
+        for n in (0, 1, 7, 8, 9, 15, 16, 17, 1000, 4099):
+            a = rng.integers(0, 256, n, dtype=np.uint8)
+            pad = np.concatenate([a, np.zeros((-n) % 8, np.uint8)]).view("<u8")
+            want = int(mix(np.array([n], np.uint64))[0] + (mix(np.arange(pad.size, dtype=np.uint64)) * (pad + np.uint64(1))).sum(dtype=np.uint64))
+            assert O.digest_bytes(a) == want, n
+        recs = rng.integers(-5, 1 << 31, (300, 9)).astype(np.int64)
+        want = int((mix(np.arange(2700, dtype=np.uint64)) * (recs.reshape(-1).view(np.uint64) + np.uint64(1))).sum(dtype=np.uint64))
+        assert O.digest_fields(recs) == want
+    a = rng.integers(0, 256, 100, dtype=np.uint8)
+    b = a.copy(); b[[3, 4]] = b[[4, 3]]
+    assert a[3] == a[4] or O.digest_bytes(a) != O.digest_bytes(b)
+    assert O.digest_bytes(a) != O.digest_bytes(a[:-1]) and O.digest_bytes(np.zeros(8, np.uint8)) != O.digest_bytes(np.zeros(9, np.uint8))
+    r2 = recs.copy(); r2[[0, 1]] = r2[[1, 0]]
+    assert O.digest_fields(recs) != O.digest_fields(r2)
+
+
+def test_chunk_digests_mt_equals_single_chunk_calls():
+    gz = corpus.gz_member(corpus.fastq(9000, fixed=150), 6)
+    ox = O.OracleIndex.build(gz, 1000)
+    d = O.chunk_digests(gz, ox, threads=4)
+    assert d.shape[0] == ox.count - 1
+    for k in range(ox.count - 1):
+        n, recs, buf, _ = O.chunk(gz, ox, k)
+        assert (int(d[k, 0]), int(d[k, 1])) == (buf.size, n)
+        assert int(d[k, 2]) == O.digest_bytes(buf) and int(d[k, 3]) == O.digest_fields(recs)

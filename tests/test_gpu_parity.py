@@ -547,3 +547,212 @@ def test_decompress_all_with_irregular_records(device):
         total += n
     assert total == info.total_records
     job.free()
+
+
+# ----------------------------------------------------------------------------------------------
+# Parity at the BASELINE.json configurations, at their stated sizes.  Every chunk is compared with
+# the oracle through four integers (inflated length, record count, digest of the inflated bytes,
+# digest of the nine per-record integers); the digests are computed on the GPU (pp_job_digests) and,
+# independently, by the oracle over its own output — only K x 4 integers cross PCIe.
+# ----------------------------------------------------------------------------------------------
+import functools
+import hashlib
+import os
+import subprocess
+import tempfile
+
+
+def _digest_parity(pp, device, gz, ix, ox, zero_copy=False, gz_ptr=None):
+    """All chunks of (gz, ix) on the GPU against the oracle's (length, records, bytes digest, fields digest)."""
+    assert ix.Count == ox.count
+    job = pp.Job(device, ix, gz.size, zero_copy=zero_copy)
+    if zero_copy:
+        job.upload(gz_ptr); job.execute(); job.download()
+        info = job.info()
+    else:
+        info = job.run(gz)
+    assert info.status == 0 and info.n_chunks == ox.count - 1
+    want = O.chunk_digests(gz, ox)
+    bd, fd = job.digests()
+    base = 0
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        assert (c.status, c.inflated, c.records, c.record_base) == (0, int(want[k, 0]), int(want[k, 1]), base), f"chunk {k}"
+        assert int(bd[k]) == int(want[k, 2]), f"chunk {k}: inflated bytes differ (digest)"
+        assert int(fd[k]) == int(want[k, 3]), f"chunk {k}: record fields differ (digest)"
+        base += c.records
+    assert info.total_records == base
+    job.free()
+    return info
+
+
+@functools.lru_cache(maxsize=None)
+def _generator_file(reads, fixed=150, seed=0, system_gzip=False, lognormal=None, cap=0):
+    """Generator-exact FASTQ -> one gzip member on disk (cached for the session); returns the .gz path."""
+    d = tempfile.mkdtemp(prefix="pp_cfg_")
+    fq_path, gz_path = os.path.join(d, "reads.fastq"), os.path.join(d, "reads.fastq.gz")
+    cmd = [corpus.PPGEN, str(reads), "--seed", str(seed)]
+    if lognormal:
+        cmd += ["--lognormal", str(lognormal[0]), str(lognormal[1])]
+        if cap:
+            cmd += ["--cap", str(cap)]
+    elif fixed:
+        cmd += ["--fixed", str(fixed)]
+    if system_gzip:
+        with open(fq_path, "wb") as f:
+            subprocess.check_call(cmd, stdout=f)
+        subprocess.check_call(["gzip", "-6", "-f", fq_path])     # the reference's inputs: `gzip -6`
+    else:
+        p1 = subprocess.Popen(cmd, stdout=subprocess.PIPE)
+        p2 = subprocess.Popen([corpus.PPGZIP, "-l", "6", "-", gz_path], stdin=p1.stdout)
+        p1.stdout.close()
+        assert p2.wait() == 0 and p1.wait() == 0
+    return gz_path
+
+
+def test_baseline_config1_1M_reads_gzip6_chunk10000(device):
+    """BASELINE config 1: Generator seed 0, 1 M reads x 150 bp, `gzip -6`, chunk 10 000 — the
+    reference's own CPU-runnable case.  Must reproduce SURVEY.md §8c's known answers (381 111 160 B,
+    md5 4e84..., 99 points / 98 chunks, 4 209-10 284 records per chunk) and equal the oracle on every
+    chunk: chunk boundaries, inflated length, bytes, record count, the nine integers of every record."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(1_000_000, system_gzip=True), np.uint8)
+    ix = pp.Core.BuildDeflateIndex(gz, 10_000)
+    ox = O.OracleIndex.build(gz, 10_000)
+    assert ix.Count == ox.count == 99
+    so, si, sb, sl = ix.scalars()
+    assert list(so) == ox.outputs() and list(si) == ox.inputs()
+    info = _digest_parity(pp, device, gz, ix, ox)
+    assert info.total_bytes == 381_111_160 and info.n_chunks == 98
+    job = pp.Job(device, ix, gz.size)
+    job.run(gz)
+    recs = [job.chunk(k).records for k in range(98)]
+    assert (min(recs), max(recs)) == (4209, 10284) and sum(recs) == info.total_records >= 1_000_000
+    assert hashlib.md5(job.all_bytes().tobytes()).hexdigest() == "4e840faad7d4a77e3a8bd25b0f47dd23"
+    job.free()
+
+
+def test_baseline_config2_10M_reads_chunk10000_every_chunk(device):
+    """BASELINE config 2 at full size (10 M reads x 150 bp, 3.8 GB inflated, ~977 chunks): every chunk
+    against the oracle (boundaries from the oracle's own CreateIndex), in staged and in pull mode."""
+    import parallelparsing_b200 as pp
+    gz_np = np.fromfile(_generator_file(10_000_000), np.uint8)
+    gz, ptr = pp.pinned_copy(gz_np)
+    ix = pp.Core.BuildDeflateIndex(gz_np, 10_000)
+    ox = O.OracleIndex.build(gz_np, 10_000)
+    assert list(ix.scalars()[1]) == ox.inputs()
+    info = _digest_parity(pp, device, gz, ix, ox)
+    assert info.total_records >= 10_000_000 and info.n_chunks > 900
+    _digest_parity(pp, device, gz, ix, ox, zero_copy=True, gz_ptr=ptr)
+    pp.lib().pp_host_free(ptr)
+
+
+def test_baseline_config4_long_reads_capped_chunk1000(device):
+    """BASELINE config 4 (reference-legal variant, quirk H2): lognormal lengths, mean 10 kbp, sigma 0.5,
+    capped at 16 000 bp, chunk 1 000 — ~20 MB chunks, long matches, records of up to 32 KB."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(30_000, lognormal=(10000, 0.5), cap=16000), np.uint8)
+    ix = pp.Core.BuildDeflateIndex(gz, 1000)
+    ox = O.OracleIndex.build(gz, 1000)
+    info = _digest_parity(pp, device, gz, ix, ox)
+    assert info.n_chunks >= 25 and info.total_bytes > 500_000_000
+
+
+def test_baseline_config4_long_reads_uncapped_chunk1000(device):
+    """BASELINE config 4 as stated (uncapped): records above 32 768 B make the reference's CreateIndex
+    throw (quirk H2), so the cap is lifted on both sides — a documented extension."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(20_000, lognormal=(10000, 0.5)), np.uint8)
+    with pytest.raises(pp.ZException):
+        pp.Core.BuildDeflateIndex(gz, 1000)
+    ix = pp.Core.BuildDeflateIndex(gz, 1000, lift_record_cap=True)
+    ox = O.OracleIndex.build(gz, 1000, True)
+    _digest_parity(pp, device, gz, ix, ox)
+
+
+@pytest.mark.parametrize("chunk", [1000, 10_000, 100_000])
+def test_baseline_config5_chunk_sweep_every_chunk(device, chunk):
+    """BASELINE config 5's chunk-size sweep on a 1 M-read file: per-chunk oracle comparison at every
+    chunk size (781 / 99 / 11 points), not totals only."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(1_000_000), np.uint8)
+    ix = pp.Core.BuildDeflateIndex(gz, chunk)
+    ox = O.OracleIndex.build(gz, chunk)
+    info = _digest_parity(pp, device, gz, ix, ox)
+    assert info.total_bytes == 381_111_160
+
+
+def test_gpu_records_equal_naive_parser_field_by_field(device):
+    """Second, independent pin: on well-formed input the GPU's records (PP_JOB_STRICT: without the H1
+    duplicates) are, field by field, the records of the reference's OTHER parser
+    (SimpleDecompressor/Parsing.cs:9-49, restated in the oracle) run over the whole stream."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(200_000)  # native U[128,512) lengths
+    gz = corpus.gz_parallel(fq, 6, segment=4 << 20, threads=4)
+    data = np.frombuffer(fq, np.uint8)
+    n_naive, naive = O.naive_records(np.concatenate([data, np.zeros(65536, np.uint8)]))
+    assert n_naive == 200_000
+    ix = pp.Core.BuildDeflateIndex(gz, 3000)
+    job = pp.Job(device, ix, gz.size, strict=True)
+    info = job.run(gz)
+    assert info.status == 0 and info.total_records == n_naive
+    l0, l1, l2, l3 = [x.astype(np.int64) for x in job.line_starts()]
+    outs, _, _, offl = ix.scalars()
+    base = np.zeros(info.total_records, np.int64)   # stream offset of combined-memory index 0, per record
+    pend = np.zeros(info.total_records, np.int64)
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        base[c.record_base: c.record_base + c.records] = outs[k] - offl[k]
+        pend[c.record_base: c.record_base + c.records] = c.parse_end
+    nxt = np.concatenate([l0[1:], [0]])
+    last = np.ones(info.total_records, bool)
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        if c.records:
+            last[c.record_base: c.record_base + c.records - 1] = False
+    nxt = np.where(last, pend, nxt)
+    got = np.stack([l0 + 1 + base, l1 - l0 - 2, l1 + base, l2 - l1 - 1, l2 + 1 + base, l3 - l2 - 2, l3 + base,
+                    nxt - l3 - 1], axis=1)
+    assert np.array_equal(got, naive)
+    job.free()
+
+
+def test_zero_copy_reads_nothing_past_a_registered_buffer(device):
+    """PP_JOB_ZEROCOPY on a caller buffer pinned with pp_host_register that ENDS at the end of a
+    mapping (the page behind it is inaccessible): the kernels may read exactly gz_len bytes."""
+    import ctypes as C
+    import mmap
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(20000, fixed=150)
+    gz_np = corpus.gz_member(fq, 6)
+    for trim in (0, 1, 5, 13):   # ragged tails: the buffer ends 0..15 bytes past a 16-byte boundary
+        n = gz_np.size - trim
+        pages = (n + mmap.PAGESIZE - 1) // mmap.PAGESIZE
+        mm = mmap.mmap(-1, (pages + 1) * mmap.PAGESIZE)
+        addr = C.addressof(C.c_char.from_buffer(mm))
+        libc = C.CDLL(None, use_errno=True)
+        assert libc.mprotect(C.c_void_p(addr + pages * mmap.PAGESIZE), C.c_size_t(mmap.PAGESIZE), 0) == 0  # PROT_NONE
+        start = pages * mmap.PAGESIZE - n
+        view = np.frombuffer(mm, np.uint8, n, start)
+        view[:] = gz_np[:n]
+        ix = pp.Core.BuildDeflateIndex(gz_np, 1000)
+        pp.check(pp.lib().pp_host_register(C.c_void_p(addr + start), n))
+        try:
+            # all chunks but (for trimmed buffers) the last, whose input is cut short
+            nch = ix.Count - 1 - (1 if trim else 0)
+            job = pp.Job(device, ix, n, 0, nch, zero_copy=True)
+            job.upload(C.c_void_p(addr + start)); job.execute(); job.download()
+            info = job.info()
+            assert info.status == 0
+            outs = ix.scalars()[0]
+            assert job.all_bytes().tobytes() == fq[: int(outs[nch])]
+            job.free()
+            if trim:  # the last chunk alone: its input ends early -> the reference's DATA_ERROR (Core.cs:174), no fault
+                job = pp.Job(device, ix, n, ix.Count - 2, 1, zero_copy=True)
+                job.upload(C.c_void_p(addr + start)); job.execute(); job.download()
+                assert job.info().status in (0, -3)
+                job.free()
+        finally:
+            pp.lib().pp_host_unregister(C.c_void_p(addr + start))
+        del view
+        mm.close()
