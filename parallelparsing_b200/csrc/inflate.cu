@@ -10,7 +10,7 @@ namespace pp {
 __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
     pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
                       uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
-                      uint32_t *scratch, size_t scratch_words, int *next_chunk)
+                      uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift)
 {
     extern __shared__ __align__(128) uint8_t pp_smem_raw[];
     ppinf::Sm sm;
@@ -28,7 +28,11 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         const int k = (int)sm.u[16];
         __syncthreads();
         if (k >= n) break;
-        ppinf::inflate_chunk(sm, descs[k], comp, comp_bytes, slots, lead, map, results[k], stage_phase);
+        ppinf::ChunkDesc d = descs[k];
+        // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
+        d.in_bit += 8ull * comp_shift;
+        d.in_limit += comp_shift;
+        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase);
     }
 }
 
@@ -69,12 +73,16 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
                            const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
+    // TMA bulk copies need 16-byte aligned global addresses: align the base down and shift the bit cursors
+    const uint32_t comp_shift = (uint32_t)((uintptr_t)comp & 15u);
+    comp -= comp_shift;
+    comp_bytes += comp_shift;
     cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);
     const int grid = n < cfg.grid ? n : cfg.grid;
     pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
-                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter);
+                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift);
     return cudaGetLastError();
 }
 

@@ -117,23 +117,15 @@ constexpr int kHdrWords = 160;          // a dynamic block header is < 4600 bits
 constexpr int kSlackWords = 16;         // last symbol overrun (<= 48 bits) + reader look-ahead
 constexpr int kMaxThreads = 1024;
 constexpr int kTileB = 16;              // output bytes per thread per resolve tile
-constexpr uint32_t kMinMapCap = 160u * 1024u;  // one sub-sequence can emit kSubBits/2*258 < 128 Ki bytes
 
 PP_HD uint32_t cw_words_for(int T) { return (uint32_t)(T * kSubW + kHdrWords + kSlackWords + 3) & ~3u; }
-// output bytes one window may produce before the window is cut short
-PP_HD uint32_t map_cap_for(int T)
-{
-    const uint32_t c = (uint32_t)T * (uint32_t)kSubW * 4u * 8u;  // 8x expansion of a full window
-    return c > kMinMapCap ? c : kMinMapCap;
-}
 // Per-CTA scratch in global memory (u32 words): the tokens of a window — token k of
-// sub-sequence s at tok[s * kTokRows + k], so the tokens one 16-byte output group needs are
-// neighbours in memory (one or two sectors, fetched in a single round trip) — followed by
-// the group index (one word per 16 output bytes).
-constexpr int kTokRows = kSubBits + 16;  // a sub-sequence holds at most kSubBits symbols (+ read-ahead slack)
+// sub-sequence s at tok[s * kTokRows + k] (a row is read by one warp, 32 tokens = 128 bytes
+// per load).  A sub-sequence holds at most kSubBits symbols; a match that crosses a resolve-tile
+// boundary is written twice (once per tile), at most once every 31 tokens.
+constexpr int kTokRows = kSubBits + kSubBits / 16 + 16;
 PP_HD uint32_t tok_words_for(int T) { return (uint32_t)kTokRows * (uint32_t)T; }
-PP_HD uint32_t idx_words_for(int T) { return map_cap_for(T) / 16u + 16u; }
-PP_HD size_t scratch_words_for(int T) { return (size_t)tok_words_for(T) + idx_words_for(T); }
+PP_HD size_t scratch_words_for(int T) { return (size_t)tok_words_for(T); }
 
 // ---- table entry ------------------------------------------------------------
 // [4:0] bits to consume (code + extra)  [7:5] kind  [12:8] code length
@@ -717,27 +709,33 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 }
 
 // ---- GUESS / SYNC / EMIT: one thread walks one segment ---------------------------------
-// Decodes the symbols that START in [start, limit) (window-relative bits).
-// WRITE: also emits one TOKEN per symbol, token k of this thread at tok[t * kTokRows + k]
-//   literal: 1 << 16 | 0x8000 | byte      match: len << 16 | (dist - 1) | (dist < len) << 25
-// and, for every multiple of 16 below oclip that a token's output range [o, o + len) covers,
-// the GROUP INDEX entry idx[m / 16] = t | k << 10 | (m - o) << 20, which tells the resolve
-// stage where the bytes of group m / 16 start.  `o` is the virtual output index (window
-// output offset + misalignment of the window's first byte).
+// EMIT decodes the symbols that START in [start, limit) (window-relative bits) and writes one
+// 32-bit TOKEN per symbol, token k of this thread at tok[t * kTokRows + k]:
+//   [15:0]  entry: what the resolve stage starts from for every byte of the token —
+//           0x8000 | byte for a literal, distance - 1 for a match;
+//   [29:16] position of the token's first byte inside its RESOLVE TILE (tiles are R = 16 T
+//           output bytes, cut in the window's virtual index space; R <= 16384);
+//   [31:30] tile number modulo 4 (a row's tokens are in output order, so "the tokens of tile i"
+//           is a run of equal tags; a token is at most 258 bytes, so no tag is skipped).
+// A match that crosses a tile boundary is written a second time as a token that starts at the
+// boundary: bytes repeat with period `distance` inside a match, so the continuation is an
+// ordinary match of the same distance.  The token's length is not stored: the resolve stage
+// sees where the next token starts.  `o` is the virtual output index of the segment's first
+// byte (window output offset + misalignment of the window's first byte).
 struct Seg {
     uint32_t end, out, flag, ntok;
 };
-// token = entry | len << 16 | overlap << 25: `entry` is what the resolve stage writes for every byte
-// of the token (0x8000|byte for a literal, dist-1 for a match), `overlap` marks dist < len
-PP_DEV uint32_t tok_lit(uint32_t byte) { return (1u << 16) | 0x8000u | byte; }
-PP_DEV uint32_t tok_match(uint32_t len, uint32_t dist) { return (len << 16) | (dist - 1u) | (dist < len ? 1u << 25 : 0u); }
-PP_DEV uint32_t idx_pack(uint32_t t, uint32_t k, uint32_t off) { return t | (k << 10) | (off << 20); }
+PP_DEV uint32_t tok_pack(uint32_t entry, uint32_t p0, uint32_t rshift)
+{
+    return entry | ((p0 & ((1u << rshift) - 1u)) << 16) | ((p0 >> rshift) << 30);
+}
 
 template <int WRITE>
-PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *tok, uint32_t *idx, uint32_t T,
-                      uint32_t t, uint32_t o, uint32_t oclip)
+PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *tok, uint32_t rshift, uint32_t t,
+                      uint32_t o)
 {
     const uint32_t *cw = sm.cw;
+    uint32_t *row = tok + t * (uint32_t)kTokRows;
     uint32_t wp = start >> 5;
     const uint32_t sh = start & 31u;
     uint64_t buf = ((uint64_t)cw[wp] | ((uint64_t)cw[wp + 1] << 32)) >> sh;
@@ -752,12 +750,7 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
         if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
         const uint32_t kind = e_kind(e), tot = e_tot(e);
         if (kind == K_LIT) {
-            if (WRITE) {
-                const uint32_t p0 = o + out;
-                tok[t * (uint32_t)kTokRows + k] = tok_lit(e_val(e) & 0xffu);
-                if ((p0 & 15u) == 0u && p0 < oclip) idx[p0 >> 4] = idx_pack(t, k, 0);
-                k++;
-            }
+            if (WRITE) row[k++] = tok_pack(e_val(e), o + out, rshift);
             out++;
             buf >>= tot;
             cnt -= tot;
@@ -779,12 +772,9 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
             // dist <= 32768 <= lead_len always, so "distance too far back" cannot occur:
             // the reference primes a full 32 KB dictionary (Core.cs:158)
             if (WRITE) {
-                const uint32_t p0 = o + out;
-                tok[t * (uint32_t)kTokRows + k] = tok_match(len, dist);
-                uint32_t end = p0 + len;
-                if (end > oclip) end = oclip;
-                for (uint32_t m = (p0 + 15u) & ~15u; m < end; m += 16u) idx[m >> 4] = idx_pack(t, k, m - p0);
-                k++;
+                const uint32_t p0 = o + out, p1 = p0 + len - 1u;
+                row[k++] = tok_pack(dist - 1u, p0, rshift);
+                if ((p0 ^ p1) >> rshift) row[k++] = tok_pack(dist - 1u, (p1 >> rshift) << rshift, rshift);
             }
             out += len;
             continue;
@@ -947,20 +937,26 @@ struct WindowOut {
 // ---- RESOLVE ------------------------------------------------------------------------
 // Tokens -> bytes for window output [0, total) that lands at outp[0..total).
 // `a` = misalignment of outp (outp - a is 16-byte aligned); virtual index v = q + a.
-// The output is walked in tiles of 16 bytes per thread, three steps per tile:
-//  EXPAND   thread g owns group g (16 consecutive bytes): the group index names the token its
-//           first byte lies in; it walks the tokens and writes one u16 per byte into shared
-//           memory: 0x8000|literal, or distance-1 (overlapping matches are rewritten so that
-//           every source lies before the match).
-//  GATHER   lanes now own INTERLEAVED bytes (byte j*32+lane of the warp's 512): a source in
-//           front of the tile is final in global memory — the 32 lanes of a load mostly read
-//           one or two runs of consecutive bytes, so it costs a few sectors, not 32 — a source
-//           inside the tile becomes the tile-relative index of that byte.
+// The output is walked in tiles of R = 16 bytes per thread; per tile:
+//  SCATTER  (one tile ahead, overlapped with CHASE of the previous tile) the tile's tokens are
+//           brought from the rows in global memory into shared memory BY POSITION: a warp takes
+//           a row, its lanes take consecutive tokens (coalesced), each writes its 16-bit entry
+//           at ent[position] and sets bit `position` of the tile's HEAD MASK.  Per row a cursor
+//           remembers how far earlier tiles got.
+//  EXPAND   lanes own INTERLEAVED bytes (byte j*32+lane of the warp's 512): the token a byte
+//           belongs to is the last head at or before it — one mask word, one count-leading-
+//           zeros — and its offset inside the token falls out of the same subtraction.  A
+//           literal is final; a match byte whose source lies in front of the tile is final in
+//           global memory (the 32 lanes of a load read one or two runs of consecutive bytes, a
+//           few sectors) and is fetched right here; a source inside the tile becomes the
+//           tile-relative index of that byte.  Overlapping matches (distance < offset) are
+//           re-pointed at the same byte one or more periods earlier, in front of the match.
 //  CHASE    in-tile sources are followed through shared memory with no barrier: an entry is
 //           always either the byte or the index of an EARLIER byte with the same value and
 //           every hop is published, so chains collapse like pointer jumping whatever the
-//           interleaving of the warps.  Then the bytes leave, 32 consecutive bytes per warp
-//           store; '\n' and NUL are counted on the way for the parse stage.
+//           interleaving of the warps.
+//  STORE    thread t packs the sixteen final entries of group t and writes one 16-byte vector;
+//           '\n' and NUL are counted on the way for the parse stage.
 PP_DEV uint32_t div_small(uint32_t i, uint32_t d)  // floor(i / d) for i, d < 512
 {
 #ifdef PP_HOST_EMU
@@ -969,138 +965,217 @@ PP_DEV uint32_t div_small(uint32_t i, uint32_t d)  // floor(i / d) for i, d < 51
     return (uint32_t)__fdividef((float)i + 0.5f, (float)d);  // (i+0.5)/d is >= 0.5/d away from an integer
 #endif
 }
-
-// Shared layout of the tile's u16 entries: entry q lives at res[q].  GATHER/CHASE touch 32
-// consecutive entries per warp access (no bank conflicts); EXPAND stores its 16 entries as two
-// 16-byte vectors (lanes 32 bytes apart: two-way conflicts at most).
+PP_DEV uint32_t clz32(uint32_t v)
+{
+#ifdef PP_HOST_EMU
+    return v ? (uint32_t)__builtin_clz(v) : 32u;
+#else
+    return (uint32_t)__clz((int)v);
+#endif
+}
+// Shared-memory accesses of the EXPAND step by 32-bit shared address (device) / plain pointer
+// (emulation): keeps the per-byte address arithmetic to one add.
+#ifdef PP_HOST_EMU
+typedef uint8_t *SAddr;
+PP_DEV SAddr saddr(const volatile void *p) { return (uint8_t *)p; }
+PP_DEV uint32_t lds_u32(SAddr a, uint32_t off) { uint32_t v; memcpy(&v, a + off, 4); return v; }
+PP_DEV uint32_t lds_u16(SAddr a, uint32_t off) { uint16_t v; memcpy(&v, a + off, 2); return v; }
+PP_DEV void sts_u16(SAddr a, uint32_t off, uint32_t v) { const uint16_t x = (uint16_t)v; memcpy(a + off, &x, 2); }
+#else
+typedef uint32_t SAddr;
+PP_DEV SAddr saddr(const volatile void *p) { return (uint32_t)__cvta_generic_to_shared(const_cast<const void *>(p)); }
+PP_DEV uint32_t lds_u32(SAddr a, uint32_t off)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + off) : "memory");
+    return v;
+}
+PP_DEV uint32_t lds_u16(SAddr a, uint32_t off)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a + off) : "memory");
+    return v;
+}
+PP_DEV void sts_u16(SAddr a, uint32_t off, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + off), "h"((uint16_t)v) : "memory");
+}
+#endif
 PP_DEV uint32_t res_pos(uint32_t q) { return q; }
 PP_HD uint32_t res_entries_for(int T) { return (uint32_t)T * kTileB + (uint32_t)T * kTileB / 32u + 2u; }
 
-PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *idx, uint8_t *outp, uint32_t a,
-                           uint32_t total)
+// Shared-memory staging of a tile's tokens (lives in the compressed-window buffer, idle during
+// RESOLVE): two buffers (the tile being expanded, the tile being scattered), each R u16 entries
+// indexed by tile position + R/32 head-mask words.
+static_assert(kSubW * 4 >= 2 * 2 * kTileB + 2 * kTileB / 8, "the tile token staging (68 bytes per thread) must fit the compressed-window buffer");
+struct TileTok {
+    uint16_t *ent;   // [2][R]
+    uint32_t *mask;  // [2][R/32]
+    uint32_t *kcur;  // [T] per row: tokens consumed by earlier tiles
+};
+
+// One row's tokens of tile `tile` -> ent / mask.  Device: the lanes of the calling warp take
+// consecutive tokens.  Emulation: one thread walks the row.
+PP_DEV void scatter_row(const Sm &sm, const uint32_t *tok, const TileTok &tt, uint32_t buf, uint32_t R, uint32_t tile,
+                        uint32_t row, uint32_t lane)
+{
+    const uint32_t k0 = tt.kcur[row], nt = sm.ntok[row], tag = tile & 3u;
+    const uint32_t *rp = tok + row * (uint32_t)kTokRows;
+    uint16_t *ent = tt.ent + buf * R;
+    uint32_t *mask = tt.mask + buf * (R / 32u);
+#ifdef PP_HOST_EMU
+    (void)lane;
+    uint32_t k = k0;
+    for (; k < nt; k++) {
+        const uint32_t tv = rp[k];
+        if ((tv >> 30) != tag) break;
+        const uint32_t pos = (tv >> 16) & 0x3fffu;
+        ent[pos] = (uint16_t)tv;
+        mask[pos >> 5] |= 1u << (pos & 31u);
+    }
+    tt.kcur[row] = k;
+#else
+    uint32_t cnt = 0;
+    for (uint32_t k = k0 + lane; k < nt; k += 32u) {
+        const uint32_t tv = rp[k];
+        if ((tv >> 30) != tag) break;
+        const uint32_t pos = (tv >> 16) & 0x3fffu;
+        ent[pos] = (uint16_t)tv;
+        atomicOr(&mask[pos >> 5], 1u << (pos & 31u));
+        cnt++;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);  // the tile's tokens are a run: their count is the cursor's advance
+    if (lane == 0u) tt.kcur[row] = k0 + cnt;
+#endif
+}
+
+// Rows whose output intersects virtual range [tb, tb + R): row r starts at a + outc[r] and ends
+// where the next live row starts (the last live row has no end).  Warp w takes rows lo+w, lo+w+nw, ...
+PP_DEV void scatter_tile(const Sm &sm, const uint32_t *tok, const TileTok &tt, uint32_t buf, uint32_t R, uint32_t tile,
+                         uint32_t a, uint32_t nlive, uint32_t t)
+{
+    const uint32_t tb = tile * R, te = tb + R;
+    // hi: first row starting at or after te
+    uint32_t lo = 0, hi = nlive;
+    {
+        uint32_t l = 0, h = nlive;
+        while (l < h) { const uint32_t m = (l + h) >> 1; if (a + sm.outc[m] < te) l = m + 1u; else h = m; }
+        hi = l;
+        // lo: first row whose end (= start of row+1, or infinity for the last live row) is past tb
+        l = 0; h = hi;
+        while (l < h) {
+            const uint32_t m = (l + h) >> 1;
+            const bool ends_after = (m + 1u >= nlive) || (a + sm.outc[m + 1u] > tb);
+            if (!ends_after) l = m + 1u; else h = m;
+        }
+        lo = l;
+    }
+    const uint32_t warp = t >> 5, lane = t & 31u, nw = ((uint32_t)PP_NT + 31u) >> 5;
+#ifdef PP_HOST_EMU
+    if (lane != 0u) return;
+#endif
+    for (uint32_t row = lo + warp; row < hi; row += nw) scatter_row(sm, tok, tt, buf, R, tile, row, lane);
+}
+
+// EXPAND of one tile for thread t (see RESOLVE above).  FULL: every byte of the tile is a valid
+// output byte (all tiles but the first and the last of a window).
+template <bool FULL>
+PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask, const uint8_t *vbase, uint32_t tb,
+                        uint32_t a, uint32_t vend, int32_t near_lo, uint32_t t)
+{
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    const uint32_t qb = warp * (32u * kTileB) + lane;       // this lane's first byte; the others follow 32 apart
+    const uint32_t below = 0xffffffffu >> (31u - lane);     // bits 0..lane
+    const int32_t safe = near_lo - 1;                       // the byte just before the tile/window: final, inside the slot
+    const SAddr ent_s = saddr(ent), res_s = saddr(sm.res) + 2u * qb;
+    const SAddr mask_s = saddr(mask), mask_w = mask_s + 4u * (warp * (uint32_t)kTileB);  // the warp's 16 mask words
+    const int32_t vq = (int32_t)(tb + qb);                  // virtual index of the lane's first byte
+#pragma unroll
+    for (int h = 0; h < kTileB; h += 8) {
+        uint32_t e[8];
+        int32_t sv[8];
+        uint32_t b[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int s = h + j;                            // step: byte qb + 32 s lies in mask word warp * 16 + s
+            e[j] = 0x8000u;                                 // bytes outside the window: harmless literals
+            sv[j] = 0;
+            const uint32_t v = (uint32_t)vq + 32u * (uint32_t)s;
+            if (FULL || (v >= a && v < vend)) {
+                uint32_t m = lds_u32(mask_w, 4u * (uint32_t)s) & below;
+                uint32_t hp32 = 32u * (warp * (uint32_t)kTileB + (uint32_t)s);  // first position of the word the head is in
+                if (m == 0u) {                              // the token started in an earlier word (11 % of the bytes)
+                    uint32_t off = 4u * (warp * (uint32_t)kTileB + (uint32_t)s);
+                    while (m == 0u && off > 0u) { off -= 4u; m = lds_u32(mask_s, off); }
+                    if (m == 0u) m = 1u;                    // no head before a valid byte: cannot happen for consistent tokens
+                    hp32 = off * 8u;
+                }
+                const uint32_t hp = hp32 + 31u - clz32(m);
+                uint32_t x = lds_u16(ent_s, 2u * hp);
+                const uint32_t i = qb + 32u * (uint32_t)s - hp;
+                if (i > x) {                                // a match (x < 0x8000 <= ... never true for a literal: i < 512) whose
+                    const uint32_t dist = x + 1u;           // offset reached its distance: overlapping run, take the same byte
+                    x = dist * (div_small(i, dist) + 1u) - 1u;  // one or more periods earlier, in front of the match
+                }
+                sv[j] = (int32_t)v - (int32_t)x - 1;        // virtual index of the source (meaningless for a literal)
+                e[j] = x;
+            }
+        }
+        // unconditional loads (lanes with nothing to fetch read one shared, always valid byte), so that
+        // the eight loads of a batch are in flight together instead of one per branch
+#pragma unroll
+        for (int j = 0; j < 8; j++) b[j] = vbase[(!(e[j] & 0x8000u) && sv[j] < near_lo) ? sv[j] : safe];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t o = e[j];
+            if (!(o & 0x8000u)) o = sv[j] < near_lo ? 0x8000u | b[j] : (uint32_t)(sv[j] - (int32_t)tb);
+            sts_u16(res_s, 64u * (uint32_t)(h + j), o);
+        }
+    }
+}
+
+PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uint32_t a, uint32_t total, uint32_t nlive,
+                           uint32_t rshift)
 {
     const int T = PP_NT;
     const uint32_t R = (uint32_t)T * kTileB;
     const uint32_t vend = a + total;         // valid bytes: a <= v < vend
     uint8_t *vbase = outp - a;               // 16-byte aligned; vbase[v] is the byte of virtual index v
     volatile uint16_t *res = sm.res;
-    volatile uint32_t *stq = sm.cw;  // per-thread token queue [8][T] (cw is restaged for every window anyway)
-    for (uint32_t tb = 0; tb < vend; tb += R) {
+    TileTok tt;
+    tt.ent = reinterpret_cast<uint16_t *>(sm.cw);      // cw is restaged for every window anyway
+    tt.mask = sm.cw + R;                               // 2 R u16 = R words
+    tt.kcur = sm.ns;                                   // idle outside SYNC
+    (void)rshift;
+    PP_FOR_T(t)
+    for (uint32_t i = (uint32_t)t; i < 2u * (R / 32u); i += (uint32_t)T) tt.mask[i] = 0;
+    tt.kcur[t] = 0;
+    PP_END_T
+    PP_SYNC();
+    PP_FOR_T(t)
+    scatter_tile(sm, tok, tt, 0, R, 0, a, nlive, (uint32_t)t);
+    PP_END_T
+    PP_SYNC();
+    uint32_t tile = 0;
+    for (uint32_t tb = 0; tb < vend; tb += R, tile++) {
+        const uint32_t cb = tile & 1u;
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
-        // EXPAND: tokens -> one entry per byte.  Uniform control flow: sixteen predicated byte steps
-        // over a register queue of the group's next eight tokens (neighbours in memory, one round trip).
-        PP_FOR_W(t)
+        // EXPAND: the byte's token is the last head at or before it
+        PP_FOR_T(t)
         {
-            const uint32_t q0 = (uint32_t)t * kTileB;          // tile-relative index of the group's first byte
-            const uint32_t v0 = tb + q0;
-            uint32_t lo = v0 < a ? a - v0 : 0u;                // first valid byte of the group
-            uint32_t hi = v0 < vend ? (vend - v0 < (uint32_t)kTileB ? vend - v0 : (uint32_t)kTileB) : 0u;  // one past the last
-            if (lo > hi) lo = hi;
-            uint32_t r[kTileB / 2];                            // entries, two per word
-#pragma unroll
-            for (int j = 0; j < kTileB / 2; j++) r[j] = 0x80008000u;  // bytes outside the window: harmless literals
-            if (lo < hi) {
-                const uint32_t ie = idx[v0 >> 4];
-                uint32_t sgm = ie & 1023u, k = (ie >> 10) & 1023u, i = ie >> 20;
-                // the group's next eight tokens: one round trip, parked in shared memory (the compressed
-                // staging buffer is idle during RESOLVE) so that advancing is one indexed load.  A refill
-                // (more than eight tokens in the group, or the sub-sequence ends inside it) happens inside
-                // the byte step that runs dry, so no lane ever repeats the sixteen steps.
-                uint32_t t0 = 0, avail = 0, qi = 0;
-#define PP_REFILL()                                                                                    \
-    do {                                                                                               \
-        k += qi; /* tokens taken from the queue since the last refill */                               \
-        uint32_t nts = sm.ntok[sgm];                                                                   \
-        while (k >= nts && sgm + 1u < (uint32_t)T) { sgm++; k = 0; nts = sm.ntok[sgm]; }               \
-        const uint32_t *tp = tok + sgm * (uint32_t)kTokRows + k;                                       \
-        t0 = tp[0];                                                                                    \
-        const uint32_t t1 = tp[1], t2 = tp[2], t3 = tp[3], t4 = tp[4], t5 = tp[5], t6 = tp[6], t7 = tp[7]; \
-        stq[1u * (uint32_t)T + (uint32_t)t] = t1; stq[2u * (uint32_t)T + (uint32_t)t] = t2;            \
-        stq[3u * (uint32_t)T + (uint32_t)t] = t3; stq[4u * (uint32_t)T + (uint32_t)t] = t4;            \
-        stq[5u * (uint32_t)T + (uint32_t)t] = t5; stq[6u * (uint32_t)T + (uint32_t)t] = t6;            \
-        stq[7u * (uint32_t)T + (uint32_t)t] = t7;                                                      \
-        avail = nts - k < 8u ? nts - k : 8u;                                                           \
-        if (avail == 0u) avail = 1u; /* cannot happen for consistent tokens; never spin */             \
-        qi = 0;                                                                                        \
-    } while (0)
-                PP_REFILL();
-                // The current token is kept DECODED: cur = the entry its bytes get, rem = bytes still to
-                // emit, odist != 0 only for an overlapping run (dist < len: byte i repeats the `dist` bytes
-                // before the match, so its source is dist*(i/dist+1) back — always in front of the match
-                // itself).  A byte step is then: take cur, count down, and only at a token's last byte
-                // decode the next one.
-                uint32_t cur, rem, odist = 0, orr = 0;
-#define PP_DECODE_TOKEN(first)                                                                         \
-    do {                                                                                               \
-        const uint32_t i0 = (first) ? i : 0u;                                                          \
-        cur = t0 & 0xffffu;                                                                            \
-        rem = ((t0 >> 16) & 0x1ffu) - i0;                                                              \
-        odist = 0u;                                                                                    \
-        if (t0 >> 25) {                                                                                \
-            const uint32_t dist = cur + 1u;                                                            \
-            const uint32_t qd = div_small(i0, dist);                                                   \
-            cur = dist * (qd + 1u) - 1u;                                                               \
-            orr = i0 - qd * dist;                                                                      \
-            odist = dist;                                                                              \
-        }                                                                                              \
-    } while (0)
-                PP_DECODE_TOKEN(true);
-#pragma unroll
-                for (int j = 0; j < kTileB; j++) {
-                    if ((uint32_t)j >= lo && (uint32_t)j < hi) {  // the group's valid bytes: one byte per step
-                        // even byte: the odd half keeps its harmless literal until the next step overwrites it
-                        r[j >> 1] = (j & 1) ? (r[j >> 1] & 0x0000ffffu) | (cur << 16) : 0x80000000u | cur;
-                        if (odist) { if (++orr == odist) { orr = 0; cur += odist; } }
-                        if (--rem == 0u) {
-                            if (++qi == avail) { if ((uint32_t)j + 1u < hi) PP_REFILL(); }
-                            else t0 = stq[qi * (uint32_t)T + (uint32_t)t];
-                            PP_DECODE_TOKEN(false);
-                        }
-                    }
-                }
-#undef PP_DECODE_TOKEN
-#undef PP_REFILL
-            }
-            // entries 16 t .. 16 t + 15: two 16-byte vectors
-            uint4 *dst = reinterpret_cast<uint4 *>(sm.res + q0);
-            uint4 w0, w1;
-            w0.x = r[0]; w0.y = r[1]; w0.z = r[2]; w0.w = r[3];
-            w1.x = r[4]; w1.y = r[5]; w1.z = r[6]; w1.w = r[7];
-            dst[0] = w0;
-            dst[1] = w1;
+            const uint16_t *ent = tt.ent + cb * R;
+            const uint32_t *mask = tt.mask + cb * (R / 32u);
+            if (tb >= a && tb + R <= vend) expand_tile<true>(sm, ent, mask, vbase, tb, a, vend, near_lo, (uint32_t)t);
+            else expand_tile<false>(sm, ent, mask, vbase, tb, a, vend, near_lo, (uint32_t)t);
         }
-        // GATHER: the entries a lane reads (bytes j*32+lane of the warp's 512) were written by its own warp,
-        // so a warp-level sync is all that separates the two steps
-        PP_WARP_SPLIT(t)
-        {
-            const uint32_t qb = ((uint32_t)t >> 5) * (32u * kTileB) + ((uint32_t)t & 31u);
-            const uint32_t pb = qb;
-            // Unconditional loads (lanes with nothing to fetch read one shared, always valid byte), so
-            // that the eight loads of a batch are in flight together instead of one per branch.
-            const int32_t safe = near_lo - 1;  // the byte just before the tile/window: final, inside the slot
-#pragma unroll
-            for (int h = 0; h < kTileB; h += 8) {
-                uint32_t e[8];
-                int32_t sv[8];
-                uint32_t b[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    e[j] = res[pb + (uint32_t)(h + j) * 32u];
-                    sv[j] = (int32_t)(tb + qb + (uint32_t)(h + j) * 32u) - (int32_t)e[j] - 1;  // virtual index of the source
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) b[j] = vbase[(!(e[j] & 0x8000u) && sv[j] < near_lo) ? sv[j] : safe];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (!(e[j] & 0x8000u))
-                        res[pb + (uint32_t)(h + j) * 32u] =
-                            (uint16_t)(sv[j] < near_lo ? 0x8000u | b[j] : (uint32_t)(sv[j] - (int32_t)tb));
-                }
-            }
-        }
-        PP_END_W
+        PP_END_T
         PP_SYNC();
         PP_PHASE(PH_R_GATHER);
+        // this tile's head mask is free again; the next tile's tokens go to the other buffer
+        PP_FOR_T(t)
+        if ((uint32_t)t < R / 32u) tt.mask[cb * (R / 32u) + (uint32_t)t] = 0;
+        if (tb + R < vend) scatter_tile(sm, tok, tt, cb ^ 1u, R, tile + 1u, a, nlive, (uint32_t)t);
+        PP_END_T
         // CHASE: follow in-tile sources through shared memory (published pointer jumping, no barrier)
         PP_FOR_W(t)
         {
@@ -1128,7 +1203,7 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
             }
         }
         // STORE: every entry of the warp's 512 bytes is 0x8000|byte in shared memory now; thread t takes
-        // the group it expanded (bytes 16 t .. 16 t + 15 of the tile) and writes it with one 16-byte store
+        // group t (bytes 16 t .. 16 t + 15 of the tile) and writes it with one 16-byte store
         PP_WARP_SPLIT(t)
         {
             const uint32_t q0 = (uint32_t)t * kTileB;
@@ -1174,15 +1249,14 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, const uint32_t *id
             }
         }
         PP_END_W
-        PP_SYNC();  // stores visible to the next tile's gathers; res free again
+        PP_SYNC();  // stores visible to the next tile's gathers; res free again; the next tile's tokens are in place
         PP_PHASE(PH_R_CHASE);
     }
 }
 
 // One window of a Huffman block: GUESS, SYNC, SCAN, EMIT, RESOLVE.
 // s0: window-relative bit of the first symbol; room: output bytes still wanted (> 0).
-PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t *idx, uint32_t mapcap, uint8_t *outp,
-                                uint32_t room)
+PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room)
 {
     const int T = PP_NT;
     uint32_t *cp = reinterpret_cast<uint32_t *>(sm.res);  // checkpoints live in the (idle) resolve tile buffer
@@ -1252,9 +1326,8 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_SYNC();
     // outc -> exclusive sums; keep each thread's own count in nl-free scratch: recomputed from neighbours below
     uint32_t total = block_excl_scan(sm, sm.outc);
-    // live threads: up to the flagged one, cut where the source map or the output is full
+    // live threads: up to the flagged one, cut where the output is full
     const uint32_t a = (uint32_t)((uintptr_t)outp & 15u);
-    const uint32_t capv = mapcap - 16u - a;  // entries usable by this window
     PP_T0_BEGIN
     sm.u[10] = f < (uint32_t)T ? f + 1u : (uint32_t)T;  // nlive
     PP_T0_END
@@ -1262,8 +1335,6 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_FOR_T(t)
     {
         const uint32_t endsum = (t + 1 < T) ? sm.outc[t + 1] : total;  // inclusive sum of thread t
-        // the first thread whose output crosses the map capacity is cut (never thread 0: kMinMapCap)
-        if (t > 0 && (uint32_t)t <= f && endsum > capv) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t);
         // the first thread that completes the wanted output is the last live one
         if ((uint32_t)t <= f && endsum >= room) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t + 1u);
     }
@@ -1296,8 +1367,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
         if ((uint32_t)t < nlive) {
             const uint32_t lim = s0 + (uint32_t)(t + 1) * kSubBits;
             const uint32_t st = sm.start[t];
-            if (t == 0 && a) idx[0] = idx_pack(0, 0, 0);  // group 0 starts at the window's first byte, not at a multiple of 16
-            if (st < lim) nt = decode_seg<1>(sm, st, lim, tok, idx, (uint32_t)T, (uint32_t)t, a + sm.outc[t], a + produced).ntok;
+            if (st < lim) nt = decode_seg<1>(sm, st, lim, tok, rshift, (uint32_t)t, a + sm.outc[t]).ntok;
         }
         sm.ntok[t] = nt;
     }
@@ -1305,7 +1375,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_SYNC();
     PP_PHASE(PH_EMIT);
     // RESOLVE
-    resolve_window(sm, tok, idx, outp, a, produced);
+    resolve_window(sm, tok, outp, a, produced, nlive, rshift);
     PP_PHASE(PH_RESOLVE);
     WindowOut w;
     w.next_bit = next_bit;
@@ -1364,8 +1434,9 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
 #endif
     uint8_t *out = slot + d.lead_len;
     const uint32_t out_len = d.out_len;
-    const uint32_t mapcap = map_cap_for(T);
-    uint32_t *tok = scratch, *idx = scratch + tok_words_for(T);
+    uint32_t *tok = scratch;
+    uint32_t rshift = 4;  // log2 of the resolve tile (16 T bytes; T is a power of two)
+    while ((1u << rshift) < (uint32_t)T * kTileB) rshift++;
     const uint32_t cww = cw_words_for(T);
     // 2. bit cursor: 8*Input - Bits (Core.cs:151-157 inflatePrime semantics)
     uint64_t bit = d.in_bit;
@@ -1410,7 +1481,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
             PP_PHASE(PH_HEADER);
             need_header = false;
         }
-        const WindowOut w = huffman_window(sm, s0, tok, idx, mapcap, out + produced, out_len - produced);
+        const WindowOut w = huffman_window(sm, s0, tok, rshift, out + produced, out_len - produced);
         produced += w.produced;
         bit = base_byte * 8u + w.next_bit;
         // Core.cs:174: the reference throws DATA_ERROR when zlib wants input past the end of fileBuffer

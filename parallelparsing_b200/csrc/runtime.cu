@@ -62,7 +62,7 @@ static int ctx_setup_inflate(pp_ctx *c)
     int t_wide = 1024, t_dense = 512;
     if (const char *e = getenv("PPB200_INFLATE_T")) {
         const int v = atoi(e);
-        if (v >= 32 && v <= 1024 && v % 32 == 0) t_wide = t_dense = v;
+        if (v >= 32 && v <= 1024 && (v & (v - 1)) == 0) t_wide = t_dense = v;  // a power of two: resolve tiles are 16 T bytes
     }
     // dynamic shared memory opt-in: once per context, for the largest CTA size (never per launch)
     CK(inflate_set_max_smem(std::max(t_wide, t_dense)));

@@ -41,7 +41,7 @@ def test_emulated_inflate_block_types(mode):
     assert n >= 2
 
 
-@pytest.mark.parametrize("T,subw", [(32, 31), (96, 31), (256, 31), (512, 31), (1024, 31), (128, 15), (64, 63)])  # 512 / 1024: the shipped CTA sizes
+@pytest.mark.parametrize("T,subw", [(32, 31), (64, 31), (256, 31), (512, 31), (1024, 31), (128, 23), (64, 63)])  # 512 / 1024: the shipped CTA sizes
 def test_emulated_inflate_geometries(T, subw):
     gz = corpus.gz_member(corpus.fastq(12000, fixed=150), 6)
     n, bits = _check(gz, 2000, T, subw)
@@ -50,8 +50,8 @@ def test_emulated_inflate_geometries(T, subw):
 
 def test_emulated_inflate_other_writers():
     _check(corpus.gz_system(corpus.fastq(8000), 6), 2000, 128)
-    _check(corpus.gz_parallel(corpus.fastq(20000, fixed=150), 6, segment=1 << 20), 1000, 96)
-    _check(corpus.gz_member(corpus.fastq(200, lognormal=(10000, 0.5), seed=3), 6), 20, 160, lift=True)
+    _check(corpus.gz_parallel(corpus.fastq(20000, fixed=150), 6, segment=1 << 20), 1000, 64)
+    _check(corpus.gz_member(corpus.fastq(200, lognormal=(10000, 0.5), seed=3), 6), 20, 128, lift=True)
 
 
 def test_emulated_inflate_incompressible_and_runs():
