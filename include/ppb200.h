@@ -151,6 +151,15 @@ int64_t pp_parse(pp_ctx *ctx, const uint8_t *prepend, int64_t prepend_len, const
  * pp_job_upload must then be device-accessible pinned memory (pp_host_alloc, or any buffer passed
  * through pp_host_register); exactly gz_len bytes are readable, nothing behind them is touched. */
 #define PP_JOB_ZEROCOPY 2u
+/* staged mode only: pp_job_upload queues the compressed range in pieces on a copy stream and returns;
+ * pp_job_execute's inflate kernel starts at once and each chunk waits (on the device) only until ITS
+ * bytes are in place, so the PCIe copy hides under the decode (LazyFileReader's read-ahead,
+ * LazyFileReader.cs:77-97, expressed on the device).  `gz` must stay valid until pp_job_download. */
+#define PP_JOB_PIPELINE 4u
+/* the checkpoint windows cross PCIe zlib-compressed (the form IndexIO version 1 stores,
+ * pp_index_serialize_v1) and are inflated on the GPU into place by a pre-pass of the inflate kernel:
+ * ~8 KB instead of 32 KB per checkpoint (the windows are +27 % of the bytes moved at chunk 1000). */
+#define PP_JOB_COMPACT_WINDOWS 8u
 
 typedef struct pp_job_info {
     int32_t first_chunk, n_chunks;
@@ -192,6 +201,15 @@ int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_
                   uint32_t flags, pp_job **out);
 int pp_job_upload(pp_job *job, const uint8_t *gz);
 int pp_job_execute(pp_job *job);
+/*
+ * pp_job_execute that also delivers every chunk's inflated bytes to HOST memory, concatenated in
+ * chunk order (`dst` capacity >= sum of to.Output-from.Output; pinned memory for full speed), while
+ * the decode is still running: the kernel raises a per-chunk flag in mapped host memory and the call
+ * queues that chunk's device-to-host copy at once, so the PCIe download overlaps the kernels — what
+ * a host consumer of FastqRecords (Parsing.cs:41-49 copies every record's bytes) needs.  Returns when
+ * all bytes are in `dst`; follow with pp_job_download for counts / line starts.
+ */
+int pp_job_execute_to_host(pp_job *job, uint8_t *dst, int64_t cap);
 int pp_job_download(pp_job *job);
 int pp_job_info_get(const pp_job *job, pp_job_info *out);
 int pp_job_chunk_info(const pp_job *job, int32_t chunk /* relative to first_chunk */, pp_chunk_info *out);
@@ -241,6 +259,43 @@ void pp_job_free(pp_job *job);
 /* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */
 int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t gz_len, int32_t first_chunk,
                       int32_t n_chunks, uint32_t flags, pp_job **out);
+
+/* ------------------------------------------------------ DecompressAll on several GPUs */
+
+typedef struct pp_multi pp_multi; /* one DecompressAll spread over several GPUs */
+
+typedef struct pp_multi_info {
+    int32_t n_parts;          /* GPUs used (= entries of `devices`)                           */
+    int32_t n_chunks;         /* chunks over all parts                                        */
+    int64_t total_records;    /* records over all parts, canonical order                      */
+    int64_t total_bytes;      /* inflated bytes over all parts                                */
+    int64_t compressed_bytes; /* compressed bytes consumed over all parts                     */
+    int32_t status;           /* first non-zero chunk status in part order, else 0            */
+    int32_t pad;
+} pp_multi_info;
+
+/*
+ * The split the multi-GPU DecompressAll uses, also exported for callers that run one process per
+ * GPU: chunks 0..Count-2 cut into `parts` contiguous ranges of near-equal COMPRESSED size (Input
+ * deltas; LazyFileReader.cs:53-69 defines a chunk's byte range).  Ranges are disjoint, ordered,
+ * cover every chunk, and may be empty when there are fewer chunks than parts.
+ */
+int pp_partition_chunks(const pp_index *ix, int32_t parts, int32_t *first_chunk, int32_t *n_chunks);
+
+/*
+ * DecompressAll (BatchedFASTQ.cs:54-98) over the GPUs `devices[0..n_devices)` of this box: the chunk
+ * list is partitioned with pp_partition_chunks, every GPU gets its own context and host thread and
+ * touches only ITS compressed byte range and ITS checkpoint windows; nothing is exchanged between
+ * GPUs (chunks are independent), the global ordinal of a part's first record is a host-side prefix
+ * sum.  `flags` are pp_job_create's.  Returns 0, a chunk's negative ZResult (the handle is still
+ * returned: per-part jobs tell which chunk), or an API error (no handle).
+ */
+int pp_decompress_all_multi(const int32_t *devices, int32_t n_devices, const pp_index *ix, const uint8_t *gz,
+                            size_t gz_len, uint32_t flags, pp_multi **out);
+int pp_multi_info_get(const pp_multi *m, pp_multi_info *out);
+/* Part `part`: its job (owned by the handle: do not free), its device, the global ordinal of its first record. */
+int pp_multi_part(const pp_multi *m, int32_t part, pp_job **job, int32_t *device, int64_t *record_base);
+void pp_multi_free(pp_multi *m);
 
 #ifdef __cplusplus
 }

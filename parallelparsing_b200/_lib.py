@@ -11,7 +11,7 @@ WINSIZE = 32768
 PP_OK = 0
 PP_E_CUDA, PP_E_NO_DEVICE, PP_E_ARG, PP_E_IO, PP_E_RECORD_TOO_LONG, PP_E_FORMAT = -100, -101, -102, -103, -104, -105
 PP_INDEX_LIFT_RECORD_CAP = 1
-PP_JOB_STRICT, PP_JOB_ZEROCOPY = 1, 2
+PP_JOB_STRICT, PP_JOB_ZEROCOPY, PP_JOB_PIPELINE, PP_JOB_COMPACT_WINDOWS = 1, 2, 4, 8
 
 
 class PPPoint(C.Structure):
@@ -31,6 +31,11 @@ class PPJobInfo(C.Structure):
 class PPChunkInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("prefix_len", C.c_int32), ("inflated", C.c_int64), ("records", C.c_int64),
                 ("record_base", C.c_int64), ("parse_end", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class PPMultiInfo(C.Structure):
+    _fields_ = [("n_parts", C.c_int32), ("n_chunks", C.c_int32), ("total_records", C.c_int64),
+                ("total_bytes", C.c_int64), ("compressed_bytes", C.c_int64), ("status", C.c_int32), ("pad", C.c_int32)]
 
 
 class ZException(Exception):
@@ -73,6 +78,7 @@ SYMBOLS = [
     ("pp_job_create", C.c_int, [_p, _p, _sz, _i32, _i32, _u32, _PP]),
     ("pp_job_upload", C.c_int, [_p, _p]),
     ("pp_job_execute", C.c_int, [_p]),
+    ("pp_job_execute_to_host", C.c_int, [_p, _p, _i64]),
     ("pp_job_download", C.c_int, [_p]),
     ("pp_job_info_get", C.c_int, [_p, C.POINTER(PPJobInfo)]),
     ("pp_job_chunk_info", C.c_int, [_p, _i32, C.POINTER(PPChunkInfo)]),
@@ -85,6 +91,11 @@ SYMBOLS = [
     ("pp_job_digests", C.c_int, [_p, _p, _p]),
     ("pp_job_free", None, [_p]),
     ("pp_decompress_all", C.c_int, [_p, _p, _p, _sz, _i32, _i32, _u32, _PP]),
+    ("pp_partition_chunks", C.c_int, [_p, _i32, _p, _p]),
+    ("pp_decompress_all_multi", C.c_int, [_p, _i32, _p, _p, _sz, _u32, _PP]),
+    ("pp_multi_info_get", C.c_int, [_p, C.POINTER(PPMultiInfo)]),
+    ("pp_multi_part", C.c_int, [_p, _i32, _PP, C.POINTER(_i32), C.POINTER(_i64)]),
+    ("pp_multi_free", None, [_p]),
 ]
 
 

@@ -21,6 +21,7 @@ from . import _lib
 from ._lib import WINSIZE, ZException, check, lib
 
 __all__ = ["Device", "Index", "Point", "IndexIO", "Core", "Parsing", "BatchedFASTQ", "PairedFASTQ", "FastqRecord", "Job",
+           "MultiGpuDecompressAll", "partition_chunks",
            "ZException", "pinned_copy"]
 
 
@@ -239,17 +240,19 @@ class Parsing:
 class Job:
     """A DecompressAll plan over chunks [first, first+n) (pp_job)."""
 
-    def __init__(self, device: Device, index: Index, gz_len: int, first=0, n=-1, strict=False, zero_copy=False):
-        flags = (_lib.PP_JOB_STRICT if strict else 0) | (_lib.PP_JOB_ZEROCOPY if zero_copy else 0)
+    def __init__(self, device: Device, index: Index, gz_len: int, first=0, n=-1, strict=False, zero_copy=False,
+                 pipeline=False, compact_windows=False):
+        flags = ((_lib.PP_JOB_STRICT if strict else 0) | (_lib.PP_JOB_ZEROCOPY if zero_copy else 0) |
+                 (_lib.PP_JOB_PIPELINE if pipeline else 0) | (_lib.PP_JOB_COMPACT_WINDOWS if compact_windows else 0))
         h = C.c_void_p()
         check(lib().pp_job_create(device.h, index.h, gz_len, first, n, flags, C.byref(h)), "pp_job_create")
         self.h = h
         self.device, self.index = device, index  # keep alive
 
     def free(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and getattr(self, "_owned", True):
             lib().pp_job_free(self.h)
-            self.h = None
+        self.h = None
 
     __del__ = free
 
@@ -258,6 +261,10 @@ class Job:
 
     def execute(self):
         check(lib().pp_job_execute(self.h), "pp_job_execute")
+
+    def execute_to_host(self, dst_ptr, cap):
+        """execute + every chunk's inflated bytes streamed to host memory while the decode runs."""
+        check(lib().pp_job_execute_to_host(self.h, dst_ptr, cap), "pp_job_execute_to_host")
 
     def download(self):
         check(lib().pp_job_download(self.h), "pp_job_download")
@@ -316,6 +323,58 @@ class Job:
         out = np.zeros(max(n, 1), np.uint8)
         check(lib().pp_job_fetch_bytes(self.h, _ptr(out), out.size), "fetch_bytes")
         return out[:n]
+
+
+def partition_chunks(index: Index, parts: int):
+    """pp_partition_chunks: [(first_chunk, n_chunks)] per part — contiguous ranges of near-equal compressed size."""
+    f = (C.c_int32 * parts)()
+    n = (C.c_int32 * parts)()
+    check(lib().pp_partition_chunks(index.h, parts, f, n), "pp_partition_chunks")
+    return [(int(f[i]), int(n[i])) for i in range(parts)]
+
+
+class MultiGpuDecompressAll:
+    """DecompressAll over several GPUs of one box (pp_decompress_all_multi): the chunk list is cut into
+    contiguous ranges of near-equal compressed size, one per GPU; every GPU reads only its byte range.
+    `gz` must stay alive (and, for zero_copy, be pinned) while the object lives."""
+
+    def __init__(self, devices, index: Index, gz, gz_len=None, strict=False, zero_copy=False, pipeline=False,
+                 compact_windows=False):
+        flags = ((_lib.PP_JOB_STRICT if strict else 0) | (_lib.PP_JOB_ZEROCOPY if zero_copy else 0) |
+                 (_lib.PP_JOB_PIPELINE if pipeline else 0) | (_lib.PP_JOB_COMPACT_WINDOWS if compact_windows else 0))
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        if isinstance(gz, np.ndarray):
+            ptr, n = _ptr(gz), gz.size
+        else:
+            ptr, n = gz, gz_len
+        rc = lib().pp_decompress_all_multi(devs, len(devices), index.h, ptr, n, flags, C.byref(h))
+        if not h:
+            check(rc, "pp_decompress_all_multi")
+        self.h, self.status = h, rc
+        self._keep = (index, gz)
+
+    def info(self):
+        i = _lib.PPMultiInfo()
+        check(lib().pp_multi_info_get(self.h, C.byref(i)))
+        return i
+
+    def part(self, r):
+        """(Job view, device ordinal, global ordinal of the part's first record)."""
+        jh, dev, base = C.c_void_p(), C.c_int32(), C.c_int64()
+        check(lib().pp_multi_part(self.h, r, C.byref(jh), C.byref(dev), C.byref(base)), "pp_multi_part")
+        j = Job.__new__(Job)
+        j.h = jh
+        j._owned = False   # the multi handle frees it
+        j._keep = self
+        return j, dev.value, base.value
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().pp_multi_free(self.h)
+            self.h = None
+
+    __del__ = free
 
 
 class BatchedFASTQ:

@@ -11,22 +11,73 @@
 
 #include <zlib.h>
 
+#include <atomic>
 #include <cstdio>
 #include <memory>
 #include <new>
+#include <thread>
 
 static const int32_t kChunk = 16384;  // Common/Constants.cs:12
 
 pp_index::~pp_index()
 {
+    pp_internal_unpin_cwin(this);
     if (windows) {
         pp_internal_unpin_index(this);
         free(windows);
     }
 }
 
+// zlib-compress every window (level 6, the streams IndexIO version 1 stores) on all host cores.
+bool index_build_compact_windows(const pp_index *ix)
+{
+    std::lock_guard<std::mutex> lk(ix->cw_mu);
+    const int32_t n = ix->count();
+    if (ix->cwin_points == n) return true;
+    pp_internal_unpin_cwin(ix);
+    try {
+        const size_t bound = (compressBound(PP_WINSIZE) + 15) & ~(size_t)15;
+        std::vector<uint8_t> tmp((size_t)n * bound);
+        std::vector<uint32_t> len((size_t)n, 0);
+        std::atomic<int32_t> next{0};
+        std::atomic<bool> ok{true};
+        auto work = [&]() {
+            for (;;) {
+                const int32_t i = next.fetch_add(1);
+                if (i >= n) break;
+                uLongf m = (uLongf)bound;
+                if (compress2(tmp.data() + (size_t)i * bound, &m, ix->window(i), PP_WINSIZE, 6) != Z_OK) ok = false;
+                len[(size_t)i] = (uint32_t)m;
+            }
+        };
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt ? (nt > 32 ? 32 : nt) : 1;
+        if ((unsigned)n < nt) nt = n > 0 ? (unsigned)n : 1;
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (!ok) return false;
+        ix->cwin_off.assign((size_t)n + 1, 0);
+        uint64_t acc = 0;
+        for (int32_t i = 0; i < n; i++) {
+            ix->cwin_off[(size_t)i] = acc;
+            acc += ((uint64_t)len[(size_t)i] + 15u) & ~(uint64_t)15;
+        }
+        ix->cwin_off[(size_t)n] = acc;
+        ix->cwin.assign((size_t)acc + 4096, 0);
+        for (int32_t i = 0; i < n; i++)
+            memcpy(ix->cwin.data() + ix->cwin_off[(size_t)i], tmp.data() + (size_t)i * bound, len[(size_t)i]);
+        ix->cwin_points = n;
+    } catch (...) {
+        return false;
+    }
+    return true;
+}
+
 uint8_t *pp_index::append_window()
 {
+    cwin_points = -1;  // the compact windows no longer cover every point
     size_t n = output.size();  // caller has already pushed the scalar fields
     if (n > win_cap) {
         size_t cap = win_cap ? win_cap * 2 : 64;

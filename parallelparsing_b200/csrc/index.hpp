@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "ppb200.h"
@@ -23,6 +24,14 @@ struct pp_index {
     int32_t chunk_max_bytes = 0;   // Index.ChunkMaxBytes
     mutable void *pinned_base = nullptr;  // set by the runtime when `windows` is cudaHostRegister'ed
     mutable size_t pinned_bytes = 0;
+    // Compact form of the windows (zlib streams, as IndexIO version 1 stores them), built on first
+    // use by a job with PP_JOB_COMPACT_WINDOWS: what crosses PCIe instead of 32 KB per checkpoint.
+    // cwin_off has count+1 entries; every stream starts 16-byte aligned.
+    mutable std::mutex cw_mu;
+    mutable std::vector<uint8_t> cwin;
+    mutable std::vector<uint64_t> cwin_off;
+    mutable int32_t cwin_points = -1;      // points covered by cwin (-1: not built)
+    mutable void *cwin_pinned = nullptr;   // set by the runtime when cwin is cudaHostRegister'ed
 
     int32_t count() const { return (int32_t)output.size(); }
     const uint8_t *window(int32_t i) const { return windows + (size_t)i * PP_WINSIZE; }
@@ -34,3 +43,6 @@ struct pp_index {
 // Runtime hook: called before `windows` is reallocated or freed so a pinned
 // registration can be dropped (implemented in runtime.cu).
 extern "C" void pp_internal_unpin_index(const pp_index *ix);
+extern "C" void pp_internal_unpin_cwin(const pp_index *ix);
+// Build (once; thread safe) the compact windows.  Returns false when out of memory.
+bool index_build_compact_windows(const pp_index *ix);

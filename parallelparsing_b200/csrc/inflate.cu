@@ -10,7 +10,7 @@ namespace pp {
 __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
     pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
                       uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
-                      uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift)
+                      uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy)
 {
     extern __shared__ __align__(128) uint8_t pp_smem_raw[];
     ppinf::Sm sm;
@@ -32,7 +32,43 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
         d.in_bit += 8ull * comp_shift;
         d.in_limit += comp_shift;
+        if (sy.avail) {
+            // pipelined upload: the compressed bytes arrive on a copy stream while this kernel runs; the
+            // host publishes how many bytes are in place.  Chunks are handed out in file order, so this
+            // waits only when the decode has caught up with the PCIe copy.  Bounded (~4 s): a copy that
+            // never arrives must not hang the GPU.
+            if (threadIdx.x == 0) {
+                // + one staged window: the decoder looks that far ahead speculatively; the host sets the
+                // mark to "everything" after the last piece, so the tail never waits for bytes that do not exist
+                const unsigned long long need = d.in_limit - comp_shift + 4ull * ppinf::cw_words_for((int)blockDim.x);
+                const long long t0 = clock64();
+                unsigned ok = 1;
+                while (*sy.avail < need) {
+                    __nanosleep(200);
+                    if (clock64() - t0 > 8000000000LL) { ok = 0; break; }
+                }
+                sm.u[17] = ok;
+            }
+            __syncthreads();
+            const bool ok = sm.u[17] != 0;
+            __syncthreads();
+            if (!ok) {
+                if (threadIdx.x == 0) {
+                    results[k].status = -100;
+                    results[k].produced = 0;
+                    results[k].newlines = 0;
+                    results[k].min_byte = 1;
+                    results[k].end_bit = 0;
+                }
+                continue;
+            }
+        }
         ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase);
+        if (sy.done && threadIdx.x == 0) {
+            // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
+            __threadfence_system();
+            *((volatile uint32_t *)sy.done + k) = 1u;
+        }
     }
 }
 
@@ -70,7 +106,8 @@ size_t inflate_scratch_bytes(int threads, int grid)
 }
 
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st)
+                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st,
+                           InflateSync sy)
 {
     if (n <= 0) return cudaSuccess;
     // TMA bulk copies need 16-byte aligned global addresses: align the base down and shift the bit cursors
@@ -82,7 +119,7 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);
     const int grid = n < cfg.grid ? n : cfg.grid;
     pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
-                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift);
+                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy);
     return cudaGetLastError();
 }
 

@@ -155,6 +155,7 @@ struct ChunkDesc {
     uint32_t prefix_len;  // |from.offset| (used by the parse stage)
     uint32_t prefix_nl;   // '\n' count inside from.offset (host counted)
 };
+constexpr uint64_t kLeadInPlace = ~0ull;
 struct ChunkResult {
     int32_t status;     // 0 or negative ZResult
     uint32_t produced;  // bytes written (Core.cs:191)
@@ -742,6 +743,9 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
     uint32_t cnt = 64u - sh;
     wp += 2;
     uint32_t out = 0, flag = F_NONE, k = 0;
+    // One loop body for literals and matches (the lanes of a warp are in different kinds of symbol
+    // all the time: a branch per kind makes every iteration pay for both): the distance lookup is
+    // done for a literal too, on whatever bits follow, and consumes nothing.
     for (;;) {
         if (wp * 32u - cnt >= limit) break;
         if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
@@ -749,44 +753,33 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
         uint32_t e = sm.lit[lo & ((1u << kRootL) - 1u)];
         if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
         const uint32_t kind = e_kind(e), tot = e_tot(e);
-        if (kind == K_LIT) {
-            if (WRITE) row[k++] = tok_pack(e_val(e), o + out, rshift);
-            out++;
-            buf >>= tot;
-            cnt -= tot;
-            continue;
-        }
-        if (kind == K_BASE) {
-            const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
-            buf >>= tot;
-            cnt -= tot;
-            if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
-            lo = (uint32_t)buf;
-            uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
-            if (e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
-            if (e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
-            const uint32_t dtot = e_tot(d);
-            const uint32_t dist = e_val(d) + ((lo & ~(0xffffffffu << dtot)) >> e_cl(d));
-            buf >>= dtot;
-            cnt -= dtot;
-            // dist <= 32768 <= lead_len always, so "distance too far back" cannot occur:
-            // the reference primes a full 32 KB dictionary (Core.cs:158)
-            if (WRITE) {
-                const uint32_t p0 = o + out, p1 = p0 + len - 1u;
-                row[k++] = tok_pack(dist - 1u, p0, rshift);
-                if ((p0 ^ p1) >> rshift) row[k++] = tok_pack(dist - 1u, (p1 >> rshift) << rshift, rshift);
-            }
-            out += len;
-            continue;
-        }
-        if (kind == K_EOB) {
-            buf >>= tot;
-            cnt -= tot;
-            flag = F_EOB;
+        if (kind > K_BASE) {  // end of block, or an invalid literal/length code
+            if (kind == K_EOB) { buf >>= tot; cnt -= tot; flag = F_EOB; }
+            else flag = F_BAD;
             break;
         }
-        flag = F_BAD;  // invalid literal/length code
-        break;
+        const bool ism = kind == K_BASE;
+        const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));  // (a literal: its entry, unused)
+        buf >>= tot;
+        cnt -= tot;
+        if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+        lo = (uint32_t)buf;
+        uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
+        if (ism && e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
+        if (ism && e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
+        const uint32_t dtot = ism ? e_tot(d) : 0u;
+        // dist <= 32768 <= lead_len always, so "distance too far back" cannot occur:
+        // the reference primes a full 32 KB dictionary (Core.cs:158)
+        const uint32_t dist = e_val(d) + ((lo & ~(0xffffffffu << dtot)) >> e_cl(d));
+        buf >>= dtot;
+        cnt -= dtot;
+        const uint32_t n = ism ? len : 1u;
+        if (WRITE) {
+            const uint32_t p0 = o + out, p1 = p0 + n - 1u;
+            row[k++] = tok_pack(ism ? dist - 1u : e_val(e), p0, rshift);
+            if ((p0 ^ p1) >> rshift) row[k++] = tok_pack(dist - 1u, (p1 >> rshift) << rshift, rshift);  // only a match crosses
+        }
+        out += n;
     }
     Seg r;
     r.end = wp * 32u - cnt;
@@ -840,35 +833,25 @@ PP_DEV Seg decode_count(const Sm &sm, uint32_t start, uint32_t limit, uint32_t b
         uint32_t e = sm.lit[lo & ((1u << kRootL) - 1u)];
         if (e_kind(e) == K_SUB) e = sm.lit[e_val(e) + ((lo >> kRootL) & ((1u << e_sub(e)) - 1u))];
         const uint32_t kind = e_kind(e), tot = e_tot(e);
-        if (kind == K_LIT) {
-            out++;
-            buf >>= tot;
-            cnt -= tot;
-            continue;
-        }
-        if (kind == K_BASE) {
-            const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
-            buf >>= tot;
-            cnt -= tot;
-            if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
-            lo = (uint32_t)buf;
-            uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
-            if (e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
-            if (e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
-            const uint32_t dtot = e_tot(d);
-            buf >>= dtot;
-            cnt -= dtot;
-            out += len;
-            continue;
-        }
-        if (kind == K_EOB) {
-            buf >>= tot;
-            cnt -= tot;
-            flag = F_EOB;
+        if (kind > K_BASE) {  // end of block, or an invalid literal/length code
+            if (kind == K_EOB) { buf >>= tot; cnt -= tot; flag = F_EOB; }
+            else flag = F_BAD;
             break;
         }
-        flag = F_BAD;  // invalid literal/length code
-        break;
+        // one body for literals and matches (see decode_seg)
+        const bool ism = kind == K_BASE;
+        const uint32_t len = e_val(e) + ((lo & ~(0xffffffffu << tot)) >> e_cl(e));
+        buf >>= tot;
+        cnt -= tot;
+        if (cnt < 32u) { buf |= (uint64_t)cw[wp] << cnt; cnt += 32u; wp++; }
+        lo = (uint32_t)buf;
+        uint32_t d = sm.dist[lo & ((1u << kRootD) - 1u)];
+        if (ism && e_kind(d) == K_SUB) d = sm.dist[e_val(d) + ((lo >> kRootD) & ((1u << e_sub(d)) - 1u))];
+        if (ism && e_kind(d) != K_BASE) { flag = F_BAD; break; }  // invalid distance code
+        const uint32_t dtot = ism ? e_tot(d) : 0u;
+        buf >>= dtot;
+        cnt -= dtot;
+        out += ism ? len : 1u;
     }
     Seg r;
     if (reused) {
@@ -1007,19 +990,25 @@ PP_HD uint32_t res_entries_for(int T) { return (uint32_t)T * kTileB + (uint32_t)
 // Shared-memory staging of a tile's tokens (lives in the compressed-window buffer, idle during
 // RESOLVE): two buffers (the tile being expanded, the tile being scattered), each R u16 entries
 // indexed by tile position + R/32 head-mask words.
-static_assert(kSubW * 4 >= 2 * 2 * kTileB + 2 * kTileB / 8, "the tile token staging (68 bytes per thread) must fit the compressed-window buffer");
+static_assert(kSubW * 4 >= 2 * 2 * kTileB + 2 * kTileB / 8 + kTileB / 8 + 32,
+              "the tile token staging (entries, head masks, word heads, row map: 102 bytes per thread) must fit the compressed-window buffer");
 struct TileTok {
-    uint16_t *ent;   // [2][R]
-    uint32_t *mask;  // [2][R/32]
-    uint32_t *kcur;  // [T] per row: tokens consumed by earlier tiles
+    uint16_t *ent;     // [2][R]
+    uint32_t *mask;    // [2][R/32]
+    uint32_t *kcur;    // [T] per row: tokens consumed by earlier tiles
+    uint32_t *wprev;   // [R/32] per mask word: position of the last head BEFORE the word (EXPAND scratch)
+    uint16_t *tfirst;  // [max_tiles_for(T)+2] per tile: first row that starts in it or later (the window's row map)
 };
+// tiles one window may produce before it is cut short (its row map must fit the staging buffer)
+PP_HD uint32_t max_tiles_for(int T) { return 16u * (uint32_t)T; }
 
 // One row's tokens of tile `tile` -> ent / mask.  Device: the lanes of the calling warp take
-// consecutive tokens.  Emulation: one thread walks the row.
+// consecutive tokens, three loads in flight per lane.  Emulation: one thread walks the row.
 PP_DEV void scatter_row(const Sm &sm, const uint32_t *tok, const TileTok &tt, uint32_t buf, uint32_t R, uint32_t tile,
                         uint32_t row, uint32_t lane)
 {
-    const uint32_t k0 = tt.kcur[row], nt = sm.ntok[row], tag = tile & 3u;
+    const uint32_t nt = sm.ntok[row], tag = tile & 3u;
+    uint32_t k0 = tt.kcur[row];
     const uint32_t *rp = tok + row * (uint32_t)kTokRows;
     uint16_t *ent = tt.ent + buf * R;
     uint32_t *mask = tt.mask + buf * (R / 32u);
@@ -1035,41 +1024,39 @@ PP_DEV void scatter_row(const Sm &sm, const uint32_t *tok, const TileTok &tt, ui
     }
     tt.kcur[row] = k;
 #else
-    uint32_t cnt = 0;
-    for (uint32_t k = k0 + lane; k < nt; k += 32u) {
-        const uint32_t tv = rp[k];
-        if ((tv >> 30) != tag) break;
-        const uint32_t pos = (tv >> 16) & 0x3fffu;
-        ent[pos] = (uint16_t)tv;
-        atomicOr(&mask[pos >> 5], 1u << (pos & 31u));
-        cnt++;
+    for (;;) {
+        // a row's tokens of one tile are a run starting at the cursor: lane l looks at tokens k0+l, k0+l+32, k0+l+64
+        uint32_t tv[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const uint32_t k = k0 + lane + 32u * (uint32_t)u;
+            tv[u] = k < nt ? rp[k] : ((tag ^ 1u) << 30);  // past the row's end: a tag that never matches
+        }
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            if ((tv[u] >> 30) == tag) {
+                const uint32_t pos = (tv[u] >> 16) & 0x3fffu;
+                ent[pos] = (uint16_t)tv[u];
+                atomicOr(&mask[pos >> 5], 1u << (pos & 31u));
+                cnt++;
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);  // the run's length is the cursor's advance
+        k0 += cnt;
+        if (cnt < 96u) break;
     }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);  // the tile's tokens are a run: their count is the cursor's advance
-    if (lane == 0u) tt.kcur[row] = k0 + cnt;
+    if (lane == 0u) tt.kcur[row] = k0;
 #endif
 }
 
-// Rows whose output intersects virtual range [tb, tb + R): row r starts at a + outc[r] and ends
-// where the next live row starts (the last live row has no end).  Warp w takes rows lo+w, lo+w+nw, ...
+// Rows with tokens in tile `tile`: those that START in it — [tfirst[tile], tfirst[tile+1]) — and the
+// one before them, which may reach into it.  Warp w takes rows lo+w, lo+w+nw, ...
 PP_DEV void scatter_tile(const Sm &sm, const uint32_t *tok, const TileTok &tt, uint32_t buf, uint32_t R, uint32_t tile,
-                         uint32_t a, uint32_t nlive, uint32_t t)
+                         uint32_t t)
 {
-    const uint32_t tb = tile * R, te = tb + R;
-    // hi: first row starting at or after te
-    uint32_t lo = 0, hi = nlive;
-    {
-        uint32_t l = 0, h = nlive;
-        while (l < h) { const uint32_t m = (l + h) >> 1; if (a + sm.outc[m] < te) l = m + 1u; else h = m; }
-        hi = l;
-        // lo: first row whose end (= start of row+1, or infinity for the last live row) is past tb
-        l = 0; h = hi;
-        while (l < h) {
-            const uint32_t m = (l + h) >> 1;
-            const bool ends_after = (m + 1u >= nlive) || (a + sm.outc[m + 1u] > tb);
-            if (!ends_after) l = m + 1u; else h = m;
-        }
-        lo = l;
-    }
+    const uint32_t f0 = tt.tfirst[tile], hi = tt.tfirst[tile + 1u];
+    const uint32_t lo = f0 ? f0 - 1u : 0u;
     const uint32_t warp = t >> 5, lane = t & 31u, nw = ((uint32_t)PP_NT + 31u) >> 5;
 #ifdef PP_HOST_EMU
     if (lane != 0u) return;
@@ -1078,17 +1065,30 @@ PP_DEV void scatter_tile(const Sm &sm, const uint32_t *tok, const TileTok &tt, u
 }
 
 // EXPAND of one tile for thread t (see RESOLVE above).  FULL: every byte of the tile is a valid
-// output byte (all tiles but the first and the last of a window).
+// output byte (all tiles but the first and the last of a window).  wprev[w] = position of the last
+// head before mask word w (expand_prev, run by the same warp just before).
+PP_DEV void expand_prev(const uint32_t *mask, uint32_t *wprev, uint32_t t)
+{
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    if (lane < (uint32_t)kTileB) {
+        const uint32_t w = warp * (uint32_t)kTileB + lane;
+        uint32_t off = w, m = 0;
+        while (m == 0u && off > 0u) m = mask[--off];
+        wprev[w] = m ? off * 32u + 31u - clz32(m) : 0u;  // (no head before a valid byte: cannot happen for consistent tokens)
+    }
+}
+
 template <bool FULL>
-PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask, const uint8_t *vbase, uint32_t tb,
-                        uint32_t a, uint32_t vend, int32_t near_lo, uint32_t t)
+PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask, const uint32_t *wprev,
+                        const uint8_t *vbase, uint32_t tb, uint32_t a, uint32_t vend, int32_t near_lo, uint32_t t)
 {
     const uint32_t lane = t & 31u, warp = t >> 5;
     const uint32_t qb = warp * (32u * kTileB) + lane;       // this lane's first byte; the others follow 32 apart
     const uint32_t below = 0xffffffffu >> (31u - lane);     // bits 0..lane
     const int32_t safe = near_lo - 1;                       // the byte just before the tile/window: final, inside the slot
     const SAddr ent_s = saddr(ent), res_s = saddr(sm.res) + 2u * qb;
-    const SAddr mask_s = saddr(mask), mask_w = mask_s + 4u * (warp * (uint32_t)kTileB);  // the warp's 16 mask words
+    const SAddr mask_w = saddr(mask) + 4u * (warp * (uint32_t)kTileB);   // the warp's 16 mask words
+    const SAddr prev_w = saddr(wprev) + 4u * (warp * (uint32_t)kTileB);
     const int32_t vq = (int32_t)(tb + qb);                  // virtual index of the lane's first byte
 #pragma unroll
     for (int h = 0; h < kTileB; h += 8) {
@@ -1099,32 +1099,30 @@ PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask,
         for (int j = 0; j < 8; j++) {
             const int s = h + j;                            // step: byte qb + 32 s lies in mask word warp * 16 + s
             e[j] = 0x8000u;                                 // bytes outside the window: harmless literals
-            sv[j] = 0;
+            sv[j] = safe;
             const uint32_t v = (uint32_t)vq + 32u * (uint32_t)s;
             if (FULL || (v >= a && v < vend)) {
-                uint32_t m = lds_u32(mask_w, 4u * (uint32_t)s) & below;
-                uint32_t hp32 = 32u * (warp * (uint32_t)kTileB + (uint32_t)s);  // first position of the word the head is in
-                if (m == 0u) {                              // the token started in an earlier word (11 % of the bytes)
-                    uint32_t off = 4u * (warp * (uint32_t)kTileB + (uint32_t)s);
-                    while (m == 0u && off > 0u) { off -= 4u; m = lds_u32(mask_s, off); }
-                    if (m == 0u) m = 1u;                    // no head before a valid byte: cannot happen for consistent tokens
-                    hp32 = off * 8u;
-                }
-                const uint32_t hp = hp32 + 31u - clz32(m);
+                const uint32_t m = lds_u32(mask_w, 4u * (uint32_t)s) & below;
+                // the byte's token: the last head at or before it — in this word, else the last one before the word
+                const uint32_t hp = m ? 32u * (warp * (uint32_t)kTileB + (uint32_t)s) + 31u - clz32(m)
+                                      : lds_u32(prev_w, 4u * (uint32_t)s);
                 uint32_t x = lds_u16(ent_s, 2u * hp);
                 const uint32_t i = qb + 32u * (uint32_t)s - hp;
-                if (i > x) {                                // a match (x < 0x8000 <= ... never true for a literal: i < 512) whose
+                if (i > x) {                                // a match (never true for a literal: x >= 0x8000 > i) whose
                     const uint32_t dist = x + 1u;           // offset reached its distance: overlapping run, take the same byte
                     x = dist * (div_small(i, dist) + 1u) - 1u;  // one or more periods earlier, in front of the match
                 }
-                sv[j] = (int32_t)v - (int32_t)x - 1;        // virtual index of the source (meaningless for a literal)
+                // virtual index of the source; for a literal (0x8000 | byte) a harmless address at most 256
+                // bytes back (there is always that much in front of an output: a 32 KB window, or the
+                // spare bytes the runtime keeps in front of the first slot)
+                sv[j] = (int32_t)v - (int32_t)(x & 0x7fffu) - 1;
                 e[j] = x;
             }
         }
-        // unconditional loads (lanes with nothing to fetch read one shared, always valid byte), so that
-        // the eight loads of a batch are in flight together instead of one per branch
+        // unconditional loads (a source inside the tile reads the byte just before the tile instead), so
+        // that the eight loads of a batch are in flight together instead of one per branch
 #pragma unroll
-        for (int j = 0; j < 8; j++) b[j] = vbase[(!(e[j] & 0x8000u) && sv[j] < near_lo) ? sv[j] : safe];
+        for (int j = 0; j < 8; j++) b[j] = vbase[sv[j] < safe ? sv[j] : safe];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             uint32_t o = e[j];
@@ -1146,14 +1144,44 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uin
     tt.ent = reinterpret_cast<uint16_t *>(sm.cw);      // cw is restaged for every window anyway
     tt.mask = sm.cw + R;                               // 2 R u16 = R words
     tt.kcur = sm.ns;                                   // idle outside SYNC
-    (void)rshift;
+    tt.wprev = tt.mask + 2u * (R / 32u);               // R/32 words
+    tt.tfirst = reinterpret_cast<uint16_t *>(tt.wprev + R / 32u);  // max_tiles_for(T) + 2 u16
+    const uint32_t ntiles = (vend + R - 1u) >> rshift;
+    // the window's row map: tfirst[i] = first row that starts in tile i or later
     PP_FOR_T(t)
     for (uint32_t i = (uint32_t)t; i < 2u * (R / 32u); i += (uint32_t)T) tt.mask[i] = 0;
+    for (uint32_t i = (uint32_t)t; i <= ntiles + 1u; i += (uint32_t)T) tt.tfirst[i] = (uint16_t)nlive;
     tt.kcur[t] = 0;
     PP_END_T
     PP_SYNC();
     PP_FOR_T(t)
-    scatter_tile(sm, tok, tt, 0, R, 0, a, nlive, (uint32_t)t);
+    if ((uint32_t)t < nlive && (t == 0 || sm.outc[t] != sm.outc[t - 1])) {  // (an empty row starts where the next one does)
+        const uint32_t ti = (a + sm.outc[t]) >> rshift;
+        if (ti <= ntiles) {
+            // 16-bit atomic min through the containing word
+            uint32_t *w32 = reinterpret_cast<uint32_t *>(tt.tfirst) + (ti >> 1);
+            const uint32_t sh = (ti & 1u) * 16u;
+#ifdef PP_HOST_EMU
+            if ((uint32_t)t < ((*w32 >> sh) & 0xffffu)) *w32 = (*w32 & ~(0xffffu << sh)) | ((uint32_t)t << sh);
+#else
+            uint32_t old = *w32;
+            while ((uint32_t)t < ((old >> sh) & 0xffffu)) {
+                const uint32_t assumed = old;
+                old = atomicCAS(w32, assumed, (assumed & ~(0xffffu << sh)) | ((uint32_t)t << sh));
+                if (old == assumed) break;
+            }
+#endif
+        }
+    }
+    PP_END_T
+    PP_SYNC();
+    PP_T0_BEGIN
+    for (uint32_t i = ntiles + 1u; i-- > 0u;)  // suffix minimum: a tile no row starts in inherits the next one's
+        if (tt.tfirst[i] > tt.tfirst[i + 1u]) tt.tfirst[i] = tt.tfirst[i + 1u];
+    PP_T0_END
+    PP_SYNC();
+    PP_FOR_T(t)
+    scatter_tile(sm, tok, tt, 0, R, 0, (uint32_t)t);
     PP_END_T
     PP_SYNC();
     uint32_t tile = 0;
@@ -1161,20 +1189,22 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uin
         const uint32_t cb = tile & 1u;
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
         // EXPAND: the byte's token is the last head at or before it
-        PP_FOR_T(t)
+        PP_FOR_W(t)
+        expand_prev(tt.mask + cb * (R / 32u), tt.wprev, (uint32_t)t);
+        PP_WARP_SPLIT(t)
         {
             const uint16_t *ent = tt.ent + cb * R;
             const uint32_t *mask = tt.mask + cb * (R / 32u);
-            if (tb >= a && tb + R <= vend) expand_tile<true>(sm, ent, mask, vbase, tb, a, vend, near_lo, (uint32_t)t);
-            else expand_tile<false>(sm, ent, mask, vbase, tb, a, vend, near_lo, (uint32_t)t);
+            if (tb >= a && tb + R <= vend) expand_tile<true>(sm, ent, mask, tt.wprev, vbase, tb, a, vend, near_lo, (uint32_t)t);
+            else expand_tile<false>(sm, ent, mask, tt.wprev, vbase, tb, a, vend, near_lo, (uint32_t)t);
         }
-        PP_END_T
+        PP_END_W
         PP_SYNC();
         PP_PHASE(PH_R_GATHER);
         // this tile's head mask is free again; the next tile's tokens go to the other buffer
         PP_FOR_T(t)
         if ((uint32_t)t < R / 32u) tt.mask[cb * (R / 32u) + (uint32_t)t] = 0;
-        if (tb + R < vend) scatter_tile(sm, tok, tt, cb ^ 1u, R, tile + 1u, a, nlive, (uint32_t)t);
+        if (tb + R < vend) scatter_tile(sm, tok, tt, cb ^ 1u, R, tile + 1u, (uint32_t)t);
         PP_END_T
         // CHASE: follow in-tile sources through shared memory (published pointer jumping, no barrier)
         PP_FOR_W(t)
@@ -1326,8 +1356,10 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_SYNC();
     // outc -> exclusive sums; keep each thread's own count in nl-free scratch: recomputed from neighbours below
     uint32_t total = block_excl_scan(sm, sm.outc);
-    // live threads: up to the flagged one, cut where the output is full
+    // live threads: up to the flagged one, cut where the output is full or the window would need more
+    // resolve tiles than its row map holds
     const uint32_t a = (uint32_t)((uintptr_t)outp & 15u);
+    const uint32_t capv = (max_tiles_for(T) - 1u) * ((uint32_t)T * kTileB) - 16u;
     PP_T0_BEGIN
     sm.u[10] = f < (uint32_t)T ? f + 1u : (uint32_t)T;  // nlive
     PP_T0_END
@@ -1335,6 +1367,9 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_FOR_T(t)
     {
         const uint32_t endsum = (t + 1 < T) ? sm.outc[t + 1] : total;  // inclusive sum of thread t
+        // the first thread whose output crosses the capacity is cut (never thread 0: one sub-sequence
+        // emits < 128 Ki bytes, the capacity is 256 T^2 >= 256 Ki)
+        if (t > 0 && (uint32_t)t <= f && endsum > capv) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t);
         // the first thread that completes the wanted output is the last live one
         if ((uint32_t)t <= f && endsum >= room) PP_ATOMIC_MIN(&sm.u[10], (uint32_t)t + 1u);
     }
@@ -1415,9 +1450,11 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     uint8_t *slot = slots + d.slot_off;
     // 1. history: copy the checkpoint window (Core.cs:158 inflateSetDictionary) in front of the output
     {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(lead_src + d.lead_src);
+        // (lead_src == kLeadInPlace: the history is already there — the checkpoint windows were inflated
+        // straight into the slots by a pre-pass of this same kernel)
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(lead_src + (d.lead_src == kLeadInPlace ? 0 : d.lead_src));
         uint4 *d4 = reinterpret_cast<uint4 *>(slot);
-        const uint32_t n4 = d.lead_len / 16u;
+        const uint32_t n4 = d.lead_src == kLeadInPlace ? 0u : d.lead_len / 16u;
         PP_FOR_T(t)
         for (uint32_t i = (uint32_t)t; i < n4; i += (uint32_t)T) d4[i] = s4[i];
         sm.nl[t] = 0;

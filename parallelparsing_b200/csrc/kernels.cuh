@@ -46,11 +46,17 @@ struct InflateLaunch {
     uint32_t *map = nullptr; // token/index scratch: grid x scratch_words_for(threads) words
     int *counter = nullptr;  // chunk counter the CTAs pull work from
 };
+// Optional host <-> kernel hand-shakes of the inflate kernel (both may be null).
+struct InflateSync {
+    const volatile unsigned long long *avail = nullptr;  // device memory: compressed bytes already copied in (pipelined upload)
+    uint32_t *done = nullptr;                            // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
+};
 int inflate_max_ctas_per_sm(int threads);
 cudaError_t inflate_set_max_smem(int threads);
 size_t inflate_scratch_bytes(int threads, int grid);
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st);
+                           const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st,
+                           InflateSync sy = InflateSync());
 cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
                                cudaStream_t st);
 cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,

@@ -17,8 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "index.hpp"
@@ -46,7 +48,9 @@ struct DevBuf {
 
 struct pp_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels, and every copy of the plain (non-pipelined) paths
+    cudaStream_t copy_stream = nullptr;  // H2D of a pipelined upload (overlaps the kernels)
+    cudaStream_t d2h_stream = nullptr;   // D2H of a streamed download (overlaps the kernels)
     std::mutex mu;
     int sm_count = 0;
     // inflate launch geometries: few chunks -> large CTAs (one per SM), many chunks -> more CTAs per SM
@@ -126,6 +130,23 @@ struct pp_job {
     bool have_results = false;
     bool zero_copy = false;
     const uint8_t *zc_comp = nullptr;  // device-visible alias of the caller's pinned gz buffer
+    // pipelined upload (PP_JOB_PIPELINE): pieces of the compressed range go over a copy stream while the
+    // inflate kernel runs; after every piece the host publishes the bytes in place (d_avail)
+    bool pipeline = false;
+    unsigned long long *d_avail = nullptr;
+    unsigned long long *h_marks = nullptr;  // pinned: cumulative bytes after piece i; last entry = "everything"
+    int n_marks = 0;
+    cudaEvent_t ev_reset = nullptr, ev_lead = nullptr, ev_exec_done = nullptr;
+    bool exec_pending = false;
+    // compact windows (PP_JOB_COMPACT_WINDOWS): the checkpoint windows cross PCIe zlib-compressed and a
+    // pre-pass of the inflate kernel unpacks them straight into the slots' lead areas
+    bool compact = false;
+    uint64_t cwin_lo = 0, cwin_bytes = 0;   // range of the index's compact blob this job needs
+    uint8_t *d_cwin = nullptr;
+    ChunkDesc *d_wdescs = nullptr;
+    ChunkResult *d_wresults = nullptr, *h_wresults = nullptr;
+    // streamed download (pp_job_execute_to_host): done[k] = 1 (mapped pinned memory) when chunk k is final
+    uint32_t *h_done = nullptr;
     cudaEvent_t ev[8] = {};
     pp_job_info info{};
 };
@@ -156,6 +177,26 @@ extern "C" void pp_internal_unpin_index(const pp_index *ix)
     }
 }
 
+extern "C" void pp_internal_unpin_cwin(const pp_index *ix)
+{
+    if (ix && ix->cwin_pinned) {
+        cudaHostUnregister(ix->cwin_pinned);
+        ix->cwin_pinned = nullptr;
+    }
+}
+
+static void pin_index_cwin(const pp_index *ix)
+{
+    std::lock_guard<std::mutex> lk(ix->cw_mu);
+    if (ix->cwin.empty() || ix->cwin_pinned == ix->cwin.data()) return;
+    if (ix->cwin_pinned) cudaHostUnregister(ix->cwin_pinned);
+    ix->cwin_pinned = nullptr;
+    if (cudaHostRegister(ix->cwin.data(), ix->cwin.size(), cudaHostRegisterDefault) == cudaSuccess)
+        ix->cwin_pinned = ix->cwin.data();
+    else
+        cudaGetLastError();  // stay pageable: copies still work, just slower (pull mode then refuses)
+}
+
 static void pin_index_windows(const pp_index *ix)
 {
     const size_t bytes = (size_t)ix->count() * PP_WINSIZE;
@@ -184,7 +225,9 @@ int pp_open(int32_t device, pp_ctx **out)
     if (!c) return PP_MEM_ERROR;
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return PP_E_CUDA;
     }
@@ -202,10 +245,11 @@ void pp_close(pp_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-    }
+    for (cudaStream_t st : {ctx->stream, ctx->copy_stream, ctx->d2h_stream})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
     cudaFree(ctx->d_map);
     cudaFree(ctx->d_counter);
     delete ctx;
@@ -246,6 +290,8 @@ void pp_job_free(pp_job *j)
         std::lock_guard<std::mutex> lk(j->ctx->mu);
         cudaSetDevice(j->ctx->device);
         cudaStreamSynchronize(j->ctx->stream);
+        cudaStreamSynchronize(j->ctx->copy_stream);
+        cudaStreamSynchronize(j->ctx->d2h_stream);
     }
     cudaFree(j->d_comp);
     cudaFree(j->d_lead);
@@ -259,6 +305,15 @@ void pp_job_free(pp_job *j)
     cudaFree(j->d_lines);
     cudaFree(j->d_tile_base);
     cudaFree(j->d_parse_work);
+    cudaFree(j->d_avail);
+    cudaFree(j->d_cwin);
+    cudaFree(j->d_wdescs);
+    cudaFree(j->d_wresults);
+    cudaFreeHost(j->h_marks);
+    cudaFreeHost(j->h_wresults);
+    cudaFreeHost(j->h_done);
+    for (cudaEvent_t e : {j->ev_reset, j->ev_lead, j->ev_exec_done})
+        if (e) cudaEventDestroy(e);
     cudaFreeHost(j->h_lead);
     cudaFreeHost(j->h_results);
     cudaFreeHost(j->h_pdesc);
@@ -313,7 +368,9 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         j->comp_file_lo = lo;
         j->comp_copy = hi - lo;
         j->comp_alloc = align_up(j->comp_copy, kTile) + 2 * kTile;
-        uint64_t slot_off = 0, lead_off = 0;
+        // 512 spare bytes in front of the first slot: a decode with no history in front of it (the
+        // window pre-pass) may touch up to 256 bytes before its output
+        uint64_t slot_off = 512, lead_off = 0;
         int64_t scanned = 0;
         for (int k = 0; k < n; k++) {
             const int c = first_chunk + k;
@@ -347,8 +404,30 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
             slot_off += align_up((uint64_t)d.lead_len + d.out_len + 1, 128);
             scanned += (int64_t)d.prefix_len + d.out_len;
         }
-        j->slots_bytes = std::max<uint64_t>(slot_off, 128);
+        j->slots_bytes = std::max<uint64_t>(slot_off, 1024);
         j->lead_bytes = std::max<uint64_t>(lead_off, 16);
+        // compact windows: only when every lead is exactly the checkpoint window
+        std::vector<ChunkDesc> wdescs;
+        if (j->compact && (!j->lead_direct || n == 0)) j->compact = false;
+        if (j->compact) {
+            if (!index_build_compact_windows(ix)) return fail(PP_MEM_ERROR);
+            pin_index_cwin(ix);
+            j->cwin_lo = ix->cwin_off[(size_t)first_chunk];
+            j->cwin_bytes = ix->cwin_off[(size_t)(first_chunk + n)] - j->cwin_lo;
+            wdescs.resize((size_t)n);
+            for (int k = 0; k < n; k++) {
+                const int c = first_chunk + k;
+                ChunkDesc &w = wdescs[(size_t)k];
+                w = ChunkDesc{};
+                w.in_bit = (ix->cwin_off[(size_t)c] - j->cwin_lo) * 8u + 16u;  // past the 2-byte zlib header
+                w.in_limit = ix->cwin_off[(size_t)c + 1] - j->cwin_lo;
+                w.slot_off = j->descs[(size_t)k].slot_off;                       // the chunk's lead area
+                w.lead_src = ppinf::kLeadInPlace;
+                w.lead_len = 0;
+                w.out_len = PP_WINSIZE;
+                j->descs[(size_t)k].lead_src = ppinf::kLeadInPlace;
+            }
+        }
         // parse tiles: chunk k's combined memory starts prefix_len bytes before its output
         std::vector<uint32_t> tile_base((size_t)n + 1, 0);
         {
@@ -385,9 +464,43 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         if (!j->zero_copy) {
             CK(cudaMalloc(&j->d_comp, j->comp_alloc));
             CK(cudaMemsetAsync(j->d_comp, 0, j->comp_alloc, ctx->stream));
-            CK(cudaMalloc(&j->d_lead, j->lead_bytes));
+            if (j->compact) {
+                CK(cudaMalloc(&j->d_cwin, j->cwin_bytes + 4096));
+                CK(cudaMemsetAsync(j->d_cwin, 0, j->cwin_bytes + 4096, ctx->stream));
+            } else {
+                CK(cudaMalloc(&j->d_lead, j->lead_bytes));
+            }
         }
-        if (j->lead_direct) {
+        if (j->compact) {
+            CK(cudaMalloc(&j->d_wdescs, sizeof(ChunkDesc) * (size_t)n));
+            CK(cudaMalloc(&j->d_wresults, sizeof(ChunkResult) * (size_t)n));
+            CK(cudaHostAlloc(&j->h_wresults, sizeof(ChunkResult) * (size_t)n, cudaHostAllocDefault));
+            CK(cudaMemcpyAsync(j->d_wdescs, wdescs.data(), sizeof(ChunkDesc) * (size_t)n, cudaMemcpyHostToDevice,
+                               ctx->stream));
+            CK(cudaMemsetAsync(j->d_wresults, 0, sizeof(ChunkResult) * (size_t)n, ctx->stream));
+            memset(j->h_wresults, 0, sizeof(ChunkResult) * (size_t)n);
+        }
+        if (j->pipeline) {
+            // pieces of kPiece bytes; marks[i] = bytes in place after piece i, the last one "everything"
+            const uint64_t kPiece = 8ull << 20;
+            j->n_marks = (int)std::max<uint64_t>((j->comp_copy + kPiece - 1) / kPiece, 1);
+            CK(cudaMalloc(&j->d_avail, sizeof(unsigned long long)));
+            CK(cudaHostAlloc(&j->h_marks, sizeof(unsigned long long) * ((size_t)j->n_marks + 1), cudaHostAllocDefault));
+            for (int i = 0; i < j->n_marks; i++)
+                j->h_marks[i] = i + 1 < j->n_marks ? (unsigned long long)(i + 1) * kPiece : ~0ull;
+            j->h_marks[j->n_marks] = 0;  // the reset value
+            // until the first upload nothing waits
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[j->n_marks - 1], sizeof(unsigned long long),
+                               cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CK(cudaEventCreateWithFlags(&j->ev_reset, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->ev_lead, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&j->ev_exec_done, cudaEventDisableTiming));
+        CK(cudaHostAlloc(&j->h_done, sizeof(uint32_t) * (size_t)std::max(n, 1), cudaHostAllocMapped));
+        memset(j->h_done, 0, sizeof(uint32_t) * (size_t)std::max(n, 1));
+        if (j->compact) {
+            // nothing: the leads come out of the compact blob
+        } else if (j->lead_direct) {
             pin_index_windows(ix);
         } else {
             CK(cudaHostAlloc(&j->h_lead, j->lead_bytes, cudaHostAllocDefault));
@@ -450,6 +563,8 @@ int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_
         j->n = n_chunks;
         j->flags = flags;
         j->zero_copy = (flags & PP_JOB_ZEROCOPY) != 0;
+        j->pipeline = (flags & PP_JOB_PIPELINE) != 0 && !j->zero_copy;
+        j->compact = (flags & PP_JOB_COMPACT_WINDOWS) != 0;
         rc = job_create_inner(j, ctx, ix, gz_len, first_chunk, n_chunks);
     }
     if (rc != PP_OK) {
@@ -476,12 +591,44 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
         void *dp = nullptr;
         CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(gz), 0));
         j->zc_comp = (const uint8_t *)dp + j->comp_file_lo;
-    } else if (j->n > 0) {
+    } else if (j->n > 0 && !j->pipeline) {
         CK(cudaMemcpyAsync(j->d_comp, gz + j->comp_file_lo, j->comp_copy, cudaMemcpyHostToDevice, st));
         h2d += (int64_t)j->comp_copy;
-        const uint8_t *src = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
-        CK(cudaMemcpyAsync(j->d_lead, src, j->lead_bytes, cudaMemcpyHostToDevice, st));
-        h2d += (int64_t)j->lead_bytes;
+        if (j->compact) {
+            CK(cudaMemcpyAsync(j->d_cwin, j->ix->cwin.data() + j->cwin_lo, j->cwin_bytes, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)j->cwin_bytes;
+        } else {
+            const uint8_t *src = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
+            CK(cudaMemcpyAsync(j->d_lead, src, j->lead_bytes, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)j->lead_bytes;
+        }
+    } else if (j->n > 0) {
+        // pipelined: the copies go to the copy stream and pp_job_execute's kernel overlaps them.
+        // The buffers may still be read by the previous execute: order the copies behind it.
+        cudaStream_t cs = j->ctx->copy_stream;
+        if (j->exec_pending) CK(cudaStreamWaitEvent(cs, j->ev_exec_done, 0));
+        CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[j->n_marks], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(j->ev_reset, cs));
+        if (j->compact) {
+            CK(cudaMemcpyAsync(j->d_cwin, j->ix->cwin.data() + j->cwin_lo, j->cwin_bytes, cudaMemcpyHostToDevice, cs));
+            h2d += (int64_t)j->cwin_bytes;
+        } else {
+            const uint8_t *src = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
+            CK(cudaMemcpyAsync(j->d_lead, src, j->lead_bytes, cudaMemcpyHostToDevice, cs));
+            h2d += (int64_t)j->lead_bytes;
+        }
+        CK(cudaEventRecord(j->ev_lead, cs));
+        const uint64_t kPiece = 8ull << 20;
+        for (int i = 0; i < j->n_marks; i++) {
+            const uint64_t off = (uint64_t)i * kPiece;
+            const uint64_t len = std::min<uint64_t>(kPiece, j->comp_copy - off);
+            if (len) CK(cudaMemcpyAsync(j->d_comp + off, gz + j->comp_file_lo + off, len, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[i], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+        }
+        h2d += (int64_t)j->comp_copy;
+        // the kernels must not start before the mark was reset and the leads are in place
+        CK(cudaStreamWaitEvent(st, j->ev_reset, 0));
+        CK(cudaStreamWaitEvent(st, j->ev_lead, 0));
     }
     CK(cudaEventRecord(j->ev[1], st));
     j->info.h2d_bytes = h2d;
@@ -503,35 +650,100 @@ static int job_parse_stage(pp_job *j, cudaStream_t st, bool with_pout_flags, int
     return PP_OK;
 }
 
-int pp_job_execute(pp_job *j)
+static int job_execute_locked(pp_job *j, bool stream_done)
 {
-    if (!j || !j->ctx) return PP_E_ARG;
-    std::lock_guard<std::mutex> lk(j->ctx->mu);
     CK(cudaSetDevice(j->ctx->device));
     cudaStream_t st = j->ctx->stream;
     int launches = 0;
     CK(cudaEventRecord(j->ev[2], st));
     const uint8_t *comp = j->zero_copy ? j->zc_comp : j->d_comp;
     const uint8_t *lead = j->d_lead;
+    const uint8_t *cwin = j->d_cwin;
     uint64_t comp_bytes = j->comp_alloc;
     if (j->zero_copy) {
         if (!comp) return PP_E_ARG;
         void *dp = nullptr;
-        const uint8_t *hl = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
-        CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(hl), 0));
-        lead = (const uint8_t *)dp;
+        if (j->compact) {
+            if (!j->ix->cwin_pinned) return PP_E_CUDA;  // the compact blob could not be pinned
+            CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(j->ix->cwin.data()), 0));
+            cwin = (const uint8_t *)dp + j->cwin_lo;
+        } else {
+            const uint8_t *hl = j->lead_direct ? j->ix->window(j->first) : j->h_lead;
+            CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(hl), 0));
+            lead = (const uint8_t *)dp;
+        }
         // the TRUE extent of what the job may read: nothing behind the caller's buffer is touched, so
         // any pinned buffer works (pp_host_alloc or pp_host_register); the kernel zero-fills past it
         comp_bytes = j->comp_copy;
     }
+    if (j->compact) {
+        // pre-pass: every checkpoint window is a small independent zlib stream; the same kernel inflates
+        // them into the slots' lead areas (chunk descriptors then say "history already in place")
+        CK(launch_inflate(j->d_wdescs, j->n, cwin, j->cwin_bytes, j->d_slots, j->d_slots, j->d_wresults,
+                          j->ctx->inflate_cfg(j->n), st));
+        launches += j->n > 0 ? 1 : 0;
+        lead = j->d_slots;  // unused
+    }
+    InflateSync sy;
+    if (j->pipeline) sy.avail = j->d_avail;
+    if (stream_done) {
+        void *dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, j->h_done, 0));
+        sy.done = (uint32_t *)dp;
+    }
     CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
-                      st));
+                      st, sy));
     launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)
     CK(cudaEventRecord(j->ev[3], st));
+    CK(cudaEventRecord(j->ev_exec_done, st));
+    j->exec_pending = true;
     int rc = job_parse_stage(j, st, false, &launches);
     if (rc != PP_OK) return rc;
     j->info.launches = launches;
     j->have_results = false;
+    return PP_OK;
+}
+
+int pp_job_execute(pp_job *j)
+{
+    if (!j || !j->ctx) return PP_E_ARG;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    return job_execute_locked(j, false);
+}
+
+int pp_job_execute_to_host(pp_job *j, uint8_t *dst, int64_t cap)
+{
+    if (!j || !j->ctx || !dst) return PP_E_ARG;
+    int64_t need = 0;
+    for (int k = 0; k < j->n; k++) need += j->descs[(size_t)k].out_len;
+    if (cap < need) return PP_BUF_ERROR;
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    CK(cudaSetDevice(j->ctx->device));
+    for (int k = 0; k < j->n; k++) ((volatile uint32_t *)j->h_done)[k] = 0;
+    int rc = job_execute_locked(j, true);
+    if (rc != PP_OK) return rc;
+    // chunks are handed out, and so finish, in file order: copy each one out as soon as its flag is up
+    cudaStream_t ds = j->ctx->d2h_stream;
+    int64_t pos = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 0; k < j->n; k++) {
+        const ChunkDesc &d = j->descs[(size_t)k];
+        unsigned spins = 0;
+        while (((volatile uint32_t *)j->h_done)[k] == 0) {
+            if ((++spins & 0xfffu) == 0) {
+                // a kernel that died never raises the flag: notice, and never spin forever
+                const cudaError_t q = cudaStreamQuery(j->ctx->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) { CK(q); }
+                if (q == cudaSuccess && ((volatile uint32_t *)j->h_done)[k] == 0) return PP_E_CUDA;
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) return PP_E_CUDA;
+                std::this_thread::yield();
+            }
+        }
+        if (d.out_len)
+            CK(cudaMemcpyAsync(dst + pos, j->d_slots + d.slot_off + d.lead_len, d.out_len, cudaMemcpyDeviceToHost, ds));
+        pos += d.out_len;
+    }
+    CK(cudaStreamSynchronize(ds));
     return PP_OK;
 }
 
@@ -754,6 +966,131 @@ int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t
     }
     *out = j;
     return j->info.status;
+}
+
+
+// ------------------------------------------------------------ multi-GPU DecompressAll
+//
+// Index chunks are independent (chunk k needs index[k], index[k+1] and the file bytes
+// [Input_k - 1, Input_{k+1}), LazyFileReader.cs:53-69), so DecompressAll over several GPUs is a
+// partition of the chunk list into contiguous ranges of near-equal COMPRESSED size, one range per
+// GPU, each GPU touching only its byte range and its points' windows.  No collective: the only
+// cross-GPU quantity is the global ordinal of a range's first record, an exclusive prefix sum over
+// `n_parts` integers done here on the host.
+
+int pp_partition_chunks(const pp_index *ix, int32_t parts, int32_t *first_chunk, int32_t *n_chunks)
+{
+    if (!ix || parts <= 0 || !first_chunk || !n_chunks) return PP_E_ARG;
+    const int32_t n = std::max(ix->count() - 1, 0);
+    if (n == 0) {
+        for (int32_t r = 0; r < parts; r++) first_chunk[r] = n_chunks[r] = 0;
+        return PP_OK;
+    }
+    const int64_t in0 = ix->input[0], total = ix->input[(size_t)n] - in0;
+    int32_t prev = 0;
+    for (int32_t r = 0; r < parts; r++) {
+        int32_t cut = n;
+        if (r + 1 < parts) {
+            // first point whose Input reaches this rank's share of the compressed bytes; never backwards
+            const int64_t target = in0 + (int64_t)((__int128)total * (r + 1) / parts);
+            cut = (int32_t)(std::lower_bound(ix->input.begin(), ix->input.begin() + n + 1, target) - ix->input.begin());
+            cut = std::min(std::max(cut, prev), n);
+        }
+        first_chunk[r] = prev;
+        n_chunks[r] = cut - prev;
+        prev = cut;
+    }
+    return PP_OK;
+}
+
+struct pp_multi {
+    std::vector<pp_ctx *> ctxs;
+    std::vector<pp_job *> jobs;
+    std::vector<int64_t> record_base;
+    std::vector<int> rc;
+    pp_multi_info info{};
+};
+
+void pp_multi_free(pp_multi *m)
+{
+    if (!m) return;
+    for (pp_job *j : m->jobs) pp_job_free(j);
+    for (pp_ctx *c : m->ctxs) pp_close(c);
+    delete m;
+}
+
+int pp_decompress_all_multi(const int32_t *devices, int32_t n_devices, const pp_index *ix, const uint8_t *gz,
+                            size_t gz_len, uint32_t flags, pp_multi **out)
+{
+    if (!devices || n_devices <= 0 || !ix || !out || (!gz && gz_len)) return PP_E_ARG;
+    *out = nullptr;
+    pp_multi *m = new (std::nothrow) pp_multi();
+    if (!m) return PP_MEM_ERROR;
+    int rc = PP_OK;
+    try {
+        m->ctxs.assign((size_t)n_devices, nullptr);
+        m->jobs.assign((size_t)n_devices, nullptr);
+        m->record_base.assign((size_t)n_devices, 0);
+        m->rc.assign((size_t)n_devices, PP_OK);
+        std::vector<int32_t> first((size_t)n_devices), cnt((size_t)n_devices);
+        rc = pp_partition_chunks(ix, n_devices, first.data(), cnt.data());
+        if (rc == PP_OK && (flags & PP_JOB_COMPACT_WINDOWS) && !index_build_compact_windows(ix)) rc = PP_MEM_ERROR;
+        if (rc == PP_OK) {
+            // pin the shared host buffers ONCE, before the per-GPU threads start (cudaHostRegister is
+            // portable across the contexts of one process)
+            pin_index_windows(ix);
+            if (flags & PP_JOB_COMPACT_WINDOWS) pin_index_cwin(ix);
+            // one host thread per GPU: context, plan, upload, kernels, download
+            std::vector<std::thread> th;
+            for (int32_t r = 0; r < n_devices; r++)
+                th.emplace_back([&, r]() {
+                    int e = pp_open(devices[r], &m->ctxs[(size_t)r]);
+                    if (e == PP_OK)
+                        e = pp_decompress_all(m->ctxs[(size_t)r], ix, gz, gz_len, first[(size_t)r], cnt[(size_t)r], flags,
+                                              &m->jobs[(size_t)r]);
+                    m->rc[(size_t)r] = e;
+                });
+            for (auto &t : th) t.join();
+            int64_t base = 0;
+            m->info.n_parts = n_devices;
+            for (int32_t r = 0; r < n_devices; r++) {
+                const int e = m->rc[(size_t)r];
+                if (e < 0 && !(m->jobs[(size_t)r])) { rc = e; break; }   // an API failure (no job to report from)
+                if (e < 0 && m->info.status == 0) m->info.status = e;      // a chunk's ZResult: the job exists
+                m->record_base[(size_t)r] = base;
+                const pp_job_info &I = m->jobs[(size_t)r]->info;
+                base += I.total_records;
+                m->info.total_records += I.total_records;
+                m->info.total_bytes += I.total_bytes;
+                m->info.compressed_bytes += I.compressed_bytes;
+                m->info.n_chunks += I.n_chunks;
+            }
+        }
+    } catch (...) {
+        rc = PP_MEM_ERROR;
+    }
+    if (rc != PP_OK) {
+        pp_multi_free(m);
+        return rc;
+    }
+    *out = m;
+    return m->info.status;
+}
+
+int pp_multi_info_get(const pp_multi *m, pp_multi_info *out)
+{
+    if (!m || !out) return PP_E_ARG;
+    *out = m->info;
+    return PP_OK;
+}
+
+int pp_multi_part(const pp_multi *m, int32_t part, pp_job **job, int32_t *device, int64_t *record_base)
+{
+    if (!m || part < 0 || part >= (int32_t)m->jobs.size()) return PP_E_ARG;
+    if (job) *job = m->jobs[(size_t)part];
+    if (device) *device = m->ctxs[(size_t)part] ? m->ctxs[(size_t)part]->device : -1;
+    if (record_base) *record_base = m->record_base[(size_t)part];
+    return PP_OK;
 }
 
 // ------------------------------------------------------------ single-call entry points

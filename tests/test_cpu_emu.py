@@ -41,7 +41,7 @@ def test_emulated_inflate_block_types(mode):
     assert n >= 2
 
 
-@pytest.mark.parametrize("T,subw", [(32, 31), (64, 31), (256, 31), (512, 31), (1024, 31), (128, 23), (64, 63)])  # 512 / 1024: the shipped CTA sizes
+@pytest.mark.parametrize("T,subw", [(32, 31), (64, 31), (256, 31), (512, 31), (1024, 31), (128, 27), (64, 63)])  # 512 / 1024: the shipped CTA sizes
 def test_emulated_inflate_geometries(T, subw):
     gz = corpus.gz_member(corpus.fastq(12000, fixed=150), 6)
     n, bits = _check(gz, 2000, T, subw)

@@ -286,3 +286,21 @@ def test_record_cap_verdict_matches_oracle_around_the_limit():
         assert got == want, (seq_len, got, want)
         verdicts.add(want)
     assert verdicts == {0, -104}
+
+
+def test_cxx_partitioner_equals_python_partitioner():
+    """pp_partition_chunks (what pp_decompress_all_multi and bench.py's ranks use) against shard.partition_chunks."""
+    import parallelparsing_b200 as pp
+    from parallelparsing_b200.shard import partition_chunks
+    gz = corpus.gz_member(corpus.fastq(20000, fixed=150), 6, flush_every=50000)
+    for chunk in (100, 700, 5000, 10**6):
+        ix = pp.Core.BuildDeflateIndex(gz, chunk)
+        inputs = ix.scalars()[1]
+        for world in (1, 2, 3, 4, 7, 8, 100):
+            got = pp.partition_chunks(ix, world)
+            assert got == partition_chunks(inputs, world), (chunk, world)
+            assert sum(n for _, n in got) == ix.Count - 1 and got[0][0] == 0
+            for (f0, n0), (f1, _) in zip(got, got[1:]):
+                assert f1 == f0 + n0
+    empty = pp.Index()
+    assert pp.partition_chunks(empty, 3) == [(0, 0)] * 3

@@ -756,3 +756,136 @@ def test_zero_copy_reads_nothing_past_a_registered_buffer(device):
             pp.lib().pp_host_unregister(C.c_void_p(addr + start))
         del view
         mm.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# Runtime modes: pipelined upload, compact windows, streamed download, multi-GPU call
+# ----------------------------------------------------------------------------------------------
+
+def _job_signature(job, info):
+    """Everything a mode must reproduce: per-chunk (status, inflated, records, base, parse_end) + digests."""
+    bd, fd = job.digests()
+    rows = []
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        rows.append((c.status, c.inflated, c.records, c.record_base, c.parse_end, int(bd[k]), int(fd[k])))
+    return rows
+
+
+@pytest.mark.parametrize("chunk", [300, 2000])
+def test_upload_modes_agree(device, chunk):
+    """Plain staged, pipelined (PP_JOB_PIPELINE), pull (PP_JOB_ZEROCOPY), each with and without
+    PP_JOB_COMPACT_WINDOWS, over several back-to-back steps: identical per-chunk results and digests,
+    and the concatenation is the generator's output."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(40000, fixed=150)
+    gz_np = corpus.gz_parallel(fq, 6, segment=2 << 20, threads=4)
+    gz, ptr = pp.pinned_copy(gz_np)
+    ix = pp.Core.BuildDeflateIndex(gz_np, chunk)
+    ref_job = pp.Job(device, ix, gz.size)
+    ref_info = ref_job.run(gz)
+    assert ref_info.status == 0
+    ref = _job_signature(ref_job, ref_info)
+    h2d_plain = ref_info.h2d_bytes
+    for kw in (dict(pipeline=True), dict(compact_windows=True), dict(pipeline=True, compact_windows=True),
+               dict(zero_copy=True), dict(zero_copy=True, compact_windows=True)):
+        job = pp.Job(device, ix, gz.size, **kw)
+        for step in range(3):   # back to back: the next upload must wait for the previous kernels
+            job.upload(ptr); job.execute()
+        job.download()
+        info = job.info()
+        assert info.status == 0, kw
+        assert _job_signature(job, info) == ref, kw
+        assert job.all_bytes().tobytes() == fq, kw
+        if kw.get("compact_windows") and not kw.get("zero_copy"):
+            assert info.h2d_bytes < h2d_plain - 20000 * (ix.Count - 2), kw   # windows really crossed compressed
+        job.free()
+    ref_job.free()
+    pp.lib().pp_host_free(ptr)
+
+
+def test_compact_windows_from_a_version1_index_file(device, tmp_path):
+    """IndexIO version 1 (compact windows on disk) -> Deserialize -> PP_JOB_COMPACT_WINDOWS job == oracle."""
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(30000)
+    gz = corpus.gz_member(fq, 6)
+    p = str(tmp_path / "v1.gzi")
+    pp.IndexIO.Serialize(pp.Core.BuildDeflateIndex(gz, 1000), p, compact=True)
+    ix = pp.IndexIO.Deserialize(p)
+    ox = O.OracleIndex.build(gz, 1000)
+    job = pp.Job(device, ix, gz.size, compact_windows=True, pipeline=True)
+    info = job.run(gz)
+    assert info.status == 0 and info.n_chunks == ox.count - 1
+    want = O.chunk_digests(gz, ox)
+    bd, fd = job.digests()
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        assert (c.inflated, c.records, int(bd[k]), int(fd[k])) == tuple(int(x) for x in want[k]), f"chunk {k}"
+    job.free()
+
+
+def test_streamed_download_delivers_every_byte(device):
+    """pp_job_execute_to_host: the inflated stream arrives in pinned host memory while the decode runs."""
+    import ctypes as C
+    import parallelparsing_b200 as pp
+    fq = corpus.fastq(60000, fixed=150)
+    gz_np = corpus.gz_parallel(fq, 6, segment=2 << 20, threads=4)
+    gz, ptr = pp.pinned_copy(gz_np)
+    ix = pp.Core.BuildDeflateIndex(gz_np, 1000)
+    dst = C.c_void_p()
+    pp.check(pp.lib().pp_host_alloc(len(fq), C.byref(dst)))
+    view = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(len(fq),))
+    for kw in (dict(), dict(pipeline=True, compact_windows=True), dict(zero_copy=True)):
+        job = pp.Job(device, ix, gz.size, **kw)
+        for step in range(2):
+            view[:] = 0
+            job.upload(ptr)
+            job.execute_to_host(dst, len(fq))
+            assert view.tobytes() == fq, kw
+        job.download()
+        assert job.info().status == 0 and job.info().total_records >= 60000
+        job.free()
+    with pytest.raises(pp.ZException):
+        job = pp.Job(device, ix, gz.size)
+        job.upload(ptr)
+        job.execute_to_host(dst, len(fq) - 1)   # too small: PP_BUF_ERROR, nothing written past the end
+    pp.lib().pp_host_free(dst)
+    pp.lib().pp_host_free(ptr)
+
+
+def test_multi_gpu_call_equals_whole_file_job(device):
+    """pp_decompress_all_multi over every GPU of the box (one on the single-GPU test box: the same code
+    path with one part; the 2-GPU run exercises two contexts and host threads) against the whole-file job:
+    parts are contiguous, cover every chunk, record bases are the global prefix sums."""
+    import torch
+    import parallelparsing_b200 as pp
+    ngpu = torch.cuda.device_count()
+    fq = corpus.fastq(50000, fixed=150)
+    gz_np = corpus.gz_parallel(fq, 6, segment=2 << 20, threads=4)
+    gz, ptr = pp.pinned_copy(gz_np)
+    ix = pp.Core.BuildDeflateIndex(gz_np, 1500)
+    whole = pp.Job(device, ix, gz.size)
+    wi = whole.run(gz)
+    wsig = _job_signature(whole, wi)
+    for devices in ([0], list(range(ngpu)), [0, 0, 0]):   # [0,0,0]: three parts on one GPU (three contexts)
+        for kw in (dict(), dict(zero_copy=True, compact_windows=True), dict(pipeline=True)):
+            m = pp.MultiGpuDecompressAll(devices, ix, gz, **kw)
+            assert m.status == 0
+            mi = m.info()
+            assert (mi.n_parts, mi.n_chunks, mi.total_records, mi.total_bytes) == (len(devices), wi.n_chunks, wi.total_records, wi.total_bytes)
+            parts = pp.partition_chunks(ix, len(devices))
+            cat = []
+            for r, (first, n) in enumerate(parts):
+                job, dev, base = m.part(r)
+                info = job.info()
+                assert (info.first_chunk, info.n_chunks, dev) == (first, n, devices[r])
+                bd, fd = job.digests() if n else ([], [])
+                for k in range(n):
+                    c = job.chunk(k)
+                    w = wsig[first + k]
+                    assert (c.status, c.inflated, c.records, c.record_base + base, c.parse_end, int(bd[k]), int(fd[k])) == w
+                cat.append(job.all_bytes().tobytes() if n else b"")
+            assert b"".join(cat) == fq
+            m.free()
+    whole.free()
+    pp.lib().pp_host_free(ptr)
