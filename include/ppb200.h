@@ -200,6 +200,15 @@ typedef struct pp_chunk_info {
 int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_chunk, int32_t n_chunks,
                   uint32_t flags, pp_job **out);
 int pp_job_upload(pp_job *job, const uint8_t *gz);
+/*
+ * The bytes of the .gz file a job reads — [*file_offset, *file_offset + *length), the union of its
+ * chunks' LazyFileReader ranges (LazyFileReader.cs:63-69) — and an upload that takes just those
+ * bytes: `range` holds file bytes [range_file_offset, range_file_offset + range_len) and must cover
+ * them.  A process that decodes one partition of a large file (one rank per GPU) needs to hold only
+ * its own byte range in (pinned) host memory.
+ */
+int pp_job_file_range(const pp_job *job, int64_t *file_offset, int64_t *length);
+int pp_job_upload_range(pp_job *job, const uint8_t *range, int64_t range_file_offset, int64_t range_len);
 int pp_job_execute(pp_job *job);
 /*
  * pp_job_execute that also delivers every chunk's inflated bytes to HOST memory, concatenated in

@@ -77,6 +77,8 @@ SYMBOLS = [
     ("pp_parse", _i64, [_p, _p, _i64, _p, _i64, _p, _i64, C.POINTER(_u32)]),
     ("pp_job_create", C.c_int, [_p, _p, _sz, _i32, _i32, _u32, _PP]),
     ("pp_job_upload", C.c_int, [_p, _p]),
+    ("pp_job_file_range", C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    ("pp_job_upload_range", C.c_int, [_p, _p, _i64, _i64]),
     ("pp_job_execute", C.c_int, [_p]),
     ("pp_job_execute_to_host", C.c_int, [_p, _p, _i64]),
     ("pp_job_download", C.c_int, [_p]),

@@ -259,6 +259,15 @@ class Job:
     def upload(self, gz_ptr):
         check(lib().pp_job_upload(self.h, gz_ptr), "pp_job_upload")
 
+    def file_range(self):
+        """(file offset, length) of the .gz bytes this job reads."""
+        lo, ln = C.c_int64(), C.c_int64()
+        check(lib().pp_job_file_range(self.h, C.byref(lo), C.byref(ln)), "pp_job_file_range")
+        return lo.value, ln.value
+
+    def upload_range(self, range_ptr, range_file_offset, range_len):
+        check(lib().pp_job_upload_range(self.h, range_ptr, range_file_offset, range_len), "pp_job_upload_range")
+
     def execute(self):
         check(lib().pp_job_execute(self.h), "pp_job_execute")
 

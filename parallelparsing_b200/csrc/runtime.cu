@@ -578,6 +578,26 @@ int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_
     return PP_OK;
 }
 
+int pp_job_file_range(const pp_job *j, int64_t *file_offset, int64_t *length)
+{
+    if (!j) return PP_E_ARG;
+    if (file_offset) *file_offset = (int64_t)j->comp_file_lo;
+    if (length) *length = (int64_t)j->comp_copy;
+    return PP_OK;
+}
+
+int pp_job_upload_range(pp_job *j, const uint8_t *range, int64_t range_file_offset, int64_t range_len)
+{
+    if (!j || range_file_offset < 0 || range_len < 0) return PP_E_ARG;
+    if (j->comp_copy &&
+        (!range || (uint64_t)range_file_offset > j->comp_file_lo ||
+         (uint64_t)range_file_offset + (uint64_t)range_len < j->comp_file_lo + j->comp_copy))
+        return PP_E_ARG;  // the buffer does not cover the bytes the job reads
+    // the job addresses the file as gz[offset]: hand it the base that puts `range` at its file offset
+    // (only [comp_file_lo, comp_file_lo + comp_copy) is ever touched)
+    return pp_job_upload(j, range ? range - range_file_offset : nullptr);
+}
+
 int pp_job_upload(pp_job *j, const uint8_t *gz)
 {
     if (!j || !j->ctx || (!gz && j->comp_copy)) return PP_E_ARG;
@@ -589,8 +609,8 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
     if (j->zero_copy) {
         // kernels read the caller's pinned buffer through its device alias: nothing to copy
         void *dp = nullptr;
-        CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(gz), 0));
-        j->zc_comp = (const uint8_t *)dp + j->comp_file_lo;
+        CK(cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(gz + j->comp_file_lo), 0));
+        j->zc_comp = (const uint8_t *)dp;
     } else if (j->n > 0 && !j->pipeline) {
         CK(cudaMemcpyAsync(j->d_comp, gz + j->comp_file_lo, j->comp_copy, cudaMemcpyHostToDevice, st));
         h2d += (int64_t)j->comp_copy;

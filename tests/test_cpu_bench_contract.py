@@ -51,3 +51,48 @@ def test_our_arm_fails_loudly_without_cuda(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_never_loads_the_product(tmp_path):
+    """The reference arm's corpus index comes from the oracle's own CreateIndex: the process must not
+    map libppb200.so nor import the product package (the arm was 'tainted')."""
+    code = (
+        "import sys, os, runpy\n"
+        f"sys.argv = ['bench.py', '--impl', 'reference', '--reads', '20000', '--chunk', '2000', '--steps', '1', '--warmup', '1']\n"
+        "try:\n"
+        f"    runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libppb200' not in maps, 'product library mapped in the reference arm'\n"
+        "assert 'libpporacle' in maps\n"
+        "assert not any(m.startswith('parallelparsing_b200') for m in sys.modules), 'product package imported'\n"
+    )
+    env = dict(os.environ, PPB200_CACHE=str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["warmup"] == 1 and d["steps"] == 1
+
+
+def test_reference_arm_multi_gpu_file_is_n_times_larger(tmp_path):
+    """--gpus N: ONE file of N x reads reads (sharded generation above 10 M reads is exercised with a
+    small shard size), the same `config` our arm prints."""
+    code = (
+        "import sys, os, runpy\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "bench.SHARD_READS = 4000\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--gpus', '4', '--reads', '3000', '--chunk', '500', '--steps', '1', '--warmup', '0']\n"
+        "bench.main()\n"
+    )
+    env = dict(os.environ, PPB200_CACHE=str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["n_gpus"] == 4 and d["config"]["file_reads"] == 12000 and d["config"]["records"] >= 12000
+    assert "4 contiguous chunk ranges" in d["config"]["partition"] and "shards of 4000 reads" in d["config"]["workload"]
+    assert set(d["config"]) == {"workload", "file_reads", "chunks", "records", "uncompressed_bytes", "compressed_bytes",
+                                "partition", "l2"}
