@@ -29,10 +29,14 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         __syncthreads();
         if (k >= n) break;
         ppinf::ChunkDesc d = descs[k];
-        // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
-        d.in_bit += 8ull * comp_shift;
-        d.in_limit += comp_shift;
-        if (sy.avail) {
+        const bool alt = k < sy.n_alt;   // first-wave chunk of a hybrid upload: pulled from pinned host memory
+        const uint8_t *cbase = alt ? sy.comp_alt : comp;
+        const uint64_t cbytes = alt ? sy.comp_alt_bytes : comp_bytes;
+        const uint32_t cshift = alt ? sy.alt_shift : comp_shift;
+        // the base was aligned down to 16 bytes for the bulk copies: the chunk's bits sit cshift bytes further in
+        d.in_bit += 8ull * cshift;
+        d.in_limit += cshift;
+        if (sy.avail && !alt) {
             // pipelined upload: the compressed bytes arrive on a copy stream while this kernel runs; the
             // host publishes how many bytes are in place.  Chunks are handed out in file order, so this
             // waits only when the decode has caught up with the PCIe copy.  Bounded (~4 s): a copy that
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
             if (threadIdx.x == 0) {
                 // + one staged window: the decoder looks that far ahead speculatively; the host sets the
                 // mark to "everything" after the last piece, so the tail never waits for bytes that do not exist
-                const unsigned long long need = d.in_limit - comp_shift + 4ull * ppinf::cw_words_for((int)blockDim.x);
+                const unsigned long long need = d.in_limit - cshift + 4ull * ppinf::cw_words_for((int)blockDim.x);
                 const long long t0 = clock64();
                 unsigned ok = 1;
                 while (*sy.avail < need) {
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
                 continue;
             }
         }
-        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase);
+        ppinf::inflate_chunk(sm, d, cbase, cbytes, slots, lead, map, results[k], stage_phase);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();
@@ -114,6 +118,11 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     const uint32_t comp_shift = (uint32_t)((uintptr_t)comp & 15u);
     comp -= comp_shift;
     comp_bytes += comp_shift;
+    if (sy.comp_alt) {
+        sy.alt_shift = (uint32_t)((uintptr_t)sy.comp_alt & 15u);
+        sy.comp_alt -= sy.alt_shift;
+        sy.comp_alt_bytes += sy.alt_shift;
+    }
     cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);

@@ -38,6 +38,17 @@ using namespace pp;
         }                                                                                         \
     } while (0)
 
+// Device memory of a job comes from the device's stream-ordered pool (cudaMallocAsync) with the release
+// threshold lifted (pp_open): after the first DecompressAll the next one's allocations are served from
+// memory the previous one returned, without a trip to the driver (a cold cudaMalloc/cudaFree of a few GB
+// of slots costs more than the decode itself).
+static cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
+template <class T> static cudaError_t pool_alloc(T **p, size_t bytes, cudaStream_t st) { return pool_alloc((void **)p, bytes, st); }
+static void pool_free(void *p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
 // Small RAII helper for the single-call entry points.
 struct DevBuf {
     void *p = nullptr;
@@ -122,6 +133,9 @@ struct pp_job {
     uint32_t *d_tile_base = nullptr;        // first parse tile of every chunk (n+1 entries)
     unsigned long long *d_parse_work = nullptr;  // look-back tile states + ticket
     uint32_t total_tiles = 0, max_tiles = 0;
+    cudaStream_t st_alloc = nullptr;  // stream the pooled allocations are ordered on (the context's)
+    int device = 0;
+    uint8_t *h_arena = nullptr;       // ONE pinned, mapped allocation behind every small host mirror below
     // pinned host mirrors
     ChunkResult *h_results = nullptr;
     ParseDesc *h_pdesc = nullptr;
@@ -133,6 +147,8 @@ struct pp_job {
     // pipelined upload (PP_JOB_PIPELINE): pieces of the compressed range go over a copy stream while the
     // inflate kernel runs; after every piece the host publishes the bytes in place (d_avail)
     bool pipeline = false;
+    int n_pull = 0;                       // hybrid: chunks [0, n_pull) are pulled by the kernel from pinned host memory
+    const uint8_t *pull_alias = nullptr;  // device alias of the caller's buffer at comp_file_lo (when it is pinned)
     unsigned long long *d_avail = nullptr;
     unsigned long long *h_marks = nullptr;  // pinned: cumulative bytes after piece i; last entry = "everything"
     int n_marks = 0;
@@ -232,6 +248,15 @@ int pp_open(int32_t device, pp_ctx **out)
         return PP_E_CUDA;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;  // keep freed job memory for the next job
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
     rc = ctx_setup_inflate(c);
     if (rc != PP_OK) {
         pp_close(c);
@@ -292,33 +317,20 @@ void pp_job_free(pp_job *j)
         cudaStreamSynchronize(j->ctx->stream);
         cudaStreamSynchronize(j->ctx->copy_stream);
         cudaStreamSynchronize(j->ctx->d2h_stream);
+    } else if (j->st_alloc) {
+        cudaSetDevice(j->device);
+        cudaStreamSynchronize(j->st_alloc);
     }
-    cudaFree(j->d_comp);
-    cudaFree(j->d_lead);
-    cudaFree(j->d_slots);
-    cudaFree(j->d_descs);
-    cudaFree(j->d_results);
-    cudaFree(j->d_pdesc);
-    cudaFree(j->d_pout);
-    cudaFree(j->d_totals);
-    cudaFree(j->d_exact);
-    cudaFree(j->d_lines);
-    cudaFree(j->d_tile_base);
-    cudaFree(j->d_parse_work);
-    cudaFree(j->d_avail);
-    cudaFree(j->d_cwin);
-    cudaFree(j->d_wdescs);
-    cudaFree(j->d_wresults);
-    cudaFreeHost(j->h_marks);
-    cudaFreeHost(j->h_wresults);
-    cudaFreeHost(j->h_done);
+    cudaStream_t st = j->st_alloc;
+    for (void *p : {(void *)j->d_comp, (void *)j->d_lead, (void *)j->d_slots, (void *)j->d_descs, (void *)j->d_results,
+                    (void *)j->d_pdesc, (void *)j->d_pout, (void *)j->d_totals, (void *)j->d_exact, (void *)j->d_lines,
+                    (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_cwin,
+                    (void *)j->d_wdescs, (void *)j->d_wresults})
+        pool_free(p, st);
+    cudaFreeHost(j->h_arena);
     for (cudaEvent_t e : {j->ev_reset, j->ev_lead, j->ev_exec_done})
         if (e) cudaEventDestroy(e);
     cudaFreeHost(j->h_lead);
-    cudaFreeHost(j->h_results);
-    cudaFreeHost(j->h_pdesc);
-    cudaFreeHost(j->h_pout);
-    cudaFreeHost(j->h_totals);
     for (auto &e : j->ev)
         if (e) cudaEventDestroy(e);
     delete j;
@@ -326,10 +338,10 @@ void pp_job_free(pp_job *j)
 
 static int job_alloc_lines(pp_job *j, int64_t cap)
 {
-    if (j->d_lines) cudaFree(j->d_lines);
+    pool_free(j->d_lines, j->st_alloc);
     j->d_lines = nullptr;
     j->rec_cap = std::max<int64_t>(cap, 16);
-    CK(cudaMalloc(&j->d_lines, (size_t)j->rec_cap * 4 * sizeof(uint32_t)));
+    CK(pool_alloc(&j->d_lines, (size_t)j->rec_cap * 4 * sizeof(uint32_t), j->st_alloc));
     return PP_OK;
 }
 
@@ -446,58 +458,67 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
             j->total_tiles = (uint32_t)acc;
         }
 
-        CK(cudaMalloc(&j->d_slots, j->slots_bytes));
-        CK(cudaMalloc(&j->d_descs, sizeof(ChunkDesc) * (size_t)std::max(n, 1)));
-        CK(cudaMalloc(&j->d_results, sizeof(ChunkResult) * (size_t)std::max(n, 1)));
-        CK(cudaMalloc(&j->d_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1)));
-        CK(cudaMalloc(&j->d_pout, sizeof(ParseOut) * (size_t)std::max(n, 1)));
-        CK(cudaMalloc(&j->d_totals, sizeof(ScanTotals)));
-        CK(cudaMalloc(&j->d_exact, sizeof(int64_t) * (size_t)std::max(n, 1)));
-        CK(cudaMalloc(&j->d_tile_base, sizeof(uint32_t) * ((size_t)n + 1)));
-        CK(cudaMalloc(&j->d_parse_work, sizeof(unsigned long long) * ((size_t)j->total_tiles + 1)));
+        CK(pool_alloc(&j->d_slots, j->slots_bytes, ctx->stream));
+        CK(pool_alloc(&j->d_descs, sizeof(ChunkDesc) * (size_t)std::max(n, 1), ctx->stream));
+        CK(pool_alloc(&j->d_results, sizeof(ChunkResult) * (size_t)std::max(n, 1), ctx->stream));
+        CK(pool_alloc(&j->d_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1), ctx->stream));
+        CK(pool_alloc(&j->d_pout, sizeof(ParseOut) * (size_t)std::max(n, 1), ctx->stream));
+        CK(pool_alloc(&j->d_totals, sizeof(ScanTotals), ctx->stream));
+        CK(pool_alloc(&j->d_exact, sizeof(int64_t) * (size_t)std::max(n, 1), ctx->stream));
+        CK(pool_alloc(&j->d_tile_base, sizeof(uint32_t) * ((size_t)n + 1), ctx->stream));
+        CK(pool_alloc(&j->d_parse_work, sizeof(unsigned long long) * ((size_t)j->total_tiles + 1), ctx->stream));
         CK(cudaMemcpyAsync(j->d_tile_base, tile_base.data(), sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice,
                            ctx->stream));
-        CK(cudaHostAlloc(&j->h_results, sizeof(ChunkResult) * (size_t)std::max(n, 1), cudaHostAllocDefault));
-        CK(cudaHostAlloc(&j->h_pdesc, sizeof(ParseDesc) * (size_t)std::max(n, 1), cudaHostAllocDefault));
-        CK(cudaHostAlloc(&j->h_pout, sizeof(ParseOut) * (size_t)std::max(n, 1), cudaHostAllocDefault));
-        CK(cudaHostAlloc(&j->h_totals, sizeof(ScanTotals), cudaHostAllocDefault));
+        {
+            // one pinned + mapped allocation for every small host mirror (each cudaHostAlloc is a driver call)
+            const size_t n1 = (size_t)std::max(n, 1);
+            const uint64_t kPiece = 8ull << 20;
+            j->n_marks = (int)std::max<uint64_t>((j->comp_copy + kPiece - 1) / kPiece, 1);
+            auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
+            const size_t o_res = 0, o_pd = o_res + up(sizeof(ChunkResult) * n1), o_po = o_pd + up(sizeof(ParseDesc) * n1),
+                         o_tot = o_po + up(sizeof(ParseOut) * n1), o_wres = o_tot + up(sizeof(ScanTotals)),
+                         o_marks = o_wres + up(sizeof(ChunkResult) * n1),
+                         o_done = o_marks + up(sizeof(unsigned long long) * ((size_t)j->n_marks + 2)),
+                         total = o_done + up(sizeof(uint32_t) * n1);
+            CK(cudaHostAlloc(&j->h_arena, total, cudaHostAllocMapped));
+            memset(j->h_arena, 0, total);
+            j->h_results = (ChunkResult *)(j->h_arena + o_res);
+            j->h_pdesc = (ParseDesc *)(j->h_arena + o_pd);
+            j->h_pout = (ParseOut *)(j->h_arena + o_po);
+            j->h_totals = (ScanTotals *)(j->h_arena + o_tot);
+            j->h_wresults = (ChunkResult *)(j->h_arena + o_wres);
+            j->h_marks = (unsigned long long *)(j->h_arena + o_marks);
+            j->h_done = (uint32_t *)(j->h_arena + o_done);
+        }
         if (!j->zero_copy) {
-            CK(cudaMalloc(&j->d_comp, j->comp_alloc));
+            CK(pool_alloc(&j->d_comp, j->comp_alloc, ctx->stream));
             CK(cudaMemsetAsync(j->d_comp, 0, j->comp_alloc, ctx->stream));
             if (j->compact) {
-                CK(cudaMalloc(&j->d_cwin, j->cwin_bytes + 4096));
+                CK(pool_alloc(&j->d_cwin, j->cwin_bytes + 4096, ctx->stream));
                 CK(cudaMemsetAsync(j->d_cwin, 0, j->cwin_bytes + 4096, ctx->stream));
             } else {
-                CK(cudaMalloc(&j->d_lead, j->lead_bytes));
+                CK(pool_alloc(&j->d_lead, j->lead_bytes, ctx->stream));
             }
         }
         if (j->compact) {
-            CK(cudaMalloc(&j->d_wdescs, sizeof(ChunkDesc) * (size_t)n));
-            CK(cudaMalloc(&j->d_wresults, sizeof(ChunkResult) * (size_t)n));
-            CK(cudaHostAlloc(&j->h_wresults, sizeof(ChunkResult) * (size_t)n, cudaHostAllocDefault));
+            CK(pool_alloc(&j->d_wdescs, sizeof(ChunkDesc) * (size_t)n, ctx->stream));
+            CK(pool_alloc(&j->d_wresults, sizeof(ChunkResult) * (size_t)n, ctx->stream));
             CK(cudaMemcpyAsync(j->d_wdescs, wdescs.data(), sizeof(ChunkDesc) * (size_t)n, cudaMemcpyHostToDevice,
                                ctx->stream));
             CK(cudaMemsetAsync(j->d_wresults, 0, sizeof(ChunkResult) * (size_t)n, ctx->stream));
-            memset(j->h_wresults, 0, sizeof(ChunkResult) * (size_t)n);
         }
         if (j->pipeline) {
-            // pieces of kPiece bytes; marks[i] = bytes in place after piece i, the last one "everything"
-            const uint64_t kPiece = 8ull << 20;
-            j->n_marks = (int)std::max<uint64_t>((j->comp_copy + kPiece - 1) / kPiece, 1);
-            CK(cudaMalloc(&j->d_avail, sizeof(unsigned long long)));
-            CK(cudaHostAlloc(&j->h_marks, sizeof(unsigned long long) * ((size_t)j->n_marks + 1), cudaHostAllocDefault));
-            for (int i = 0; i < j->n_marks; i++)
-                j->h_marks[i] = i + 1 < j->n_marks ? (unsigned long long)(i + 1) * kPiece : ~0ull;
-            j->h_marks[j->n_marks] = 0;  // the reset value
-            // until the first upload nothing waits
-            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[j->n_marks - 1], sizeof(unsigned long long),
-                               cudaMemcpyHostToDevice, ctx->stream));
+            // the marks (bytes in place after every piece) are filled in by pp_job_upload; until the
+            // first upload nothing waits
+            CK(pool_alloc(&j->d_avail, sizeof(unsigned long long), ctx->stream));
+            j->h_marks[0] = ~0ull;
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[0], sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                               ctx->stream));
         }
         CK(cudaEventCreateWithFlags(&j->ev_reset, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&j->ev_lead, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&j->ev_exec_done, cudaEventDisableTiming));
-        CK(cudaHostAlloc(&j->h_done, sizeof(uint32_t) * (size_t)std::max(n, 1), cudaHostAllocMapped));
-        memset(j->h_done, 0, sizeof(uint32_t) * (size_t)std::max(n, 1));
+
         if (j->compact) {
             // nothing: the leads come out of the compact blob
         } else if (j->lead_direct) {
@@ -558,6 +579,8 @@ int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_
         j = new (std::nothrow) pp_job();
         if (!j) return PP_MEM_ERROR;
         j->ctx = nullptr;  // set on success; pp_job_free must not lock the mutex we hold
+        j->st_alloc = ctx->stream;
+        j->device = ctx->device;
         j->ix = ix;
         j->first = first_chunk;
         j->n = n_chunks;
@@ -627,7 +650,31 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
         // The buffers may still be read by the previous execute: order the copies behind it.
         cudaStream_t cs = j->ctx->copy_stream;
         if (j->exec_pending) CK(cudaStreamWaitEvent(cs, j->ev_exec_done, 0));
-        CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[j->n_marks], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+        // Hybrid: when the caller's buffer is pinned, the FIRST WAVE of chunks (one per resident CTA) is
+        // not copied at all — those CTAs pull their bytes over PCIe themselves, so every SM is busy from
+        // the first microsecond instead of idling until its chunk's bytes have been copied (that ramp
+        // costs ~12 % at 10 M reads); the copy engine meanwhile brings in everything behind them.
+        uint64_t copy_from = 0;
+        j->n_pull = 0;
+        j->pull_alias = nullptr;
+        {
+            void *dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(gz + j->comp_file_lo), 0) == cudaSuccess && dp) {
+                j->pull_alias = (const uint8_t *)dp;
+                j->n_pull = std::min(j->n, j->ctx->inflate_cfg(j->n).grid);
+                copy_from = j->n_pull < j->n ? ((j->descs[(size_t)j->n_pull].in_bit >> 3) & ~(uint64_t)127) : j->comp_copy;
+            } else {
+                cudaGetLastError();  // pageable memory: plain pipelined copies
+            }
+        }
+        const uint64_t kPiece = 8ull << 20;
+        const uint64_t todo = j->comp_copy - copy_from;
+        const int pieces = (int)((todo + kPiece - 1) / kPiece);
+        // marks: [0] = reset value, [1 + i] = bytes in place after piece i, last = "everything"
+        j->h_marks[0] = pieces ? copy_from : ~0ull;
+        for (int i = 0; i < pieces; i++)
+            j->h_marks[1 + i] = i + 1 < pieces ? copy_from + (unsigned long long)(i + 1) * kPiece : ~0ull;
+        CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[0], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
         CK(cudaEventRecord(j->ev_reset, cs));
         if (j->compact) {
             CK(cudaMemcpyAsync(j->d_cwin, j->ix->cwin.data() + j->cwin_lo, j->cwin_bytes, cudaMemcpyHostToDevice, cs));
@@ -638,14 +685,13 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
             h2d += (int64_t)j->lead_bytes;
         }
         CK(cudaEventRecord(j->ev_lead, cs));
-        const uint64_t kPiece = 8ull << 20;
-        for (int i = 0; i < j->n_marks; i++) {
-            const uint64_t off = (uint64_t)i * kPiece;
+        for (int i = 0; i < pieces; i++) {
+            const uint64_t off = copy_from + (uint64_t)i * kPiece;
             const uint64_t len = std::min<uint64_t>(kPiece, j->comp_copy - off);
-            if (len) CK(cudaMemcpyAsync(j->d_comp + off, gz + j->comp_file_lo + off, len, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[i], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(j->d_comp + off, gz + j->comp_file_lo + off, len, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[1 + i], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
         }
-        h2d += (int64_t)j->comp_copy;
+        h2d += (int64_t)j->comp_copy;  // every byte crosses PCIe once: pulled (first wave) or copied
         // the kernels must not start before the mark was reset and the leads are in place
         CK(cudaStreamWaitEvent(st, j->ev_reset, 0));
         CK(cudaStreamWaitEvent(st, j->ev_lead, 0));
@@ -705,7 +751,14 @@ static int job_execute_locked(pp_job *j, bool stream_done)
         lead = j->d_slots;  // unused
     }
     InflateSync sy;
-    if (j->pipeline) sy.avail = j->d_avail;
+    if (j->pipeline) {
+        sy.avail = j->d_avail;
+        if (j->n_pull > 0 && j->pull_alias) {
+            sy.comp_alt = j->pull_alias;
+            sy.comp_alt_bytes = j->comp_copy;
+            sy.n_alt = j->n_pull;
+        }
+    }
     if (stream_done) {
         void *dp = nullptr;
         CK(cudaHostGetDevicePointer(&dp, j->h_done, 0));

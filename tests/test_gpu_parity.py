@@ -788,10 +788,13 @@ def test_upload_modes_agree(device, chunk):
     ref = _job_signature(ref_job, ref_info)
     h2d_plain = ref_info.h2d_bytes
     for kw in (dict(pipeline=True), dict(compact_windows=True), dict(pipeline=True, compact_windows=True),
-               dict(zero_copy=True), dict(zero_copy=True, compact_windows=True)):
+               dict(zero_copy=True), dict(zero_copy=True, compact_windows=True),
+               dict(pipeline=True, pageable=True), dict(pipeline=True, compact_windows=True, pageable=True)):
+        # pinned source: the pipelined upload is hybrid (first wave pulled by the kernel); pageable: plain copies
+        src = gz_np.ctypes.data_as(__import__("ctypes").c_void_p) if kw.pop("pageable", False) else ptr
         job = pp.Job(device, ix, gz.size, **kw)
         for step in range(3):   # back to back: the next upload must wait for the previous kernels
-            job.upload(ptr); job.execute()
+            job.upload(src); job.execute()
         job.download()
         info = job.info()
         assert info.status == 0, kw
