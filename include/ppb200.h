@@ -105,6 +105,7 @@ void pp_index_free(pp_index *ix);
 
 /* ----------------------------------------------------------------- Device */
 
+
 /* Open CUDA device `device`.  Fails with PP_E_NO_DEVICE when there is no GPU. */
 int pp_open(int32_t device, pp_ctx **out);
 void pp_close(pp_ctx *ctx);
@@ -268,6 +269,24 @@ void pp_job_free(pp_job *job);
 /* One-call DecompressAll: create + upload + execute + download.  Free with pp_job_free. */
 int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t gz_len, int32_t first_chunk,
                       int32_t n_chunks, uint32_t flags, pp_job **out);
+
+/* ------------------------------------------------ GPU-assisted CreateIndex, first slice */
+
+/*
+ * The first bit and the output offset of every deflate block of the gzip member `gz` — the stops
+ * Core.BuildDeflateIndex gets from a serial inflate(Z_BLOCK) pass (Decompressor/Core.cs:64) and the only
+ * places where Core.cs:98-109 may drop a checkpoint — found on the GPU: the compressed stream is cut into
+ * segments of `segment_bytes` (<= 0: 512 KiB), every segment searches for its first block header
+ * speculatively and walks its blocks with the inflate kernel's Huffman passes (no history needed),
+ * and the segments are stitched on the host (a seam that does not close is re-walked; `passes` counts
+ * the kernel launches).  start_bits[i] = 8*Input - Bits of a checkpoint taken at block i (Common/Index.cs
+ * Point.Input/Bits), out_offsets[i] = its Point.Output.  *count receives the number of blocks (PP_BUF_ERROR
+ * when > cap), *end_bit the bit after the final block, *total_out the stream's length.  The rest of
+ * CreateIndex ('@' counting, checkpoint choice, windows) is still host code (pp_index_create).
+ */
+int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int64_t segment_bytes, int64_t *start_bits,
+                   int64_t *out_offsets, int64_t cap, int64_t *count, int64_t *end_bit, int64_t *total_out,
+                   float *kernel_ms, int32_t *passes);
 
 /* ------------------------------------------------------ DecompressAll on several GPUs */
 

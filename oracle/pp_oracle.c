@@ -745,6 +745,65 @@ int ora_chunk_digests_mt(const uint8_t *gz, size_t gz_len, const ora_index *ix, 
     return j.err;
 }
 
+/*
+ * The stops of Core.BuildDeflateIndex's inflate(Z_BLOCK) loop (Core.cs:64) at which a checkpoint may be
+ * taken (Core.cs:98: data_type & 128, not in the last block): for each, bits[i] = 8*totin - (data_type & 7)
+ * — the first bit of the next block, as Index.AddPoint stores it (Input, Bits) — and outs[i] = totout.
+ * kinds[i] (may be NULL) = the 2-bit BTYPE of the block that starts there.  Also reports the bit after
+ * the final block and the stream length.  Ground truth for the GPU block scanner (pp_scan_blocks).
+ * Returns the number of stops (counting continues past cap) or a negative ZResult.
+ */
+int64_t ora_block_stops(const uint8_t *gz, size_t gz_len, int64_t *bits, int64_t *outs, uint8_t *kinds, int64_t cap,
+                        int64_t *end_bit, int64_t *total_out)
+{
+    z_stream strm;
+    memset(&strm, 0, sizeof strm);
+    if (inflateInit2(&strm, 47) != Z_OK) return Z_MEM_ERROR;
+    uint8_t *window = (uint8_t *)malloc(WINSIZE);
+    int64_t totin = 0, totout = 0, n = 0;
+    size_t fed = 0;
+    int ret = Z_OK;
+    strm.avail_out = 0;
+    while (ret != Z_STREAM_END) {
+        if (strm.avail_in == 0) {
+            size_t m = gz_len - fed < CHUNK ? gz_len - fed : CHUNK;
+            if (m == 0) { ret = Z_DATA_ERROR; break; }
+            strm.next_in = (Bytef *)(gz + fed);
+            strm.avail_in = (uInt)m;
+            fed += m;
+        }
+        if (strm.avail_out == 0) { strm.avail_out = WINSIZE; strm.next_out = window; }
+        uInt in_before = strm.avail_in, out_before = strm.avail_out;
+        ret = inflate(&strm, Z_BLOCK);
+        totin += in_before - strm.avail_in;
+        totout += out_before - strm.avail_out;
+        if (ret != Z_OK && ret != Z_STREAM_END && ret != Z_BUF_ERROR) break;
+        if (ret == Z_BUF_ERROR) ret = Z_OK;
+        if ((strm.data_type & 128) && !(strm.data_type & 64)) {
+            int64_t bit = totin * 8 - (strm.data_type & 7);
+            if (n < cap) {
+                if (bits) bits[n] = bit;
+                if (outs) outs[n] = totout;
+                if (kinds) {
+                    /* the block header's BTYPE: bits 1..2 counted from `bit` (LSB first) */
+                    int64_t b1 = bit + 1;
+                    unsigned v = (unsigned)(gz[b1 >> 3] >> (b1 & 7));
+                    if ((b1 & 7) == 7 && (size_t)((b1 >> 3) + 1) < gz_len) v |= (unsigned)gz[(b1 >> 3) + 1] << 1;
+                    kinds[n] = (uint8_t)(v & 3u);
+                }
+            }
+            n++;
+        }
+    }
+    if (ret == Z_STREAM_END) {
+        if (end_bit) *end_bit = totin * 8 - (strm.data_type & 7);
+        if (total_out) *total_out = totout;
+    }
+    inflateEnd(&strm);
+    free(window);
+    return ret == Z_STREAM_END ? n : (ret < 0 ? ret : Z_DATA_ERROR);
+}
+
 /* Whole-stream inflate (zcat) used by tests for concat(chunks) == stream. */
 int64_t ora_zcat(const uint8_t *gz, size_t gz_len, uint8_t *out, int64_t out_cap)
 {

@@ -93,6 +93,8 @@ SYMBOLS = [
     ("pp_job_digests", C.c_int, [_p, _p, _p]),
     ("pp_job_free", None, [_p]),
     ("pp_decompress_all", C.c_int, [_p, _p, _p, _sz, _i32, _i32, _u32, _PP]),
+    ("pp_scan_blocks", C.c_int, [_p, _p, _sz, _i64, _p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                 C.POINTER(C.c_float), C.POINTER(_i32)]),
     ("pp_partition_chunks", C.c_int, [_p, _i32, _p, _p]),
     ("pp_decompress_all_multi", C.c_int, [_p, _i32, _p, _p, _sz, _u32, _PP]),
     ("pp_multi_info_get", C.c_int, [_p, C.POINTER(PPMultiInfo)]),

@@ -165,6 +165,20 @@ class Core:
         return Index(_handle=h)
 
     @staticmethod
+    def ScanBlocks(file, device=None, segment_bytes=0):
+        """GPU-assisted CreateIndex, first slice (pp_scan_blocks): (start_bits[], out_offsets[], end_bit,
+        total_out, kernel_ms, passes) — every deflate block's first bit and output offset, the stops
+        BuildDeflateIndex's inflate(Z_BLOCK) pass makes (Core.cs:64,98)."""
+        dev = device or Device.default()
+        gz = _as_u8(np.fromfile(file, np.uint8) if isinstance(file, str) else file)
+        cap = max(1024, gz.size // 64)
+        bits, outs = np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+        n, end, tot, ms, passes = C.c_int64(), C.c_int64(), C.c_int64(), C.c_float(), C.c_int32()
+        check(lib().pp_scan_blocks(dev.h, _ptr(gz), gz.size, segment_bytes, _ptr(bits), _ptr(outs), cap, C.byref(n),
+                                   C.byref(end), C.byref(tot), C.byref(ms), C.byref(passes)), "pp_scan_blocks")
+        return bits[: n.value], outs[: n.value], end.value, tot.value, ms.value, passes.value
+
+    @staticmethod
     def ExtractDeflateIndex(fileBuffer, index: Index, from_point: int, buf: np.ndarray, device=None) -> int:
         """Decompress(checkpoint).  The reference passes the two Points; here the index
         and the ordinal of `from` are passed (`to` = index[from_point+1]).  `fileBuffer` is

@@ -1,0 +1,230 @@
+// GPU-assisted CreateIndex, first slice: pp_scan_blocks — the start bit and the
+// output offset of every deflate block of a gzip member, i.e. the stops Core.BuildDeflateIndex gets
+// from inflate(Z_BLOCK) (Decompressor/Core.cs:64, :98) and the only places a checkpoint may sit.
+// Kernel + stitching; see blockscan_core.cuh for the method.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "blockscan_core.cuh"
+#include "kernels.cuh"
+#include "ppb200.h"
+
+namespace pp {
+
+using ppinf::BlockRec;
+using ppinf::ScanSegIn;
+using ppinf::ScanSegOut;
+
+__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
+    pp_blockscan_kernel(const ScanSegIn *__restrict__ segs, int nseg, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
+                        uint32_t shift_bytes, BlockRec *__restrict__ recs, ScanSegOut *__restrict__ outs)
+{
+    extern __shared__ __align__(128) uint8_t pp_smem_raw[];
+    ppinf::Sm sm;
+    ppinf::sm_carve(sm, pp_smem_raw, (int)blockDim.x);
+    if (threadIdx.x == 0) {
+        ppinf::mbar_init(sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.u[24] = 0;
+        sm.u[25] = 0;
+    }
+    __syncthreads();
+    uint32_t stage_phase = 0;
+    for (int s = (int)blockIdx.x; s < nseg; s += (int)gridDim.x)
+        ppinf::scan_segment(sm, segs[s], comp, comp_bytes, 8ull * shift_bytes, recs, outs[s], stage_phase);
+}
+
+static constexpr int kScanThreads = 512;
+
+cudaError_t launch_blockscan(const ScanSegIn *segs, int nseg, const uint8_t *comp, uint64_t comp_bytes, BlockRec *recs,
+                             ScanSegOut *outs, int sm_count, cudaStream_t st)
+{
+    if (nseg <= 0) return cudaSuccess;
+    static bool attr_set[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t smem = ppinf::sm_bytes_for(kScanThreads);
+    if (!attr_set[dev & 63]) {  // idempotent: the same value every time, so a race between contexts is harmless
+        e = cudaFuncSetAttribute(pp_blockscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const uint32_t shift = (uint32_t)((uintptr_t)comp & 15u);
+    const int grid = std::min(nseg, sm_count * 2);
+    pp_blockscan_kernel<<<grid, kScanThreads, smem, st>>>(segs, nseg, comp - shift, comp_bytes + shift, shift, recs, outs);
+    return cudaGetLastError();
+}
+
+}  // namespace pp
+
+// ---- gzip member header (RFC 1952 2.3): offset of the first deflate byte, or 0 -----------------
+static size_t gzip_header_len(const uint8_t *gz, size_t n)
+{
+    if (n < 18 || gz[0] != 0x1f || gz[1] != 0x8b || gz[2] != 8) return 0;
+    const uint8_t flg = gz[3];
+    size_t p = 10;
+    if (flg & 4) {  // FEXTRA
+        if (p + 2 > n) return 0;
+        p += 2 + ((size_t)gz[p] | ((size_t)gz[p + 1] << 8));
+    }
+    for (int f = 0; f < 2; f++)   // FNAME, FCOMMENT: zero-terminated
+        if (flg & (f ? 16 : 8)) {
+            while (p < n && gz[p]) p++;
+            p++;
+        }
+    if (flg & 2) p += 2;  // FHCRC
+    return p < n ? p : 0;
+}
+
+#define CKS(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "ppb200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            rc = PP_E_CUDA;                                                                       \
+            goto done;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+extern "C" int pp_internal_ctx_device(const pp_ctx *ctx, int *device, int *sm_count, cudaStream_t *stream);
+
+extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int64_t segment_bytes, int64_t *start_bits,
+                              int64_t *out_offsets, int64_t cap, int64_t *count, int64_t *end_bit, int64_t *total_out,
+                              float *kernel_ms, int32_t *passes)
+{
+    using namespace pp;
+    if (!ctx || !gz || !count) return PP_E_ARG;
+    *count = 0;
+    const size_t hdr = gzip_header_len(gz, gz_len);
+    if (!hdr) return PP_DATA_ERROR;
+    int device = 0, sm_count = 0;
+    cudaStream_t st = nullptr;
+    if (pp_internal_ctx_device(ctx, &device, &sm_count, &st) != PP_OK) return PP_E_ARG;
+    if (segment_bytes <= 0) segment_bytes = 512 << 10;
+    if (segment_bytes < 4096) segment_bytes = 4096;
+    int rc = PP_OK;
+    uint8_t *d_comp = nullptr;
+    ScanSegIn *d_segs = nullptr;
+    ScanSegOut *d_outs = nullptr;
+    BlockRec *d_recs = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms_total = 0.f;
+    int npass = 0;
+    std::vector<BlockRec> chain;      // accepted block starts, output offsets global
+    try {
+        CKS(cudaSetDevice(device));
+        const uint64_t comp_bytes = gz_len;   // the gzip trailer (8 bytes) is simply never reached
+        const uint64_t stream_bits = (uint64_t)gz_len * 8u;
+        const int nseg = (int)std::max<uint64_t>(1, (gz_len - hdr + (uint64_t)segment_bytes - 1) / (uint64_t)segment_bytes);
+        const uint32_t rec_cap = (uint32_t)std::max<int64_t>(256, segment_bytes / 64);  // blocks average >= 64 compressed bytes, else PP_BUF_ERROR
+        CKS(cudaMalloc(&d_comp, ((gz_len + 15) & ~(size_t)15) + 4096));
+        CKS(cudaMemsetAsync(d_comp + (gz_len & ~(size_t)15), 0, 4096 + 16, st));
+        CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
+        CKS(cudaMalloc(&d_segs, sizeof(ScanSegIn) * (size_t)nseg));
+        CKS(cudaMalloc(&d_outs, sizeof(ScanSegOut) * (size_t)nseg));
+        CKS(cudaMalloc(&d_recs, sizeof(BlockRec) * (size_t)nseg * rec_cap));
+        CKS(cudaEventCreate(&e0));
+        CKS(cudaEventCreate(&e1));
+        // pass 0: every segment searches (but the first) and walks
+        std::vector<ScanSegIn> segs((size_t)nseg);
+        std::vector<ScanSegOut> outs((size_t)nseg);
+        std::vector<BlockRec> recs;
+        for (int s = 0; s < nseg; s++) {
+            ScanSegIn &g = segs[(size_t)s];
+            g.start_bit = s ? ((uint64_t)hdr + (uint64_t)s * (uint64_t)segment_bytes) * 8u : (uint64_t)hdr * 8u;
+            g.end_bit = s + 1 < nseg ? ((uint64_t)hdr + (uint64_t)(s + 1) * (uint64_t)segment_bytes) * 8u : stream_bits;
+            g.search = s ? 1u : 0u;
+            g.rec_off = (uint32_t)s * rec_cap;
+            g.rec_cap = rec_cap;
+            g.pad = 0;
+        }
+        std::vector<int> todo((size_t)nseg);
+        for (int s = 0; s < nseg; s++) todo[(size_t)s] = s;
+        std::vector<ScanSegIn> batch;
+        recs.resize((size_t)nseg * rec_cap);
+        int verified = 0;            // segments [0, verified) are in the chain
+        uint64_t land = 0, out_base = 0;
+        bool final_seen = false;
+        for (;;) {
+            // run the segments in `todo`
+            batch.clear();
+            for (int s : todo) batch.push_back(segs[(size_t)s]);
+            CKS(cudaMemcpyAsync(d_segs, batch.data(), sizeof(ScanSegIn) * batch.size(), cudaMemcpyHostToDevice, st));
+            CKS(cudaEventRecord(e0, st));
+            CKS(launch_blockscan(d_segs, (int)batch.size(), d_comp, comp_bytes, d_recs, d_outs, sm_count, st));
+            CKS(cudaEventRecord(e1, st));
+            std::vector<ScanSegOut> bo(batch.size());
+            CKS(cudaMemcpyAsync(bo.data(), d_outs, sizeof(ScanSegOut) * batch.size(), cudaMemcpyDeviceToHost, st));
+            CKS(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms_total += ms;
+            npass++;
+            for (size_t i = 0; i < todo.size(); i++) {
+                const int s = todo[i];
+                outs[(size_t)s] = bo[i];
+                if (bo[i].nrec)
+                    CKS(cudaMemcpy(recs.data() + segs[(size_t)s].rec_off, d_recs + segs[(size_t)s].rec_off,
+                                   sizeof(BlockRec) * bo[i].nrec, cudaMemcpyDeviceToHost));
+            }
+            // stitch: extend the chain while each segment's walk starts where the chain landed
+            todo.clear();
+            while (verified < nseg && !final_seen) {
+                const int s = verified;
+                const ScanSegOut &o = outs[(size_t)s];
+                const bool anchored = (s == 0 && segs[0].search == 0) || segs[(size_t)s].search == 0;
+                if (o.status < 0 && o.status != -5 && (anchored || o.first_bit == land)) { rc = PP_DATA_ERROR; goto done; }
+                if (o.status == -5) { rc = PP_BUF_ERROR; goto done; }
+                if (s > 0 && !anchored && o.first_bit != land) {
+                    if (land >= segs[(size_t)s].end_bit) {   // the chain already walked past this whole segment
+                        verified++;
+                        continue;
+                    }
+                    // the seam does not close (a stored/fixed block the search cannot see, or a false positive):
+                    // walk this segment again from where the chain landed, no search
+                    segs[(size_t)s].start_bit = land;
+                    segs[(size_t)s].search = 0;
+                    todo.push_back(s);
+                    break;
+                }
+                for (uint32_t r = 0; r < o.nrec; r++) {
+                    BlockRec br = recs[segs[(size_t)s].rec_off + r];
+                    br.out += out_base;
+                    chain.push_back(br);
+                }
+                out_base += o.out_bytes;
+                land = o.land_bit;
+                if (o.status == 1) final_seen = true;
+                verified++;
+            }
+            if (todo.empty()) break;
+            if (npass > nseg + 2) { rc = PP_E_CUDA; goto done; }   // cannot happen: every pass verifies a segment
+        }
+        if (!final_seen) { rc = PP_DATA_ERROR; goto done; }        // the stream ended without a final block
+        *count = (int64_t)chain.size();
+        for (int64_t i = 0; i < (int64_t)chain.size() && i < cap; i++) {
+            if (start_bits) start_bits[i] = (int64_t)chain[(size_t)i].bit;
+            if (out_offsets) out_offsets[i] = (int64_t)chain[(size_t)i].out;
+        }
+        if (end_bit) *end_bit = (int64_t)land;
+        if (total_out) *total_out = (int64_t)out_base;
+        if ((int64_t)chain.size() > cap && (start_bits || out_offsets)) rc = PP_BUF_ERROR;
+    } catch (...) {
+        rc = PP_MEM_ERROR;
+    }
+done:
+    if (kernel_ms) *kernel_ms = ms_total;
+    if (passes) *passes = npass;
+    cudaFree(d_comp);
+    cudaFree(d_segs);
+    cudaFree(d_outs);
+    cudaFree(d_recs);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}

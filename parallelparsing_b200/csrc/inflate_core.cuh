@@ -1284,9 +1284,15 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uin
     }
 }
 
-// One window of a Huffman block: GUESS, SYNC, SCAN, EMIT, RESOLVE.
-// s0: window-relative bit of the first symbol; room: output bytes still wanted (> 0).
-PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room)
+// The decode half of a window — GUESS, SYNC, SCAN — which needs no history and writes no output:
+// where every sub-sequence really starts, how many bytes each produces, where the window (or the
+// block, or the wanted output) ends.  Also what the block scanner of the GPU-assisted CreateIndex
+// runs (csrc/blockscan.cu).  s0: window-relative bit of the first symbol; a: misalignment of the
+// output pointer; room: output bytes still wanted (> 0).
+struct WindowCount {
+    uint32_t next_bit, need_bit, produced, flag, rounds, nlive;
+};
+PP_DEV WindowCount count_window(const Sm &sm, uint32_t s0, uint32_t room)
 {
     const int T = PP_NT;
     uint32_t *cp = reinterpret_cast<uint32_t *>(sm.res);  // checkpoints live in the (idle) resolve tile buffer
@@ -1358,7 +1364,6 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     uint32_t total = block_excl_scan(sm, sm.outc);
     // live threads: up to the flagged one, cut where the output is full or the window would need more
     // resolve tiles than its row map holds
-    const uint32_t a = (uint32_t)((uintptr_t)outp & 15u);
     const uint32_t capv = (max_tiles_for(T) - 1u) * ((uint32_t)T * kTileB) - 16u;
     PP_T0_BEGIN
     sm.u[10] = f < (uint32_t)T ? f + 1u : (uint32_t)T;  // nlive
@@ -1395,6 +1400,24 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     }
     PP_SYNC();
     PP_PHASE(PH_SCAN);
+    WindowCount c;
+    c.next_bit = next_bit;
+    c.need_bit = sm.u[23];
+    c.produced = produced;
+    c.flag = flag;
+    c.rounds = rounds;
+    c.nlive = nlive;
+    PP_SYNC();
+    return c;
+}
+
+// One window of a Huffman block: GUESS, SYNC, SCAN (count_window), then EMIT and RESOLVE.
+PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room)
+{
+    const int T = PP_NT;
+    const WindowCount c = count_window(sm, s0, room);
+    const uint32_t a = (uint32_t)((uintptr_t)outp & 15u);
+    const uint32_t nlive = c.nlive, produced = c.produced;
     // EMIT
     PP_FOR_T(t)
     {
@@ -1413,11 +1436,11 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     resolve_window(sm, tok, outp, a, produced, nlive, rshift);
     PP_PHASE(PH_RESOLVE);
     WindowOut w;
-    w.next_bit = next_bit;
-    w.need_bit = sm.u[23];
+    w.next_bit = c.next_bit;
+    w.need_bit = c.need_bit;
     w.produced = produced;
-    w.flag = flag;
-    w.rounds = rounds;
+    w.flag = c.flag;
+    w.rounds = c.rounds;
     return w;
 }
 

@@ -184,6 +184,15 @@ static int check_device(int device)
     return PP_OK;
 }
 
+extern "C" int pp_internal_ctx_device(const pp_ctx *ctx, int *device, int *sm_count, cudaStream_t *stream)
+{
+    if (!ctx) return PP_E_ARG;
+    if (device) *device = ctx->device;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (stream) *stream = ctx->stream;
+    return PP_OK;
+}
+
 extern "C" void pp_internal_unpin_index(const pp_index *ix)
 {
     if (ix && ix->pinned_base) {

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 struct uint4 { uint32_t x, y, z, w; };
 #include "../../parallelparsing_b200/csrc/inflate_core.cuh"
+#include "../../parallelparsing_b200/csrc/blockscan_core.cuh"
 
 
 extern "C" {
@@ -33,6 +34,31 @@ int emu_inflate_chunk(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t 
     free(map);
     res[0] = r.produced; res[1] = r.newlines; res[2] = r.min_byte; res[3] = r.end_bit;
     return r.status;
+}
+// Block scanner (GPU-assisted CreateIndex, first slice): one segment, emulated CTA of T threads.
+// recs: rec_cap x {bit, out}; res[5]: first_bit, land_bit, out_bytes, nrec, status.
+int emu_scan_segment(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t start_bit, uint64_t end_bit, int search,
+                     uint64_t *recs, uint32_t rec_cap, uint64_t *res)
+{
+    ppinf::g_T = T;
+    uint8_t *raw = (uint8_t *)aligned_alloc(128, ppinf::sm_bytes_for(T));
+    memset(raw, 0xff, ppinf::sm_bytes_for(T));
+    ppinf::Sm sm;
+    ppinf::sm_carve(sm, raw, T);
+    ppinf::ScanSegIn in;
+    in.start_bit = start_bit; in.end_bit = end_bit; in.search = (uint32_t)search; in.rec_off = 0; in.rec_cap = rec_cap; in.pad = 0;
+    ppinf::ScanSegOut out;
+    uint32_t phase = 0;
+    ppinf::scan_segment(sm, in, comp, comp_bytes, 0, (ppinf::BlockRec *)recs, out, phase);
+    free(raw);
+    res[0] = out.first_bit; res[1] = out.land_bit; res[2] = out.out_bytes; res[3] = out.nrec; res[4] = (uint64_t)(int64_t)out.status;
+    return out.status;
+}
+int emu_probe_dynamic_header(const uint8_t *comp, uint64_t comp_bytes, uint64_t bit)
+{
+    ppinf::BitPeek bp;
+    bp.w = (const uint32_t *)comp; bp.nw = comp_bytes / 4; bp.shift = 0;
+    return ppinf::probe_dynamic_header(bp, bit) ? 1 : 0;
 }
 int emu_subw(void) { return ppinf::kSubW; }
 void emu_stats(uint64_t *out, int reset)

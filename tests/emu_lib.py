@@ -11,6 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "emu", "emu_inflate.cpp")
 CORE = os.path.join(ROOT, "parallelparsing_b200", "csrc", "inflate_core.cuh")
+CORE2 = os.path.join(ROOT, "parallelparsing_b200", "csrc", "blockscan_core.cuh")
 OUT = os.path.join(ROOT, "tests", "emu", "_build")
 
 _libs = {}
@@ -21,13 +22,18 @@ def lib(subw=31):
         return _libs[subw]
     os.makedirs(OUT, exist_ok=True)
     so = os.path.join(OUT, f"emu_inflate_w{subw}.so")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(CORE2)):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-w", f"-DPP_SUBW={subw}", "-o", so, SRC])
     L = C.CDLL(so)
     L.emu_inflate_chunk.restype = C.c_int
     L.emu_inflate_chunk.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                     C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     L.emu_stats.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    L.emu_scan_segment.restype = C.c_int
+    L.emu_scan_segment.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32,
+                                   C.POINTER(C.c_uint64)]
+    L.emu_probe_dynamic_header.restype = C.c_int
+    L.emu_probe_dynamic_header.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     _libs[subw] = L
     return L
 
@@ -51,3 +57,22 @@ def stats(subw=31, reset=True):
     out = (C.c_uint64 * 8)()
     lib(subw).emu_stats(out, int(reset))
     return dict(windows=int(out[0]), rounds=int(out[1]), max_rounds=int(out[2]), blocks=int(out[3]))
+
+
+def _padded(gz):
+    return np.concatenate([gz, np.zeros((-gz.size) % 16 + 64, np.uint8)])
+
+
+def scan_segment(gz: np.ndarray, start_bit: int, end_bit: int, search: bool, T=64, rec_cap=4096):
+    """Emulated block scanner over one segment: (status, first_bit, land_bit, out_bytes, recs[n,2])."""
+    L = lib()
+    comp = _padded(gz)
+    recs = np.zeros((rec_cap, 2), np.uint64)
+    res = (C.c_uint64 * 5)()
+    st = L.emu_scan_segment(T, comp.ctypes.data, comp.size - 64, start_bit, end_bit, int(search), recs.ctypes.data, rec_cap, res)
+    return st, int(res[0]), int(res[1]), int(res[2]), recs[: int(res[3])].astype(np.int64)
+
+
+def probe_dynamic_header(gz: np.ndarray, bit: int) -> bool:
+    comp = _padded(gz)
+    return bool(lib().emu_probe_dynamic_header(comp.ctypes.data, comp.size - 64, bit))

@@ -67,6 +67,8 @@ def lib():
         L.ora_digest_fields.argtypes = [p, i64]
         L.ora_chunk_digests_mt.restype = C.c_int
         L.ora_chunk_digests_mt.argtypes = [p, sz, p, C.c_int, C.c_int, C.c_int, p]
+        L.ora_block_stops.restype = i64
+        L.ora_block_stops.argtypes = [p, sz, p, p, p, i64, C.POINTER(i64), C.POINTER(i64)]
         L.ora_zcat.restype = i64
         L.ora_zcat.argtypes = [p, sz, p, i64]
         _lib = L
@@ -225,3 +227,15 @@ def chunk_digests(gz, ix, first=0, n=None, threads=None):
     if rc != 0:
         raise RuntimeError(f"oracle chunk digests failed rc={rc}")
     return out[:n]
+
+
+def block_stops(gz: np.ndarray):
+    """zlib's Z_BLOCK stops where a checkpoint may sit: (bits[], outs[], kinds[], end_bit, total_out)."""
+    cap = max(1024, gz.size // 16)
+    bits, outs, kinds = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.uint8)
+    end, tot = C.c_int64(-1), C.c_int64(-1)
+    n = lib().ora_block_stops(_ptr(gz), gz.size, _ptr(bits), _ptr(outs), _ptr(kinds), cap, C.byref(end), C.byref(tot))
+    if n < 0:
+        raise RuntimeError(f"oracle block_stops failed rc={n}")
+    assert n <= cap
+    return bits[:n], outs[:n], kinds[:n], end.value, tot.value

@@ -94,3 +94,55 @@ def test_emulated_inflate_rejects_corrupt_input():
     # a stream that ends (final block) before `len` bytes: Z_STREAM_END, short count (Core.cs:185,191)
     st, got, _, _, _ = E.inflate_chunk(gz, p["input"], p["bits"], ox.inputs()[1], p["window"], len(fq) + 500, 64)
     assert st == 0 and got.tobytes() == fq
+
+
+# ---- block scanner (GPU-assisted CreateIndex, first slice): logic on the CPU ----------------------
+
+@pytest.mark.parametrize("mode", ["dynamic6", "dynamic1", "dynamic9", "huffman", "rle", "syncflush"])
+def test_emulated_probe_finds_every_dynamic_block_start_and_nothing_else(mode):
+    """The speculative header probe (one thread per bit position on the GPU): true at every dynamic
+    block's first bit as zlib's Z_BLOCK pass reports them, false at random other positions."""
+    gz = corpus.gz_member(corpus.fastq(9000, fixed=150), **MODES[mode])
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    dyn = [int(b) for b, k in zip(bits, kinds) if k == 2]
+    assert len(dyn) >= 3
+    assert all(E.probe_dynamic_header(gz, b) for b in dyn)
+    starts = set(int(b) for b in bits)
+    rng = np.random.default_rng(3)
+    others = [int(p) for p in rng.integers(int(bits[0]), int(bits[-1]), 4000) if int(p) not in starts]
+    assert sum(E.probe_dynamic_header(gz, p) for p in others) == 0
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_emulated_block_walk_equals_zlib_block_stops(mode):
+    """Walking the blocks with the Huffman passes alone (no history, no output) from the first block
+    gives zlib's stops: every block's first bit and output offset, the stream length, the final block."""
+    gz = corpus.gz_member(corpus.fastq(6000, fixed=150), **MODES[mode])
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    for T in (32, 128):
+        st, first, land, ob, recs = E.scan_segment(gz, int(bits[0]), gz.size * 8, False, T=T, rec_cap=1 << 15)
+        assert st == 1 and first == int(bits[0]) and ob == tot
+        assert np.array_equal(recs[:, 0], bits) and np.array_equal(recs[:, 1], outs)
+        assert (land + 7) // 8 * 8 + 64 == end   # the gzip trailer (CRC-32, ISIZE) follows the final block
+
+
+def test_emulated_block_search_lands_on_a_true_block_start():
+    """SEARCH + WALK from arbitrary bit positions: the first block found is the next true block start
+    (dynamic blocks), and a walk bounded by end_bit lands on the first block start at or past it."""
+    gz = corpus.gz_member(corpus.fastq(20000), 6)
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    rng = np.random.default_rng(8)
+    for _ in range(6):
+        a = int(rng.integers(int(bits[0]) + 1, int(bits[-1])))
+        b = int(min(a + rng.integers(100_000, 3_000_000), gz.size * 8))
+        st, first, land, ob, recs = E.scan_segment(gz, a, b, True)
+        i = int(np.searchsorted(bits, a))
+        if bits[i] >= b:
+            assert first == 2 ** 64 - 1 and len(recs) == 0     # no block starts inside the segment
+            continue
+        assert first == int(bits[i]) and st in (0, 1)
+        j = int(np.searchsorted(bits, b))
+        want_land = int(bits[j]) if j < len(bits) else None
+        if want_land is not None:
+            assert land == want_land and np.array_equal(recs[:, 0], bits[i:j])
+            assert ob == int(outs[j] - outs[i]) and np.array_equal(recs[:, 1], outs[i:j] - outs[i])

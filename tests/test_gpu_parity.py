@@ -892,3 +892,42 @@ def test_multi_gpu_call_equals_whole_file_job(device):
             m.free()
     whole.free()
     pp.lib().pp_host_free(ptr)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU-assisted CreateIndex, first slice: deflate block boundaries (pp_scan_blocks) == zlib's Z_BLOCK stops
+# ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode,segment", [("dynamic6", 0), ("dynamic6", 65536), ("dynamic1", 32768), ("syncflush", 65536),
+                                           ("fixed", 200000), ("stored", 100000), ("huffman", 65536)])
+def test_scan_blocks_equals_zlib_block_stops(device, mode, segment):
+    """Every block's first bit (8*Input - Bits of a checkpoint taken there) and output offset, for streams
+    of dynamic blocks (found speculatively, segments in parallel), and for stored / fixed blocks and
+    sync-flush seams, which the search cannot see: those seams are re-walked until the chain closes."""
+    import parallelparsing_b200 as pp
+    kw = dict(dynamic6=dict(level=6), dynamic1=dict(level=1), fixed=dict(level=6, strategy=zlib.Z_FIXED), stored=dict(level=0),
+              huffman=dict(level=6, strategy=zlib.Z_HUFFMAN_ONLY), syncflush=dict(level=6, flush_every=70000))[mode]
+    gz = corpus.gz_member(corpus.fastq(40000, fixed=150), **kw)
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    gb, go, gend, gtot, ms, passes = pp.Core.ScanBlocks(gz, device, segment)
+    assert gtot == tot and (gend + 7) // 8 * 8 + 64 == end
+    assert np.array_equal(gb, bits) and np.array_equal(go, outs)
+    if mode.startswith("dynamic"):
+        assert passes == 1   # every seam closed at the first attempt
+
+
+def test_scan_blocks_baseline_config1_file(device):
+    """BASELINE config 1's file (1 M reads x 150 bp, gzip -6): 1 559 dynamic blocks found in parallel;
+    the checkpoints CreateIndex chooses are a subset of them (Core.cs:98-109)."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(1_000_000, system_gzip=True), np.uint8)
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    gb, go, gend, gtot, ms, passes = pp.Core.ScanBlocks(gz, device)
+    assert len(bits) == 1559 and gtot == tot == 381_111_160
+    assert np.array_equal(gb, bits) and np.array_equal(go, outs) and passes == 1
+    ix = pp.Core.BuildDeflateIndex(gz, 10_000)
+    so, si, sb, _ = ix.scalars()
+    cps = set(zip((8 * si - sb).tolist(), so.tolist()))
+    blocks = set(zip(gb.tolist(), go.tolist()))
+    assert cps - {(int(8 * si[-1] - sb[-1]), int(so[-1]))} <= blocks   # every checkpoint but the end sentinel is a block start
+    print(f"scan_blocks: {len(gb)} blocks of {gz.size/1e6:.1f} MB in {ms:.2f} ms kernel time = {tot/ms/1e6:.1f} GB/s inflated-equivalent")
