@@ -370,9 +370,12 @@ def main():
     gz_len = os.path.getsize(gz_path)
     first, n_mine = pp.partition_chunks(ix, world)[rank]
     dev = pp.Device(local_rank)
-    job = pp.Job(dev, ix, gz_len, first, n_mine)                                              # staged, plain: `value`
-    job_pipe = pp.Job(dev, ix, gz_len, first, n_mine, pipeline=True, compact_windows=True)    # e2e: pipelined
-    job_zc = pp.Job(dev, ix, gz_len, first, n_mine, zero_copy=True, compact_windows=True)     # e2e: pull
+    # compact windows (zlib-compressed over PCIe, a GPU pre-pass unpacks them) pay when the windows are a
+    # visible share of the bytes moved: 3 % at chunk 10,000 (the pre-pass costs more than it saves), 27 % at chunk 1,000
+    compact = 32768.0 * (ix.Count - 1) > 0.08 * gz_len
+    job = pp.Job(dev, ix, gz_len, first, n_mine)                                                 # staged, plain: `value`
+    job_pipe = pp.Job(dev, ix, gz_len, first, n_mine, pipeline=True, compact_windows=compact)    # e2e: pipelined
+    job_zc = pp.Job(dev, ix, gz_len, first, n_mine, zero_copy=True, compact_windows=compact)     # e2e: pull
     lo, ln = job.file_range()
     rng_ptr = C.c_void_p()
     pp.check(L.pp_host_alloc(max(ln, 1), C.byref(rng_ptr)), "pp_host_alloc")
@@ -491,7 +494,7 @@ def main():
         if not crc_ok:
             raise SystemExit("bench.py: CRC-32/ISIZE of the bytes streamed to the host != gzip trailer")
 
-    flags_best = (4 | 8) if best is job_pipe else (2 | 8)
+    flags_best = (4 if best is job_pipe else 2) | (8 if compact else 0)
 
     def step_one_call():
         h = C.c_void_p()
@@ -539,12 +542,15 @@ def main():
                     "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": h2d_t, "d2h_bytes_per_step": d2h_t,
                     "mode": "pipelined" if t_pipe <= t_pull else "pull",
                     "pipelined": {"value": Ut / t_pipe / 1e9, "ms_per_step": t_pipe * 1e3,
-                                  "mode": "cudaMemcpyAsync H2D in 8 MB pieces on a copy stream, the inflate kernel "
-                                          "runs meanwhile and waits per chunk on a device-side byte counter"},
+                                  "mode": "hybrid: the first wave of chunks (one per resident CTA) is pulled by the kernel "
+                                          "from pinned host memory, the rest goes by cudaMemcpyAsync in 8 MB pieces on a copy "
+                                          "stream (held back until the first wave is nearly through its input); chunks wait on "
+                                          "a device-side byte counter"},
                     "pull": {"value": Ut / t_pull / 1e9, "ms_per_step": t_pull * 1e3,
                              "mode": "kernels read the compressed range from pinned host memory (TMA over PCIe)"},
-                    "windows": "zlib-compressed over PCIe, inflated on the GPU (PP_JOB_COMPACT_WINDOWS): "
-                               f"{h2d_t} B moved per step vs {h2d_plain_t} B with raw 32 KB windows",
+                    "windows": (f"zlib-compressed over PCIe, inflated on the GPU (PP_JOB_COMPACT_WINDOWS): {h2d_t} B moved per "
+                                f"step vs {h2d_plain_t} B with raw 32 KB windows") if compact else
+                               "raw 32 KB windows (3 % of the bytes moved at this chunk size: compressing them does not pay)",
                     "one_call": {"value": Ut / t_one / 1e9, "ms_per_step": t_one * 1e3,
                                  "what": "cold pp_decompress_all + pp_job_free every step (plan, allocations, pinning included)"},
                     "with_line_offsets_to_host": {"value": Ut / t_offsets / 1e9, "ms_per_step": t_offsets * 1e3,

@@ -325,6 +325,39 @@ int pp_multi_info_get(const pp_multi *m, pp_multi_info *out);
 int pp_multi_part(const pp_multi *m, int32_t part, pp_job **job, int32_t *device, int64_t *record_base);
 void pp_multi_free(pp_multi *m);
 
+/* --------------------------------------------------------------- paired-end R1 / R2 */
+
+typedef struct pp_pair pp_pair;
+
+typedef struct pp_pair_info {
+    int32_t n_parts;        /* GPUs used                                                          */
+    int32_t topup_chunks;   /* R2 chunks decoded a second time so that every mate is co-resident   */
+    int64_t records_r1, records_r2;
+    int64_t pairs;          /* min(records_r1, records_r2): record r of R1 and record r of R2      */
+    int32_t status;         /* first non-zero chunk status, else 0                                 */
+    int32_t pad;
+} pp_pair_info;
+
+/*
+ * Paired DecompressAll (README.md:9: R1/R2 "chunks with identical record counts"; the reference has
+ * no code for it).  Checkpoints sit on deflate block ends, so the two files cannot cut their chunks at
+ * the same records; what is identical is a record's ORDINAL once the H1 duplicates are dropped
+ * (PP_JOB_STRICT is forced).  Both chunk lists are partitioned over `devices`, each GPU decodes its part
+ * of R1 and of R2 concurrently, and then the few R2 chunks that hold mates of its R1 records but belong
+ * to a neighbour's part are decoded there too, so every R1 record of a part has its mate on the same
+ * GPU.  Per part: one R1 job and 1-3 R2 jobs in ordinal order, each with the global ordinal of its first
+ * record; pp_pair_locate maps an ordinal to (R2 job, record index) — the record-range map that stands in
+ * for "identical chunk record counts".  Handles are owned by the pp_pair.
+ */
+int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_index *ix1, const uint8_t *gz1,
+                           size_t gz1_len, const pp_index *ix2, const uint8_t *gz2, size_t gz2_len, uint32_t flags,
+                           pp_pair **out);
+int pp_pair_info_get(const pp_pair *p, pp_pair_info *out);
+int pp_pair_part(const pp_pair *p, int32_t part, pp_job **r1, int64_t *r1_base, int32_t *n_r2_jobs);
+int pp_pair_part_r2(const pp_pair *p, int32_t part, int32_t which, pp_job **r2, int64_t *r2_base);
+int pp_pair_locate(const pp_pair *p, int32_t part, int64_t ordinal, int32_t *which_r2, int64_t *record_index);
+void pp_pair_free(pp_pair *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,11 @@ class PPMultiInfo(C.Structure):
                 ("total_bytes", C.c_int64), ("compressed_bytes", C.c_int64), ("status", C.c_int32), ("pad", C.c_int32)]
 
 
+class PPPairInfo(C.Structure):
+    _fields_ = [("n_parts", C.c_int32), ("topup_chunks", C.c_int32), ("records_r1", C.c_int64), ("records_r2", C.c_int64),
+                ("pairs", C.c_int64), ("status", C.c_int32), ("pad", C.c_int32)]
+
+
 class ZException(Exception):
     """Interop/Conventions.cs:33-41 — carries the ZResult-compatible code."""
 
@@ -100,6 +105,12 @@ SYMBOLS = [
     ("pp_multi_info_get", C.c_int, [_p, C.POINTER(PPMultiInfo)]),
     ("pp_multi_part", C.c_int, [_p, _i32, _PP, C.POINTER(_i32), C.POINTER(_i64)]),
     ("pp_multi_free", None, [_p]),
+    ("pp_pair_decompress_all", C.c_int, [_p, _i32, _p, _p, _sz, _p, _p, _sz, _u32, _PP]),
+    ("pp_pair_info_get", C.c_int, [_p, C.POINTER(PPPairInfo)]),
+    ("pp_pair_part", C.c_int, [_p, _i32, _PP, C.POINTER(_i64), C.POINTER(_i32)]),
+    ("pp_pair_part_r2", C.c_int, [_p, _i32, _i32, _PP, C.POINTER(_i64)]),
+    ("pp_pair_locate", C.c_int, [_p, _i32, _i64, C.POINTER(_i32), C.POINTER(_i64)]),
+    ("pp_pair_free", None, [_p]),
 ]
 
 

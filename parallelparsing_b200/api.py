@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import WINSIZE, ZException, check, lib
 
 __all__ = ["Device", "Index", "Point", "IndexIO", "Core", "Parsing", "BatchedFASTQ", "PairedFASTQ", "FastqRecord", "Job",
-           "MultiGpuDecompressAll", "partition_chunks",
+           "MultiGpuDecompressAll", "PairedDecompressAll", "partition_chunks",
            "ZException", "pinned_copy"]
 
 
@@ -395,6 +395,58 @@ class MultiGpuDecompressAll:
     def free(self):
         if getattr(self, "h", None):
             lib().pp_multi_free(self.h)
+            self.h = None
+
+    __del__ = free
+
+
+class PairedDecompressAll:
+    """Paired-end R1/R2 DecompressAll below the C ABI (pp_pair_decompress_all): both chunk lists are
+    partitioned over `devices`; per part every R1 record's mate is resident on the same GPU."""
+
+    def __init__(self, devices, index1: Index, gz1, index2: Index, gz2, zero_copy=False, pipeline=False,
+                 compact_windows=False):
+        flags = ((_lib.PP_JOB_ZEROCOPY if zero_copy else 0) | (_lib.PP_JOB_PIPELINE if pipeline else 0) |
+                 (_lib.PP_JOB_COMPACT_WINDOWS if compact_windows else 0))
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = lib().pp_pair_decompress_all(devs, len(devices), index1.h, _ptr(gz1), gz1.size, index2.h, _ptr(gz2),
+                                          gz2.size, flags, C.byref(h))
+        if not h:
+            check(rc, "pp_pair_decompress_all")
+        self.h, self.status = h, rc
+        self._keep = (index1, gz1, index2, gz2)
+
+    def info(self):
+        i = _lib.PPPairInfo()
+        check(lib().pp_pair_info_get(self.h, C.byref(i)))
+        return i
+
+    def _view(self, jh):
+        j = Job.__new__(Job)
+        j.h, j._owned, j._keep = jh, False, self
+        return j
+
+    def part(self, g):
+        """(R1 job, global ordinal of its first record, [(R2 job, global ordinal of its first record), ...])."""
+        jh, base, n2 = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(lib().pp_pair_part(self.h, g, C.byref(jh), C.byref(base), C.byref(n2)), "pp_pair_part")
+        r2 = []
+        for w in range(n2.value):
+            j2, b2 = C.c_void_p(), C.c_int64()
+            check(lib().pp_pair_part_r2(self.h, g, w, C.byref(j2), C.byref(b2)), "pp_pair_part_r2")
+            r2.append((self._view(j2), b2.value))
+        return self._view(jh), base.value, r2
+
+    def locate(self, g, ordinal):
+        """(index into part g's R2 jobs, record index inside that job) of R2's record `ordinal`."""
+        w, r = C.c_int32(), C.c_int64()
+        check(lib().pp_pair_locate(self.h, g, ordinal, C.byref(w), C.byref(r)), "pp_pair_locate")
+        return w.value, r.value
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().pp_pair_free(self.h)
             self.h = None
 
     __del__ = free

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
                 continue;
             }
         }
-        ppinf::inflate_chunk(sm, d, cbase, cbytes, slots, lead, map, results[k], stage_phase);
+        // a pulled chunk reports when it is ~85 % through its compressed bytes (hybrid upload: the bulk copies start then)
+        ppinf::inflate_chunk(sm, d, cbase, cbytes, slots, lead, map, results[k], stage_phase, alt ? sy.early : nullptr,
+                             alt ? (d.in_limit - (d.in_bit >> 3)) * 15u / 100u : 0u);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();

@@ -1466,8 +1466,12 @@ PP_DEV void stored_copy(const Sm &sm, const uint8_t *src, uint8_t *dst, uint32_t
 
 // Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
 // scratch: this CTA's token rows + group index (global memory, scratch_words_for(T) words).
+// `early` (may be null): a device counter bumped once per chunk when the decode has come within
+// early_bytes of the end of its compressed range (or ends for any reason) — the hybrid upload starts its
+// bulk copies when most of the first wave got there, see runtime.cu.
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
-                          const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase)
+                          const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
+                          unsigned int *early = nullptr, uint64_t early_bytes = 0)
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
@@ -1503,7 +1507,14 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     uint32_t produced = 0;
     int status = 0;
     bool need_header = true, last = false;
+    bool marked = early == nullptr;
     while (produced < out_len) {
+        if (!marked && (bit >> 3) + early_bytes >= d.in_limit) {
+            PP_T0_BEGIN
+            PP_ATOMIC_ADD(early, 1u);
+            PP_T0_END
+            marked = true;
+        }
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
         PP_PHASE(PH_OTHER);
@@ -1559,6 +1570,11 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         }
     }
     PP_SYNC();
+    if (!marked) {
+        PP_T0_BEGIN
+        PP_ATOMIC_ADD(early, 1u);
+        PP_T0_END
+    }
     PP_PHASE(PH_OTHER);
     // 3. NUL terminator / clean tail for the parse stage
     {

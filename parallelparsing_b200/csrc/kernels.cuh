@@ -57,6 +57,7 @@ struct InflateSync {
     uint64_t comp_alt_bytes = 0;
     int n_alt = 0;
     uint32_t alt_shift = 0;                              // set by launch_inflate (16-byte alignment of comp_alt)
+    unsigned int *early = nullptr;                       // device counter: first-wave chunks that are nearly through their input
 };
 int inflate_max_ctas_per_sm(int threads);
 cudaError_t inflate_set_max_smem(int threads);

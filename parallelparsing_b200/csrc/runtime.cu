@@ -11,6 +11,7 @@
 //   download per-chunk results.
 // Chunks are independent: a multi-GPU run gives every rank its own
 // pp_ctx and a disjoint chunk range; there is no cross-GPU exchange.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -47,6 +48,24 @@ template <class T> static cudaError_t pool_alloc(T **p, size_t bytes, cudaStream
 static void pool_free(void *p, cudaStream_t st)
 {
     if (p) cudaFreeAsync(p, st);
+}
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (the library does not link libcuda):
+// a stream-ordered wait on a device word, used to hold back the bulk copies of a hybrid upload.
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32()
+{
+    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (StreamWaitValue32Fn)p;
+    }();
+    return fn;
 }
 
 // Small RAII helper for the single-call entry points.
@@ -150,6 +169,8 @@ struct pp_job {
     int n_pull = 0;                       // hybrid: chunks [0, n_pull) are pulled by the kernel from pinned host memory
     const uint8_t *pull_alias = nullptr;  // device alias of the caller's buffer at comp_file_lo (when it is pinned)
     unsigned long long *d_avail = nullptr;
+    unsigned int *d_early = nullptr;      // hybrid: first-wave chunks that are nearly through their input (gates the bulk copies)
+    bool gate_pending = false;            // the copy stream may be waiting on d_early
     unsigned long long *h_marks = nullptr;  // pinned: cumulative bytes after piece i; last entry = "everything"
     int n_marks = 0;
     cudaEvent_t ev_reset = nullptr, ev_lead = nullptr, ev_exec_done = nullptr;
@@ -323,6 +344,8 @@ void pp_job_free(pp_job *j)
     if (j->ctx) {
         std::lock_guard<std::mutex> lk(j->ctx->mu);
         cudaSetDevice(j->ctx->device);
+        if (j->gate_pending && j->d_early)   // an upload whose execute never came: let the copy stream go
+            cudaMemsetAsync(j->d_early, 0xff, sizeof(unsigned int), j->ctx->d2h_stream);
         cudaStreamSynchronize(j->ctx->stream);
         cudaStreamSynchronize(j->ctx->copy_stream);
         cudaStreamSynchronize(j->ctx->d2h_stream);
@@ -333,7 +356,7 @@ void pp_job_free(pp_job *j)
     cudaStream_t st = j->st_alloc;
     for (void *p : {(void *)j->d_comp, (void *)j->d_lead, (void *)j->d_slots, (void *)j->d_descs, (void *)j->d_results,
                     (void *)j->d_pdesc, (void *)j->d_pout, (void *)j->d_totals, (void *)j->d_exact, (void *)j->d_lines,
-                    (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_cwin,
+                    (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_early, (void *)j->d_cwin,
                     (void *)j->d_wdescs, (void *)j->d_wresults})
         pool_free(p, st);
     cudaFreeHost(j->h_arena);
@@ -520,6 +543,8 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
             // the marks (bytes in place after every piece) are filled in by pp_job_upload; until the
             // first upload nothing waits
             CK(pool_alloc(&j->d_avail, sizeof(unsigned long long), ctx->stream));
+            CK(pool_alloc(&j->d_early, sizeof(unsigned int), ctx->stream));
+            CK(cudaMemsetAsync(j->d_early, 0xff, sizeof(unsigned int), ctx->stream));
             j->h_marks[0] = ~0ull;
             CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[0], sizeof(unsigned long long), cudaMemcpyHostToDevice,
                                ctx->stream));
@@ -658,6 +683,11 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
         // pipelined: the copies go to the copy stream and pp_job_execute's kernel overlaps them.
         // The buffers may still be read by the previous execute: order the copies behind it.
         cudaStream_t cs = j->ctx->copy_stream;
+        if (j->gate_pending) {   // the previous upload was never executed: release its gate first
+            CK(cudaMemsetAsync(j->d_early, 0xff, sizeof(unsigned int), j->ctx->d2h_stream));
+            CK(cudaStreamSynchronize(j->ctx->d2h_stream));
+            j->gate_pending = false;
+        }
         if (j->exec_pending) CK(cudaStreamWaitEvent(cs, j->ev_exec_done, 0));
         // Hybrid: when the caller's buffer is pinned, the FIRST WAVE of chunks (one per resident CTA) is
         // not copied at all — those CTAs pull their bytes over PCIe themselves, so every SM is busy from
@@ -684,6 +714,7 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
         for (int i = 0; i < pieces; i++)
             j->h_marks[1 + i] = i + 1 < pieces ? copy_from + (unsigned long long)(i + 1) * kPiece : ~0ull;
         CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[0], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+        CK(cudaMemsetAsync(j->d_early, 0, sizeof(unsigned int), cs));
         CK(cudaEventRecord(j->ev_reset, cs));
         if (j->compact) {
             CK(cudaMemcpyAsync(j->d_cwin, j->ix->cwin.data() + j->cwin_lo, j->cwin_bytes, cudaMemcpyHostToDevice, cs));
@@ -694,6 +725,17 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
             h2d += (int64_t)j->lead_bytes;
         }
         CK(cudaEventRecord(j->ev_lead, cs));
+        // While the first wave pulls its bytes the link is theirs: the bulk copies behind them start when
+        // 90 % of those chunks are ~85 % through their input (a stream-ordered wait on a device counter
+        // the kernel bumps) — early enough to have the next chunks in place when the first CTAs come
+        // free, late enough not to halve the link under the pulls (that cost 3 ms of a 24 ms step).
+        if (j->n_pull > 0 && pieces > 0) {
+            if (StreamWaitValue32Fn wait = stream_wait_value32()) {
+                const unsigned int thresh = (unsigned int)std::max(1, j->n_pull * 9 / 10);
+                if (wait((CUstream)cs, (CUdeviceptr)(uintptr_t)j->d_early, thresh, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS)
+                    j->gate_pending = true;
+            }
+        }
         for (int i = 0; i < pieces; i++) {
             const uint64_t off = copy_from + (uint64_t)i * kPiece;
             const uint64_t len = std::min<uint64_t>(kPiece, j->comp_copy - off);
@@ -766,6 +808,7 @@ static int job_execute_locked(pp_job *j, bool stream_done)
             sy.comp_alt = j->pull_alias;
             sy.comp_alt_bytes = j->comp_copy;
             sy.n_alt = j->n_pull;
+            sy.early = j->d_early;
         }
     }
     if (stream_done) {
@@ -779,6 +822,7 @@ static int job_execute_locked(pp_job *j, bool stream_done)
     CK(cudaEventRecord(j->ev[3], st));
     CK(cudaEventRecord(j->ev_exec_done, st));
     j->exec_pending = true;
+    j->gate_pending = false;  // the kernel just queued bumps the counter whatever happens to its chunks
     int rc = job_parse_stage(j, st, false, &launches);
     if (rc != PP_OK) return rc;
     j->info.launches = launches;
@@ -1173,6 +1217,212 @@ int pp_multi_part(const pp_multi *m, int32_t part, pp_job **job, int32_t *device
     if (device) *device = m->ctxs[(size_t)part] ? m->ctxs[(size_t)part]->device : -1;
     if (record_base) *record_base = m->record_base[(size_t)part];
     return PP_OK;
+}
+
+// ------------------------------------------------------------ paired-end R1/R2
+//
+// The reference names paired files only in its assignment text (README.md:9 — "chunks with identical
+// record counts"); its index cannot promise that: checkpoints sit on deflate block ends, which fall
+// at different records in R1 and R2.  What CAN be kept identical is the ORDINAL of a record: with the
+// H1 duplicates dropped (PP_JOB_STRICT) record r of R1 and record r of R2 are mates.  So a paired
+// DecompressAll is: R1 and R2 decoded as two DecompressAll's whose chunk lists are partitioned over the
+// same GPUs; per part the global ordinal ranges of its R1 and R2 records are compared and the few R2
+// chunks that hold mates of the part's R1 records but landed on a neighbour are decoded here as well
+// ("top-up" jobs).  Every R1 record's mate is then resident on the same GPU, and pp_pair_locate maps an
+// ordinal to (job, record index) — the "identical chunk record counts" of the assignment, expressed as
+// a record-range map.
+
+struct pp_pair {
+    int32_t n_parts = 0;
+    std::vector<pp_ctx *> ctx1, ctx2;
+    std::vector<pp_job *> r1;                  // per part
+    std::vector<std::vector<pp_job *>> r2;     // per part: jobs ordered by ordinal (top-up left, main, top-up right)
+    std::vector<int64_t> r1_base;              // global ordinal of the part's first R1 record
+    std::vector<std::vector<int64_t>> r2_base; // same for every R2 job of the part
+    pp_pair_info info{};
+};
+
+void pp_pair_free(pp_pair *p)
+{
+    if (!p) return;
+    for (pp_job *j : p->r1) pp_job_free(j);
+    for (auto &v : p->r2)
+        for (pp_job *j : v) pp_job_free(j);
+    for (pp_ctx *c : p->ctx1) pp_close(c);
+    for (pp_ctx *c : p->ctx2) pp_close(c);
+    delete p;
+}
+
+// chunk range [first, first+n) of `ix` (whose chunks' first-record ordinals are `chunk_base`, n+1 entries
+// with the total at the end) that holds ordinals [lo, hi)
+static void chunks_for_ordinals(const std::vector<int64_t> &chunk_base, int64_t lo, int64_t hi, int32_t *first, int32_t *n)
+{
+    const int32_t nch = (int32_t)chunk_base.size() - 1;
+    int32_t a = (int32_t)(std::upper_bound(chunk_base.begin(), chunk_base.end(), lo) - chunk_base.begin()) - 1;
+    a = std::min(std::max(a, 0), nch);
+    int32_t b = (int32_t)(std::lower_bound(chunk_base.begin(), chunk_base.end(), hi) - chunk_base.begin());
+    b = std::min(std::max(b, a), nch);
+    *first = a;
+    *n = b - a;
+}
+
+int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_index *ix1, const uint8_t *gz1,
+                           size_t gz1_len, const pp_index *ix2, const uint8_t *gz2, size_t gz2_len, uint32_t flags,
+                           pp_pair **out)
+{
+    if (!devices || n_devices <= 0 || !ix1 || !ix2 || !out || (!gz1 && gz1_len) || (!gz2 && gz2_len)) return PP_E_ARG;
+    *out = nullptr;
+    flags |= PP_JOB_STRICT;  // mates are paired by ordinal: the H1 duplicate must not shift one file against the other
+    pp_pair *p = new (std::nothrow) pp_pair();
+    if (!p) return PP_MEM_ERROR;
+    int rc = PP_OK;
+    try {
+        const size_t P = (size_t)n_devices;
+        p->n_parts = n_devices;
+        p->ctx1.assign(P, nullptr);
+        p->ctx2.assign(P, nullptr);
+        p->r1.assign(P, nullptr);
+        p->r2.assign(P, {});
+        p->r1_base.assign(P, 0);
+        p->r2_base.assign(P, {});
+        std::vector<int32_t> f1(P), n1(P), f2(P), n2(P);
+        rc = pp_partition_chunks(ix1, n_devices, f1.data(), n1.data());
+        if (rc == PP_OK) rc = pp_partition_chunks(ix2, n_devices, f2.data(), n2.data());
+        if (rc == PP_OK && (flags & PP_JOB_COMPACT_WINDOWS) &&
+            (!index_build_compact_windows(ix1) || !index_build_compact_windows(ix2)))
+            rc = PP_MEM_ERROR;
+        if (rc != PP_OK) throw rc;
+        pin_index_windows(ix1);
+        pin_index_windows(ix2);
+        if (flags & PP_JOB_COMPACT_WINDOWS) { pin_index_cwin(ix1); pin_index_cwin(ix2); }
+        // phase 1: every GPU decodes its part of R1 and of R2 concurrently (two contexts = two streams:
+        // the second job's CTAs fill the SMs the first one's last, thin wave leaves idle)
+        std::vector<pp_job *> main2(P, nullptr);
+        std::vector<int> e1(P, PP_OK), e2(P, PP_OK);
+        {
+            std::vector<std::thread> th;
+            for (size_t g = 0; g < P; g++) {
+                th.emplace_back([&, g]() {
+                    int e = pp_open(devices[g], &p->ctx1[g]);
+                    if (e == PP_OK) e = pp_decompress_all(p->ctx1[g], ix1, gz1, gz1_len, f1[g], n1[g], flags, &p->r1[g]);
+                    e1[g] = e;
+                });
+                th.emplace_back([&, g]() {
+                    int e = pp_open(devices[g], &p->ctx2[g]);
+                    if (e == PP_OK) e = pp_decompress_all(p->ctx2[g], ix2, gz2, gz2_len, f2[g], n2[g], flags, &main2[g]);
+                    e2[g] = e;
+                });
+            }
+            for (auto &t : th) t.join();
+        }
+        for (size_t g = 0; g < P; g++) {
+            if (!p->r1[g] || !main2[g]) {   // an API failure: no job to report from
+                for (pp_job *j : main2) pp_job_free(j);
+                throw (e1[g] < 0 ? e1[g] : e2[g] < 0 ? e2[g] : PP_E_CUDA);
+            }
+            if (e1[g] < 0 && p->info.status == 0) p->info.status = e1[g];
+            if (e2[g] < 0 && p->info.status == 0) p->info.status = e2[g];
+        }
+        // global ordinals: per part, and per chunk of R2 (for the top-up ranges)
+        std::vector<int64_t> b1(P + 1, 0), b2(P + 1, 0);
+        for (size_t g = 0; g < P; g++) {
+            b1[g + 1] = b1[g] + p->r1[g]->info.total_records;
+            b2[g + 1] = b2[g] + main2[g]->info.total_records;
+        }
+        std::vector<int64_t> cb2;   // first-record ordinal of every R2 chunk, total at the end
+        for (size_t g = 0; g < P; g++)
+            for (int k = 0; k < main2[g]->n; k++) cb2.push_back(b2[g] + main2[g]->h_pdesc[k].rec_base);
+        cb2.push_back(b2[P]);
+        p->info.records_r1 = b1[P];
+        p->info.records_r2 = b2[P];
+        p->info.pairs = std::min(b1[P], b2[P]);
+        // phase 2: mates of this part's R1 records that a neighbour's R2 part holds
+        std::vector<std::thread> th;
+        std::vector<int> e3(2 * P, PP_OK);
+        std::vector<pp_job *> left(P, nullptr), right(P, nullptr);
+        std::vector<int64_t> lbase(P, 0), rbase(P, 0);
+        for (size_t g = 0; g < P; g++) {
+            const int64_t a1 = b1[g], z1 = std::min(b1[g + 1], b2[P]), a2 = b2[g], z2 = b2[g + 1];
+            struct Gap { int64_t lo, hi; pp_job **dst; int64_t *base; int slot; };
+            const Gap gaps[2] = {{a1, std::min(z1, a2), &left[g], &lbase[g], (int)(2 * g)},
+                                 {std::max(a1, z2), z1, &right[g], &rbase[g], (int)(2 * g + 1)}};
+            for (const Gap &gp : gaps) {
+                if (gp.lo >= gp.hi) continue;
+                int32_t cf = 0, cn = 0;
+                chunks_for_ordinals(cb2, gp.lo, gp.hi, &cf, &cn);
+                if (cn <= 0) continue;
+                *gp.base = cb2[(size_t)cf];
+                p->info.topup_chunks += cn;
+                pp_job **dst = gp.dst;
+                const int slot = gp.slot;
+                th.emplace_back([&, g, cf, cn, dst, slot]() {
+                    e3[(size_t)slot] = pp_decompress_all(p->ctx2[g], ix2, gz2, gz2_len, cf, cn, flags, dst);
+                });
+            }
+        }
+        for (auto &t : th) t.join();
+        for (size_t g = 0; g < P; g++) {
+            p->r1_base[g] = b1[g];
+            if (left[g]) { p->r2[g].push_back(left[g]); p->r2_base[g].push_back(lbase[g]); }
+            p->r2[g].push_back(main2[g]);
+            p->r2_base[g].push_back(b2[g]);
+            if (right[g]) { p->r2[g].push_back(right[g]); p->r2_base[g].push_back(rbase[g]); }
+        }
+        for (int e : e3)
+            if (e < 0 && e > -100 && p->info.status == 0) p->info.status = e;
+            else if (e <= -100) throw e;
+        p->info.n_parts = n_devices;
+    } catch (int e) {
+        rc = e;
+    } catch (...) {
+        rc = PP_MEM_ERROR;
+    }
+    if (rc != PP_OK) {
+        pp_pair_free(p);
+        return rc;
+    }
+    *out = p;
+    return p->info.status;
+}
+
+int pp_pair_info_get(const pp_pair *p, pp_pair_info *out)
+{
+    if (!p || !out) return PP_E_ARG;
+    *out = p->info;
+    return PP_OK;
+}
+
+int pp_pair_part(const pp_pair *p, int32_t part, pp_job **r1, int64_t *r1_base, int32_t *n_r2_jobs)
+{
+    if (!p || part < 0 || part >= p->n_parts) return PP_E_ARG;
+    if (r1) *r1 = p->r1[(size_t)part];
+    if (r1_base) *r1_base = p->r1_base[(size_t)part];
+    if (n_r2_jobs) *n_r2_jobs = (int32_t)p->r2[(size_t)part].size();
+    return PP_OK;
+}
+
+int pp_pair_part_r2(const pp_pair *p, int32_t part, int32_t which, pp_job **r2, int64_t *r2_base)
+{
+    if (!p || part < 0 || part >= p->n_parts || which < 0 || which >= (int32_t)p->r2[(size_t)part].size()) return PP_E_ARG;
+    if (r2) *r2 = p->r2[(size_t)part][(size_t)which];
+    if (r2_base) *r2_base = p->r2_base[(size_t)part][(size_t)which];
+    return PP_OK;
+}
+
+int pp_pair_locate(const pp_pair *p, int32_t part, int64_t ordinal, int32_t *which_r2, int64_t *record_index)
+{
+    if (!p || part < 0 || part >= p->n_parts) return PP_E_ARG;
+    const auto &jobs = p->r2[(size_t)part];
+    const auto &base = p->r2_base[(size_t)part];
+    for (size_t i = 0; i < jobs.size(); i++) {
+        const int64_t n = jobs[i]->info.total_records;
+        if (ordinal >= base[i] && ordinal < base[i] + n) {
+            if (which_r2) *which_r2 = (int32_t)i;
+            if (record_index) *record_index = ordinal - base[i];
+            return PP_OK;
+        }
+    }
+    return PP_E_ARG;  // the mate is not on this part (or R2 holds fewer records)
 }
 
 // ------------------------------------------------------------ single-call entry points

@@ -931,3 +931,59 @@ def test_scan_blocks_baseline_config1_file(device):
     blocks = set(zip(gb.tolist(), go.tolist()))
     assert cps - {(int(8 * si[-1] - sb[-1]), int(so[-1]))} <= blocks   # every checkpoint but the end sentinel is a block start
     print(f"scan_blocks: {len(gb)} blocks of {gz.size/1e6:.1f} MB in {ms:.2f} ms kernel time = {tot/ms/1e6:.1f} GB/s inflated-equivalent")
+
+
+# ----------------------------------------------------------------------------------------------
+# Paired-end R1/R2 below the C ABI (BASELINE config 3)
+# ----------------------------------------------------------------------------------------------
+
+def _record_ids(job, index, first_chunk):
+    """Identifier line (without '@') of every record of a job, from its bytes + line starts."""
+    info = job.info()
+    l0, l1, _, _ = job.line_starts()
+    ids = []
+    for k in range(info.n_chunks):
+        c = job.chunk(k)
+        mem = np.concatenate([index[first_chunk + k].offset, job.chunk_bytes(k)])
+        for r in range(c.record_base, c.record_base + c.records):
+            ids.append(bytes(mem[l0[r] + 1: l1[r] - 1]))
+    return ids
+
+
+@pytest.mark.parametrize("parts", [1, 2, 5])
+def test_paired_end_mates_are_co_resident(device, parts):
+    """R1/R2 from two Generator streams (same read count, different compression level and chunk size, so
+    block boundaries and chunk record counts differ): every part's R1 records have their mates in the R2
+    jobs of the same part, located by ordinal; ids are the generator's, pair by pair."""
+    import parallelparsing_b200 as pp
+    nreads = 24000
+    r1, r2 = corpus.fastq(nreads, fixed=150, seed=0), corpus.fastq(nreads, fixed=150, seed=1)
+    g1, g2 = corpus.gz_member(r1, 6), corpus.gz_member(r2, 1)
+    i1, i2 = pp.Core.BuildDeflateIndex(g1, 1000), pp.Core.BuildDeflateIndex(g2, 700)
+    pe = pp.PairedDecompressAll([0] * parts, i1, g1, i2, g2)
+    info = pe.info()
+    assert pe.status == 0 and (info.records_r1, info.records_r2, info.pairs, info.n_parts) == (nreads, nreads, nreads, parts)
+    if parts > 1:
+        assert info.topup_chunks > 0      # the seams of the two partitions never coincide here
+    ids1, ids2 = [ln[1:] for ln in r1.split(b"\n")[0::4]], [ln[1:] for ln in r2.split(b"\n")[0::4]]
+    p1 = pp.partition_chunks(i1, parts)
+    seen = 0
+    for g in range(parts):
+        j1, base1, r2jobs = pe.part(g)
+        n1 = j1.info().total_records
+        got1 = _record_ids(j1, i1, p1[g][0])
+        assert got1 == ids1[base1: base1 + n1]
+        got2 = [(_record_ids(j, i2, j.info().first_chunk), b) for j, b in r2jobs]
+        for b, (ids, base) in zip([b for _, b in r2jobs], got2):
+            assert ids == ids2[base: base + len(ids)]      # every R2 job knows its true global ordinals
+        for r in (0, n1 // 2, n1 - 1) if n1 else ():
+            w, idx = pe.locate(g, base1 + r)
+            assert got2[w][0][idx] == ids2[base1 + r]      # the mate of R1 record base1+r, on the same part
+        # every ordinal of the part's R1 range is covered by the part's R2 jobs
+        cover = set()
+        for ids, base in got2:
+            cover.update(range(base, base + len(ids)))
+        assert set(range(base1, base1 + n1)) <= cover
+        seen += n1
+    assert seen == nreads
+    pe.free()
