@@ -29,47 +29,10 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         __syncthreads();
         if (k >= n) break;
         ppinf::ChunkDesc d = descs[k];
-        const bool alt = k < sy.n_alt;   // first-wave chunk of a hybrid upload: pulled from pinned host memory
-        const uint8_t *cbase = alt ? sy.comp_alt : comp;
-        const uint64_t cbytes = alt ? sy.comp_alt_bytes : comp_bytes;
-        const uint32_t cshift = alt ? sy.alt_shift : comp_shift;
-        // the base was aligned down to 16 bytes for the bulk copies: the chunk's bits sit cshift bytes further in
-        d.in_bit += 8ull * cshift;
-        d.in_limit += cshift;
-        if (sy.avail && !alt) {
-            // pipelined upload: the compressed bytes arrive on a copy stream while this kernel runs; the
-            // host publishes how many bytes are in place.  Chunks are handed out in file order, so this
-            // waits only when the decode has caught up with the PCIe copy.  Bounded (~4 s): a copy that
-            // never arrives must not hang the GPU.
-            if (threadIdx.x == 0) {
-                // + one staged window: the decoder looks that far ahead speculatively; the host sets the
-                // mark to "everything" after the last piece, so the tail never waits for bytes that do not exist
-                const unsigned long long need = d.in_limit - cshift + 4ull * ppinf::cw_words_for((int)blockDim.x);
-                const long long t0 = clock64();
-                unsigned ok = 1;
-                while (*sy.avail < need) {
-                    __nanosleep(200);
-                    if (clock64() - t0 > 8000000000LL) { ok = 0; break; }
-                }
-                sm.u[17] = ok;
-            }
-            __syncthreads();
-            const bool ok = sm.u[17] != 0;
-            __syncthreads();
-            if (!ok) {
-                if (threadIdx.x == 0) {
-                    results[k].status = -100;
-                    results[k].produced = 0;
-                    results[k].newlines = 0;
-                    results[k].min_byte = 1;
-                    results[k].end_bit = 0;
-                }
-                continue;
-            }
-        }
-        // a pulled chunk reports when it is ~85 % through its compressed bytes (hybrid upload: the bulk copies start then)
-        ppinf::inflate_chunk(sm, d, cbase, cbytes, slots, lead, map, results[k], stage_phase, alt ? sy.early : nullptr,
-                             alt ? (d.in_limit - (d.in_bit >> 3)) * 15u / 100u : 0u);
+        // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
+        d.in_bit += 8ull * comp_shift;
+        d.in_limit += comp_shift;
+        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();
@@ -120,11 +83,7 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     const uint32_t comp_shift = (uint32_t)((uintptr_t)comp & 15u);
     comp -= comp_shift;
     comp_bytes += comp_shift;
-    if (sy.comp_alt) {
-        sy.alt_shift = (uint32_t)((uintptr_t)sy.comp_alt & 15u);
-        sy.comp_alt -= sy.alt_shift;
-        sy.comp_alt_bytes += sy.alt_shift;
-    }
+    sy.gate.shift = comp_shift;
     cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);

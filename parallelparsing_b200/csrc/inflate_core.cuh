@@ -87,7 +87,7 @@ namespace ppinf { static int g_T = 64; static uint64_t g_stat[8]; }  // stat: wi
 namespace ppinf {
 
 // ---- phase timers (thread 0's clock, summed over all CTAs; read with pp_internal_phase_cycles) ----
-enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_H_PARSE, PH_H_LIT, PH_COUNT };  // PH_R_EXPAND is folded into PH_R_GATHER
+enum { PH_STAGE = 0, PH_HEADER, PH_GUESS, PH_SYNC, PH_SCAN, PH_EMIT, PH_RESOLVE, PH_STORED, PH_OTHER, PH_R_EXPAND, PH_R_GATHER, PH_R_CHASE, PH_H_PARSE, PH_H_LIT, PH_WAIT, PH_COUNT };  // PH_R_EXPAND is folded into PH_R_GATHER
 #if defined(PP_HOST_EMU)
 #define PP_PHASE(ph)
 #else
@@ -1466,12 +1466,63 @@ PP_DEV void stored_copy(const Sm &sm, const uint8_t *src, uint8_t *dst, uint32_t
 
 // Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
 // scratch: this CTA's token rows + group index (global memory, scratch_words_for(T) words).
-// `early` (may be null): a device counter bumped once per chunk when the decode has come within
-// early_bytes of the end of its compressed range (or ends for any reason) — the hybrid upload starts its
-// bulk copies when most of the first wave got there, see runtime.cu.
+// Pipelined upload: the compressed range reaches the device while the kernel runs, and NOT in file
+// order.  The resident CTAs work on ~`rows` consecutive chunks at once, each eating its chunk at the
+// same modest rate, so the range is treated as waves of `rows` rows of `row_bytes` and every wave is
+// copied column by column (one 2-D copy per column of `col_bytes`): after a wave's first column every
+// row has its first 64 KB, and from then on the copy engine only has to keep ahead of the decode.
+// The host publishes progress as mark = wave * (cols + 1) + columns done (then "everything"), and a
+// CTA waits, window by window, for the column that holds the bytes it is about to stage.
+struct ByteGate {
+    const volatile unsigned long long *mark;  // device memory, written by the copy stream (null: no gate)
+    uint64_t wave_bytes;                       // rows * row_bytes
+    uint64_t row_bytes;                        // a multiple of col_bytes
+    uint32_t col_bytes;
+    uint32_t cols;                             // row_bytes / col_bytes
+    uint64_t total;                            // bytes of the range
+    uint64_t shift;                            // bytes the kernel's base pointer was moved down (alignment)
+};
+PP_HD unsigned long long gate_need(const ByteGate &g, uint64_t b)
+{
+    if (b >= g.total) b = g.total ? g.total - 1u : 0u;
+    const uint64_t w = b / g.wave_bytes, in_row = (b % g.wave_bytes) % g.row_bytes;
+    return w * (g.cols + 1u) + in_row / g.col_bytes + 1u;
+}
+// Wait until bytes [lo, hi) (kernel coordinates) are in place.  One thread polls; bounded (~4 s): a copy
+// that never arrives must not hang the GPU.  Returns false on time-out.
+PP_DEV bool gate_wait(const Sm &sm, const ByteGate *g, uint64_t lo, uint64_t hi)
+{
+#ifdef PP_HOST_EMU
+    (void)sm; (void)g; (void)lo; (void)hi;
+    return true;
+#else
+    if (!g || !g->mark) return true;
+    if (threadIdx.x == 0) {
+        lo = lo > g->shift ? lo - g->shift : 0u;
+        hi = hi > g->shift ? hi - g->shift : 0u;
+        const unsigned long long a = gate_need(*g, lo), b = gate_need(*g, hi ? hi - 1u : 0u);
+        const unsigned long long need = a > b ? a : b;
+        unsigned ok = 1;
+        if (*g->mark < need) {
+            const long long t0 = clock64();
+            while (*g->mark < need) {
+                __nanosleep(100);
+                if (clock64() - t0 > 8000000000LL) { ok = 0; break; }
+            }
+            atomicAdd(&g_phase_cycles[PH_WAIT], (unsigned long long)(clock64() - t0));
+        }
+        sm.u[17] = ok;
+    }
+    __syncthreads();
+    const bool ok = sm.u[17] != 0;
+    __syncthreads();
+    return ok;
+#endif
+}
+
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                           const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
-                          unsigned int *early = nullptr, uint64_t early_bytes = 0)
+                          const ByteGate *gate = nullptr)
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
@@ -1507,17 +1558,11 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     uint32_t produced = 0;
     int status = 0;
     bool need_header = true, last = false;
-    bool marked = early == nullptr;
     while (produced < out_len) {
-        if (!marked && (bit >> 3) + early_bytes >= d.in_limit) {
-            PP_T0_BEGIN
-            PP_ATOMIC_ADD(early, 1u);
-            PP_T0_END
-            marked = true;
-        }
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
         PP_PHASE(PH_OTHER);
+        if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
         if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
         PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
@@ -1536,6 +1581,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
                 uint32_t n = len;
                 if (n > out_len - produced) n = out_len - produced;
                 PP_SYNC();
+                if (!gate_wait(sm, gate, byte0, byte0 + n)) { status = -100; break; }
                 stored_copy(sm, comp + byte0, out + produced, n);
                 produced += n;
                 bit = (byte0 + len) * 8u;
@@ -1570,11 +1616,6 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         }
     }
     PP_SYNC();
-    if (!marked) {
-        PP_T0_BEGIN
-        PP_ATOMIC_ADD(early, 1u);
-        PP_T0_END
-    }
     PP_PHASE(PH_OTHER);
     // 3. NUL terminator / clean tail for the parse stage
     {

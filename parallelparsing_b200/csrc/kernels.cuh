@@ -46,18 +46,10 @@ struct InflateLaunch {
     uint32_t *map = nullptr; // token/index scratch: grid x scratch_words_for(threads) words
     int *counter = nullptr;  // chunk counter the CTAs pull work from
 };
-// Optional host <-> kernel hand-shakes of the inflate kernel (both may be null).
+// Optional host <-> kernel hand-shakes of the inflate kernel.
 struct InflateSync {
-    const volatile unsigned long long *avail = nullptr;  // device memory: compressed bytes already copied in (pipelined upload)
-    uint32_t *done = nullptr;                            // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
-    // hybrid upload: chunks [0, n_alt) read their compressed bytes from comp_alt (the device alias of the
-    // caller's pinned host buffer: pulled over PCIe by the kernel itself, no waiting) while the copy engine
-    // brings the rest into `comp`; comp_alt_bytes = readable extent of comp_alt
-    const uint8_t *comp_alt = nullptr;
-    uint64_t comp_alt_bytes = 0;
-    int n_alt = 0;
-    uint32_t alt_shift = 0;                              // set by launch_inflate (16-byte alignment of comp_alt)
-    unsigned int *early = nullptr;                       // device counter: first-wave chunks that are nearly through their input
+    ppinf::ByteGate gate = {nullptr, 1, 1, 1, 1, 0, 0};  // pipelined upload: which bytes are in place (mark == null: all)
+    uint32_t *done = nullptr;                             // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
 };
 int inflate_max_ctas_per_sm(int threads);
 cudaError_t inflate_set_max_smem(int threads);

@@ -34,6 +34,8 @@ for name, kw, src in (("staged", {}, ptr), ("staged+compact", dict(compact_windo
     job = pp.Job(dev, ix, gz.size, **kw)
     for _ in range(2):
         job.upload(src); job.execute(); job.download()
+    ph = (C.c_ulonglong * 20)()
+    pp.lib().pp_internal_phase_cycles(ph, 20)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     tu = te = td = 0.0
@@ -49,4 +51,9 @@ for name, kw, src in (("staged", {}, ptr), ("staged+compact", dict(compact_windo
     print(f"{name:20s} step {dt*1e3:7.2f} ms = {U/dt/1e9:6.1f} GB/s | host: upload {tu/steps*1e3:5.2f} execute {te/steps*1e3:5.2f} "
           f"download {td/steps*1e3:6.2f} | events: upload {i.upload_ms:6.2f} inflate {i.inflate_ms:6.2f} parse {i.parse_ms:5.2f} "
           f"| h2d {i.h2d_bytes/1e6:7.1f} MB")
+    nph = pp.lib().pp_internal_phase_cycles(ph, 20)
+    names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other", "r.expand", "r.expand+gather", "r.chase+store", "h.parse", "h.lit", "wait"]
+    tot = sum(ph[i] for i in range(nph)) or 1
+    print("      CTA-time ms/step (sum over CTAs / 296 / 1.965 GHz): " + ", ".join(
+        f"{names[i]} {ph[i]/steps/296/1.965e6:.2f}" for i in range(nph) if ph[i] * 200 > tot))
     job.free()
