@@ -147,7 +147,7 @@ struct pp_job {
     // pipelined upload (PP_JOB_PIPELINE): pieces of the compressed range go over a copy stream while the
     // inflate kernel runs; after every piece the host publishes the bytes in place (d_avail)
     bool pipeline = false;
-    ppinf::ByteGate gate = {nullptr, 1, 1, 1, 1, 0, 0};  // geometry of the column-interleaved copies (see ByteGate)
+    ppinf::ByteGate gate = {nullptr, 0, 0};  // see ByteGate
     unsigned long long *d_avail = nullptr;  // the gate's mark
     unsigned long long *h_marks = nullptr;  // pinned: mark values, one per column copy (+ reset, + "everything")
     int n_marks = 0;
@@ -480,19 +480,9 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         {
             // one pinned + mapped allocation for every small host mirror (each cudaHostAlloc is a driver call)
             const size_t n1 = (size_t)std::max(n, 1);
-            // pipelined upload geometry: waves of `rows` rows (one per resident CTA), rows of whole 64 KB columns
-            {
-                ppinf::ByteGate &g = j->gate;
-                const uint64_t rows = (uint64_t)std::max(1, std::min(std::max(n, 1), ctx->inflate_cfg(n).grid));
-                g.col_bytes = 64u << 10;
-                const uint64_t avg = j->comp_copy / (uint64_t)std::max(n, 1) + 1;
-                g.row_bytes = std::max<uint64_t>(align_up(avg, g.col_bytes), g.col_bytes);
-                g.cols = (uint32_t)(g.row_bytes / g.col_bytes);
-                g.wave_bytes = rows * g.row_bytes;
-                g.total = j->comp_copy;
-                const uint64_t waves = (j->comp_copy + g.wave_bytes - 1) / g.wave_bytes;
-                j->n_marks = (int)(waves * g.cols) + 2;
-            }
+            const uint64_t kPiece = 8ull << 20;   // pipelined upload: pieces of 8 MB
+            j->gate.total = j->comp_copy;
+            j->n_marks = (int)((j->comp_copy + kPiece - 1) / kPiece) + 2;
             auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
             const size_t o_res = 0, o_pd = o_res + up(sizeof(ChunkResult) * n1), o_po = o_pd + up(sizeof(ParseDesc) * n1),
                          o_tot = o_po + up(sizeof(ParseOut) * n1), o_wres = o_tot + up(sizeof(ScanTotals)),
@@ -669,7 +659,6 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
         // The buffers may still be read by the previous execute: order the copies behind it.
         cudaStream_t cs = j->ctx->copy_stream;
         if (j->exec_pending) CK(cudaStreamWaitEvent(cs, j->ev_exec_done, 0));
-        const ppinf::ByteGate &g = j->gate;
         int nm = 0;
         j->h_marks[nm] = 0;   // reset: nothing in place
         CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[nm++], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
@@ -683,30 +672,13 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
             h2d += (int64_t)j->lead_bytes;
         }
         CK(cudaEventRecord(j->ev_lead, cs));
-        // Column-interleaved copies (see ByteGate): the CTAs in flight work on ~rows consecutive chunks at
-        // once, each at the same modest rate, so a wave of rows is delivered a 64 KB column at a time —
-        // every row gets its first bytes within the first column copy instead of waiting for all the
-        // rows in front of it (file-order copies cost the first wave an average 2.6 ms of idling per CTA).
         const uint8_t *src0 = gz + j->comp_file_lo;
-        const uint64_t waves = (j->comp_copy + g.wave_bytes - 1) / g.wave_bytes;
-        for (uint64_t w = 0; w < waves; w++) {
-            const uint64_t wbase = w * g.wave_bytes;
-            const uint64_t wlen = std::min<uint64_t>(g.wave_bytes, j->comp_copy - wbase);
-            const uint64_t full_rows = wlen / g.row_bytes, tail = wlen % g.row_bytes;  // the last row may be short
-            for (uint32_t c = 0; c < g.cols; c++) {
-                const uint64_t coff = (uint64_t)c * g.col_bytes;
-                if (full_rows)
-                    CK(cudaMemcpy2DAsync(j->d_comp + wbase + coff, g.row_bytes, src0 + wbase + coff, g.row_bytes, g.col_bytes,
-                                         full_rows, cudaMemcpyHostToDevice, cs));
-                if (tail > coff) {
-                    const uint64_t off = wbase + full_rows * g.row_bytes + coff;
-                    CK(cudaMemcpyAsync(j->d_comp + off, src0 + off, std::min<uint64_t>(g.col_bytes, tail - coff),
-                                       cudaMemcpyHostToDevice, cs));
-                }
-                const bool last = w + 1 == waves && c + 1 == g.cols;
-                j->h_marks[nm] = last ? ~0ull : w * (g.cols + 1u) + c + 1u;
-                CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[nm++], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
-            }
+        const uint64_t kPiece = 8ull << 20;
+        for (uint64_t off = 0; off < j->comp_copy; off += kPiece) {
+            const uint64_t len = std::min<uint64_t>(kPiece, j->comp_copy - off);
+            CK(cudaMemcpyAsync(j->d_comp + off, src0 + off, len, cudaMemcpyHostToDevice, cs));
+            j->h_marks[nm] = off + len >= j->comp_copy ? ~0ull : off + len;
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[nm++], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
         }
         h2d += (int64_t)j->comp_copy;
         // the kernels must not start before the mark was reset and the leads are in place

@@ -873,7 +873,7 @@ def test_multi_gpu_call_equals_whole_file_job(device):
     for devices in ([0], list(range(ngpu)), [0, 0, 0]):   # [0,0,0]: three parts on one GPU (three contexts)
         for kw in (dict(), dict(zero_copy=True, compact_windows=True), dict(pipeline=True)):
             m = pp.MultiGpuDecompressAll(devices, ix, gz, **kw)
-            assert m.status == 0
+            assert m.status == 0, (devices, kw, [m.part(r)[0].info().status for r in range(len(devices))])
             mi = m.info()
             assert (mi.n_parts, mi.n_chunks, mi.total_records, mi.total_bytes) == (len(devices), wi.n_chunks, wi.total_records, wi.total_bytes)
             parts = pp.partition_chunks(ix, len(devices))
