@@ -48,21 +48,27 @@ public sealed unsafe class GpuBatchedFASTQ : IEnumerable<FastqRecord>, IDisposab
             Check(LibPpB200.pp_job_chunk_info(_job, k, out var c));
             if (c.records == 0) continue;
             // combined memory of the chunk = Point.offset ++ inflated bytes (Parsing.cs:72-117)
-            var prefix = _managedIndex[k].offset ?? Array.Empty<byte>();
-            var owner = MemoryPool<byte>.Shared.Rent(prefix.Length + (int)c.inflated);
-            prefix.CopyTo(owner.Memory);
-            using (var h = owner.Memory.Slice(prefix.Length).Pin())
+            var prefix = _managedIndex[_info.first_chunk + k].offset ?? Array.Empty<byte>();
+            using var chunkOwner = MemoryPool<byte>.Shared.Rent(prefix.Length + (int)c.inflated);
+            prefix.CopyTo(chunkOwner.Memory);
+            using (var h = chunkOwner.Memory.Slice(prefix.Length).Pin())
                 Check(LibPpB200.pp_job_fetch_chunk(_job, k, (byte*)h.Pointer, c.inflated));
             for (long r = c.record_base; r < c.record_base + c.records; r++)
             {
                 // Parsing.cs:20-39 in terms of the four line starts
                 int next = r + 1 < c.record_base + c.records ? (int)l0[r + 1] : (int)c.parse_end;
+                int start = (int)l0[r] + 1, end = next;
+                // one rented buffer PER RECORD, as Parsing.cs:41-43 does: FastqRecord.Dispose() disposes its
+                // Owner (Common/FastqRecord.cs:80-83) and the reference's consumers dispose every record, so
+                // records must not share an owner
+                var owner = MemoryPool<byte>.Shared.Rent(end - start);
                 var m = owner.Memory;
+                chunkOwner.Memory.Slice(start, end - start).CopyTo(m);
                 yield return new FastqRecord(owner,
-                    m.Slice((int)l0[r] + 1, (int)(l1[r] - l0[r]) - 2),   // Identifier (no '@', no '\n')
-                    m.Slice((int)l1[r], (int)(l2[r] - l1[r]) - 1),       // Sequence
-                    m.Slice((int)l2[r] + 1, (int)(l3[r] - l2[r]) - 2),   // Other (no '+')
-                    m.Slice((int)l3[r], next - (int)l3[r] - 1));         // Quality
+                    m.Slice(0, (int)(l1[r] - l0[r]) - 2),                                  // Identifier (no '@', no '\n')
+                    m.Slice((int)l1[r] - start, (int)(l2[r] - l1[r]) - 1),                  // Sequence
+                    m.Slice((int)l2[r] + 1 - start, (int)(l3[r] - l2[r]) - 2),              // Other (no '+')
+                    m.Slice((int)l3[r] - start, next - (int)l3[r] - 1));                    // Quality
             }
         }
     }

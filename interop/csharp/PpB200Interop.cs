@@ -55,6 +55,35 @@ internal static class LibPpB200
     [DllImport(L)] public static unsafe extern int pp_job_count_pattern(IntPtr job, byte* pattern, int patternLen, out ulong count);
     [DllImport(L)] public static extern void pp_job_free(IntPtr job);
     [DllImport(L)] public static unsafe extern int pp_decompress_all(IntPtr ctx, IntPtr index, byte* gz, nuint gzLen, int firstChunk, int nChunks, uint flags, out IntPtr job);
+
+    // round 2: partial-file uploads, streamed download, digests
+    [DllImport(L)] public static extern int pp_job_file_range(IntPtr job, out long fileOffset, out long length);
+    [DllImport(L)] public static unsafe extern int pp_job_upload_range(IntPtr job, byte* range, long rangeFileOffset, long rangeLen);
+    [DllImport(L)] public static unsafe extern int pp_job_execute_to_host(IntPtr job, byte* dst, long cap);
+    [DllImport(L)] public static unsafe extern int pp_job_digests(IntPtr job, ulong* bytesDigest, ulong* fieldsDigest);
+
+    // DecompressAll over several GPUs (one call; partition below the ABI)
+    [DllImport(L)] public static unsafe extern int pp_partition_chunks(IntPtr index, int parts, int* firstChunk, int* nChunks);
+    [DllImport(L)] public static unsafe extern int pp_decompress_all_multi(int* devices, int nDevices, IntPtr index, byte* gz, nuint gzLen, uint flags, out IntPtr multi);
+    [DllImport(L)] public static extern int pp_multi_info_get(IntPtr multi, out pp_multi_info info);
+    [DllImport(L)] public static extern int pp_multi_part(IntPtr multi, int part, out IntPtr job, out int device, out long recordBase);
+    [DllImport(L)] public static extern void pp_multi_free(IntPtr multi);
+
+    // paired-end R1/R2 (README.md:9)
+    [DllImport(L)] public static unsafe extern int pp_pair_decompress_all(int* devices, int nDevices, IntPtr index1, byte* gz1, nuint gz1Len, IntPtr index2, byte* gz2, nuint gz2Len, uint flags, out IntPtr pair);
+    [DllImport(L)] public static extern int pp_pair_info_get(IntPtr pair, out pp_pair_info info);
+    [DllImport(L)] public static extern int pp_pair_part(IntPtr pair, int part, out IntPtr r1Job, out long r1Base, out int nR2Jobs);
+    [DllImport(L)] public static extern int pp_pair_part_r2(IntPtr pair, int part, int which, out IntPtr r2Job, out long r2Base);
+    [DllImport(L)] public static extern int pp_pair_locate(IntPtr pair, int part, long ordinal, out int whichR2, out long recordIndex);
+    [DllImport(L)] public static extern void pp_pair_free(IntPtr pair);
+
+    // GPU-assisted CreateIndex, first slice: every deflate block's first bit and output offset
+    [DllImport(L)] public static unsafe extern int pp_scan_blocks(IntPtr ctx, byte* gz, nuint gzLen, long segmentBytes, long* startBits, long* outOffsets, long cap, out long count, out long endBit, out long totalOut, out float kernelMs, out int passes);
+}
+
+internal static class PpJobFlags   // include/ppb200.h
+{
+    public const uint Strict = 1, ZeroCopy = 2, Pipeline = 4, CompactWindows = 8;
 }
 
 [StructLayout(LayoutKind.Sequential)]
@@ -72,4 +101,14 @@ internal struct pp_job_info
 internal struct pp_chunk_info
 {
     public int status, prefix_len; public long inflated, records, record_base; public uint parse_end, flags;
+}
+[StructLayout(LayoutKind.Sequential)]
+internal struct pp_multi_info
+{
+    public int n_parts, n_chunks; public long total_records, total_bytes, compressed_bytes; public int status, pad;
+}
+[StructLayout(LayoutKind.Sequential)]
+internal struct pp_pair_info
+{
+    public int n_parts, topup_chunks; public long records_r1, records_r2, pairs; public int status, pad;
 }

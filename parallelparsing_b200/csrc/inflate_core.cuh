@@ -964,6 +964,7 @@ PP_DEV SAddr saddr(const volatile void *p) { return (uint8_t *)p; }
 PP_DEV uint32_t lds_u32(SAddr a, uint32_t off) { uint32_t v; memcpy(&v, a + off, 4); return v; }
 PP_DEV uint32_t lds_u16(SAddr a, uint32_t off) { uint16_t v; memcpy(&v, a + off, 2); return v; }
 PP_DEV void sts_u16(SAddr a, uint32_t off, uint32_t v) { const uint16_t x = (uint16_t)v; memcpy(a + off, &x, 2); }
+PP_DEV void sts_u32(SAddr a, uint32_t off, uint32_t v) { memcpy(a + off, &v, 4); }
 #else
 typedef uint32_t SAddr;
 PP_DEV SAddr saddr(const volatile void *p) { return (uint32_t)__cvta_generic_to_shared(const_cast<const void *>(p)); }
@@ -982,6 +983,10 @@ PP_DEV uint32_t lds_u16(SAddr a, uint32_t off)
 PP_DEV void sts_u16(SAddr a, uint32_t off, uint32_t v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + off), "h"((uint16_t)v) : "memory");
+}
+PP_DEV void sts_u32(SAddr a, uint32_t off, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + off), "r"(v) : "memory");
 }
 #endif
 PP_DEV uint32_t res_pos(uint32_t q) { return q; }
@@ -1082,41 +1087,54 @@ template <bool FULL>
 PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask, const uint32_t *wprev,
                         const uint8_t *vbase, uint32_t tb, uint32_t a, uint32_t vend, int32_t near_lo, uint32_t t)
 {
+    // A lane owns byte PAIRS: bytes 64 s + 2 lane, + 1 of the warp's 512 (s = 0..7).  The two bytes share
+    // the mask word, the head search and — unless the second byte starts a token — the entry.
     const uint32_t lane = t & 31u, warp = t >> 5;
-    const uint32_t qb = warp * (32u * kTileB) + lane;       // this lane's first byte; the others follow 32 apart
-    const uint32_t below = 0xffffffffu >> (31u - lane);     // bits 0..lane
+    const uint32_t qb = warp * (32u * kTileB) + 2u * lane;  // this lane's first byte; its other pairs follow 64 apart
+    const uint32_t bw = lane >> 4, bp = 2u * (lane & 15u);  // the pair's mask word within the step (0/1), its first bit there
+    const uint32_t below = 0xffffffffu >> (31u - bp);       // bits 0..bp
     const int32_t safe = near_lo - 1;                       // the byte just before the tile/window: final, inside the slot
     const SAddr ent_s = saddr(ent), res_s = saddr(sm.res) + 2u * qb;
-    const SAddr mask_w = saddr(mask) + 4u * (warp * (uint32_t)kTileB);   // the warp's 16 mask words
-    const SAddr prev_w = saddr(wprev) + 4u * (warp * (uint32_t)kTileB);
+    const uint32_t w0 = warp * (uint32_t)kTileB + bw;       // mask word of the lane's pair in step 0; + 2 per step
+    const SAddr mask_w = saddr(mask) + 4u * w0, prev_w = saddr(wprev) + 4u * w0;
     const int32_t vq = (int32_t)(tb + qb);                  // virtual index of the lane's first byte
 #pragma unroll
-    for (int h = 0; h < kTileB; h += 8) {
+    for (int h = 0; h < kTileB / 2; h += 4) {
         uint32_t e[8];
         int32_t sv[8];
         uint32_t b[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int s = h + j;                            // step: byte qb + 32 s lies in mask word warp * 16 + s
-            e[j] = 0x8000u;                                 // bytes outside the window: harmless literals
-            sv[j] = safe;
-            const uint32_t v = (uint32_t)vq + 32u * (uint32_t)s;
-            if (FULL || (v >= a && v < vend)) {
-                const uint32_t m = lds_u32(mask_w, 4u * (uint32_t)s) & below;
-                // the byte's token: the last head at or before it — in this word, else the last one before the word
-                const uint32_t hp = m ? 32u * (warp * (uint32_t)kTileB + (uint32_t)s) + 31u - clz32(m)
-                                      : lds_u32(prev_w, 4u * (uint32_t)s);
-                uint32_t x = lds_u16(ent_s, 2u * hp);
-                const uint32_t i = qb + 32u * (uint32_t)s - hp;
-                if (i > x) {                                // a match (never true for a literal: x >= 0x8000 > i) whose
-                    const uint32_t dist = x + 1u;           // offset reached its distance: overlapping run, take the same byte
-                    x = dist * (div_small(i, dist) + 1u) - 1u;  // one or more periods earlier, in front of the match
-                }
-                // virtual index of the source; for a literal (0x8000 | byte) a harmless address at most 256
-                // bytes back (there is always that much in front of an output: a 32 KB window, or the
-                // spare bytes the runtime keeps in front of the first slot)
-                sv[j] = (int32_t)v - (int32_t)(x & 0x7fffu) - 1;
-                e[j] = x;
+        for (int j = 0; j < 4; j++) {
+            const int s = h + j;
+            const uint32_t q0 = qb + 64u * (uint32_t)s;
+            const uint32_t v0 = (uint32_t)vq + 64u * (uint32_t)s;
+            const uint32_t mw = lds_u32(mask_w, 8u * (uint32_t)s);
+            const uint32_t m0 = mw & below;
+            // first byte's token: the last head at or before it — in this word, else the last one before the word
+            const uint32_t hp0 = m0 ? 32u * (w0 + 2u * (uint32_t)s) + 31u - clz32(m0) : lds_u32(prev_w, 8u * (uint32_t)s);
+            uint32_t x0 = lds_u16(ent_s, 2u * hp0);
+            uint32_t i0 = q0 - hp0;
+            // second byte: a new token if its head bit is set, else the same token one byte further
+            uint32_t x1 = x0, i1 = i0 + 1u;
+            if ((mw >> (bp + 1u)) & 1u) { x1 = lds_u16(ent_s, 2u * (q0 + 1u)); i1 = 0u; }
+            if (i0 > x0) {                                  // a match (never true for a literal: x >= 0x8000 > i) whose
+                const uint32_t dist = x0 + 1u;              // offset reached its distance: overlapping run, take the same byte
+                x0 = dist * (div_small(i0, dist) + 1u) - 1u;  // one or more periods earlier, in front of the match
+            }
+            if (i1 > x1) {
+                const uint32_t dist = x1 + 1u;
+                x1 = dist * (div_small(i1, dist) + 1u) - 1u;
+            }
+            // virtual index of the source; for a literal (0x8000 | byte) a harmless address at most 256
+            // bytes back (there is always that much in front of an output: a 32 KB window, or the
+            // spare bytes the runtime keeps in front of the first slot)
+            sv[2 * j] = (int32_t)v0 - (int32_t)(x0 & 0x7fffu) - 1;
+            sv[2 * j + 1] = (int32_t)v0 - (int32_t)(x1 & 0x7fffu);
+            e[2 * j] = x0;
+            e[2 * j + 1] = x1;
+            if (!FULL) {                                    // bytes outside the window: harmless literals
+                if (v0 < a || v0 >= vend) { e[2 * j] = 0x8000u; sv[2 * j] = safe; }
+                if (v0 + 1u < a || v0 + 1u >= vend) { e[2 * j + 1] = 0x8000u; sv[2 * j + 1] = safe; }
             }
         }
         // unconditional loads (a source inside the tile reads the byte just before the tile instead), so
@@ -1124,10 +1142,11 @@ PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask,
 #pragma unroll
         for (int j = 0; j < 8; j++) b[j] = vbase[sv[j] < safe ? sv[j] : safe];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t o = e[j];
-            if (!(o & 0x8000u)) o = sv[j] < near_lo ? 0x8000u | b[j] : (uint32_t)(sv[j] - (int32_t)tb);
-            sts_u16(res_s, 64u * (uint32_t)(h + j), o);
+        for (int j = 0; j < 4; j++) {
+            uint32_t o0 = e[2 * j], o1 = e[2 * j + 1];
+            if (!(o0 & 0x8000u)) o0 = sv[2 * j] < near_lo ? 0x8000u | b[2 * j] : (uint32_t)(sv[2 * j] - (int32_t)tb);
+            if (!(o1 & 0x8000u)) o1 = sv[2 * j + 1] < near_lo ? 0x8000u | b[2 * j + 1] : (uint32_t)(sv[2 * j + 1] - (int32_t)tb);
+            sts_u32(res_s, 128u * (uint32_t)(h + j), (o0 & 0xffffu) | (o1 << 16));
         }
     }
 }
