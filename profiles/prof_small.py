@@ -21,12 +21,12 @@ dev = pp.Device(0)
 job = pp.Job(dev, ix, gz.size)
 import ctypes as C  # noqa: E402
 L = pp.lib()
-ph = (C.c_ulonglong * 16)()
-L.pp_internal_phase_cycles(ph, 16)
+ph = (C.c_ulonglong * 20)()
+L.pp_internal_phase_cycles(ph, 20)
 for _ in range(iters):
     info = job.run(gz)
-n = L.pp_internal_phase_cycles(ph, 16)
-names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other", "r.expand", "r.gather", "r.chase", "h.parse", "h.lit"]
+n = L.pp_internal_phase_cycles(ph, 20)
+names = ["stage", "header", "guess", "sync", "scan", "emit", "resolve", "stored", "other", "r.expand", "r.expand+gather", "r.chase+store+scatter", "h.parse", "h.lit", "wait"]
 tot = sum(ph[i] for i in range(n)) or 1
 print("phase share of CTA time:", ", ".join(f"{names[i]} {100*ph[i]/tot:.1f}%" for i in range(n)),
       f"| cycles/iter/CTA-sum {tot/iters:.3e}")
