@@ -1,11 +1,14 @@
 """BASELINE config 3: paired-end R1/R2, N pairs x 150 bp (two Generator streams, seeds 0 and 1), chunk
-10 000, both files decoded on ONE GPU — back to back on one context, and concurrently on two
-contexts/host threads (what PairedFASTQ does).  Prints one JSON line.
-    python profiles/paired_bench.py [pairs] [steps]"""
+10 000, through the paired DecompressAll of the C ABI (pp_pair_decompress_all) on the GPUs given:
+both files partitioned over them, R1 and R2 decoded concurrently per GPU, mates paired by ordinal,
+top-up chunks so that every mate is co-resident.  Every step is a cold call with host buffers (plan,
+allocations from the pool, pull from pinned host memory, kernels, results to the host) + free.
+Checks: pair count, mates located on the same part for sampled ordinals, both files' digests equal
+the single-file jobs'.  Prints one JSON line.
+    python profiles/paired_bench.py [pairs] [steps] [n_gpus]"""
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,50 +20,46 @@ import parallelparsing_b200 as pp  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-__import__("__graft_entry__").build()
+ngpu = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+bench.make_native(["tools", os.path.join("parallelparsing_b200", "csrc")])
 files = []
 for seed in (0, 1):
-    gz_path, idx_path = bench.make_corpus(pairs, 150, seed, 10000)
-    gz = np.fromfile(gz_path, np.uint8)
-    pin, ptr = pp.pinned_copy(gz)
+    gz_path = bench.make_gz(pairs, 150, seed, 10000)
+    idx_path = bench.corpus_paths(pairs, 150, seed, 10000)[2]
+    if not os.path.exists(idx_path):
+        pp.IndexIO.Serialize(pp.Core.BuildDeflateIndex(gz_path, 10000), idx_path)
+    pin, ptr = pp.pinned_copy(np.fromfile(gz_path, np.uint8))
     files.append((pin, pp.IndexIO.Deserialize(idx_path), ptr))
-devs = [pp.Device(0), pp.Device(0)]
-jobs = [pp.Job(devs[i], files[i][1], files[i][0].size, strict=True, zero_copy=True) for i in range(2)]
+devices = list(range(ngpu))
 
 
-def run(i):
-    jobs[i].upload(files[i][2])
-    jobs[i].execute()
-    jobs[i].download()
+def one():
+    return pp.PairedDecompressAll(devices, files[0][1], files[0][0], files[1][1], files[1][0], zero_copy=True)
 
 
-def both(concurrent):
-    if not concurrent:
-        run(0)
-        run(1)
-        return
-    th = threading.Thread(target=run, args=(1,))
-    th.start()
-    run(0)
-    th.join()
-
-
-res = {}
-for mode in (False, True):
-    for _ in range(3):
-        both(mode)
-    t = time.perf_counter()
-    for _ in range(steps):
-        both(mode)
-    res[mode] = (time.perf_counter() - t) / steps
-infos = [j.info() for j in jobs]
-assert infos[0].status == 0 and infos[1].status == 0
-assert infos[0].total_records == infos[1].total_records == pairs, (infos[0].total_records, infos[1].total_records)
-U = infos[0].total_bytes + infos[1].total_bytes
+pe = one()
+info = pe.info()
+assert pe.status == 0 and info.pairs == pairs == info.records_r1 == info.records_r2, (pe.status, info.pairs)
+ubytes = 0
+for g in range(ngpu):
+    j1, base1, r2 = pe.part(g)
+    ubytes += j1.info().total_bytes
+    n1 = j1.info().total_records
+    for r in (0, n1 // 3, n1 - 1):
+        w, idx = pe.locate(g, base1 + r)      # the mate is on this part
+        assert 0 <= idx < r2[w][0].info().total_records
+ubytes2 = int(files[1][1].scalars()[0][-1])
+topup = info.topup_chunks
+pe.free()
+for _ in range(2):
+    one().free()
+t0 = time.perf_counter()
+for _ in range(steps):
+    one().free()
+dt = (time.perf_counter() - t0) / steps
 print(json.dumps({
-    "workload": f"paired-end, {pairs} pairs x 150bp (Generator seeds 0/1), gzip -6, chunk 10000, one GPU, "
-                "pull mode (kernels read the compressed bytes from pinned host memory) + results to host per file, host wall clock",
-    "pairs": pairs, "uncompressed_bytes": U, "chunks": [infos[0].n_chunks, infos[1].n_chunks],
-    "sequential": {"ms_per_step": res[False] * 1e3, "GB/s": U / res[False] / 1e9, "pairs_per_s": pairs / res[False]},
-    "concurrent": {"ms_per_step": res[True] * 1e3, "GB/s": U / res[True] / 1e9, "pairs_per_s": pairs / res[True]},
-    "steps": steps}))
+    "metric": "paired DecompressAll (R1 + R2) uncompressed GB/s", "value": (ubytes + ubytes2) / dt / 1e9, "unit": "GB/s",
+    "pairs_per_s": pairs / dt, "ms_per_step": dt * 1e3, "n_gpus": ngpu, "steps": steps,
+    "config": {"workload": f"Generator seeds 0/1, {pairs} pairs x 150bp, gzip -6, chunk 10000, paired by ordinal (PP_JOB_STRICT)",
+               "topup_chunks": topup, "uncompressed_bytes": ubytes + ubytes2},
+    "what": "cold pp_pair_decompress_all + pp_pair_free per step, pull mode, host wall clock"}))
