@@ -60,11 +60,36 @@ int main(int argc, char **argv)
     }
     printf("rebuilt_points %d\n", pp_index_count(c));
 
+    /* the multi-GPU split (host code): contiguous, ordered, covering */
+    {
+        int32_t first[5], cnt[5], next = 0, total = 0;
+        CHECK(pp_partition_chunks(ix, 5, first, cnt));
+        for (int r = 0; r < 5; r++) {
+            if (first[r] != next || cnt[r] < 0) return 8;
+            next += cnt[r];
+            total += cnt[r];
+        }
+        if (total != n - 1) return 9;
+        printf("partition5 %d %d %d %d %d\n", cnt[0], cnt[1], cnt[2], cnt[3], cnt[4]);
+    }
+
     /* the device: either it opens (B200 box) or every entry point says so — never a CPU fallback */
     pp_ctx *ctx = NULL;
     const int rc = pp_open(0, &ctx);
     printf("open %d %s\n", rc, pp_strerror(rc));
     if (rc == 0) pp_close(ctx);
+    {
+        /* the one-call entry points over several GPUs / paired files fail the same loud way without a device */
+        const int32_t devs[1] = {0};
+        pp_multi *m = NULL;
+        pp_pair *pr = NULL;
+        const uint8_t dummy[16] = {0};
+        const int rm = pp_decompress_all_multi(devs, 1, ix, dummy, sizeof dummy, 0, &m);
+        const int rp = pp_pair_decompress_all(devs, 1, ix, dummy, sizeof dummy, ix, dummy, sizeof dummy, 0, &pr);
+        printf("multi_nodata %d\npair_nodata %d\n", rm, rp);
+        if (m) pp_multi_free(m);
+        if (pr) pp_pair_free(pr);
+    }
     pp_index_free(c);
     pp_index_free(b);
     pp_index_free(a);

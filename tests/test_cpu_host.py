@@ -254,9 +254,12 @@ def test_c_abi_from_plain_c(tmp_path):
     assert int(kv["chunk_max_bytes"]) == ix.ChunkMaxBytes
     want = sum(ix[i].Output * 31 + ix[i].Input * 7 + ix[i].Bits for i in range(ix.Count)) & 0xFFFFFFFFFFFFFFFF
     assert int(kv["point_sum"]) == want
+    assert [int(x) for x in kv["partition5"].split()] == [n for _, n in pp.partition_chunks(ix, 5)]
     import torch
     code = int(kv["open"].split()[0])
     assert code == (0 if torch.cuda.is_available() else -101), kv["open"]
+    if not torch.cuda.is_available():   # no device: the multi-GPU and paired calls say so, they never fall back
+        assert int(kv["multi_nodata"]) == -101 and int(kv["pair_nodata"]) == -101
 
 
 def test_record_cap_verdict_matches_oracle_around_the_limit():
