@@ -726,33 +726,6 @@ PP_DEV int dynamic_tables(const Sm &sm, uint32_t pos, uint32_t *pos_out)
 struct Seg {
     uint32_t end, out, flag, ntok;
 };
-// Token rows live in global scratch but are written (EMIT) and read back (SCATTER) within one window:
-// they are marked evict-last in L2 so that the output stream passing through the same cache does not
-// push them out to DRAM and back (2.1 GB of tokens per 3.9 GB of output at 10 M reads).
-#ifdef PP_HOST_EMU
-typedef int TokPolicy;
-PP_DEV TokPolicy tok_policy() { return 0; }
-PP_DEV void st_tok(uint32_t *p, uint32_t v, TokPolicy) { *p = v; }
-PP_DEV uint32_t ld_tok(const uint32_t *p, TokPolicy) { return *p; }
-#else
-typedef uint64_t TokPolicy;
-PP_DEV TokPolicy tok_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-PP_DEV void st_tok(uint32_t *p, uint32_t v, TokPolicy pol)
-{
-    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-}
-PP_DEV uint32_t ld_tok(const uint32_t *p, TokPolicy pol)
-{
-    uint32_t v;
-    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-#endif
 PP_DEV uint32_t tok_pack(uint32_t entry, uint32_t p0, uint32_t rshift)
 {
     return entry | ((p0 & ((1u << rshift) - 1u)) << 16) | ((p0 >> rshift) << 30);
@@ -770,7 +743,6 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
     uint32_t cnt = 64u - sh;
     wp += 2;
     uint32_t out = 0, flag = F_NONE, k = 0;
-    const TokPolicy pol = tok_policy();
     // One loop body for literals and matches (the lanes of a warp are in different kinds of symbol
     // all the time: a branch per kind makes every iteration pay for both): the distance lookup is
     // done for a literal too, on whatever bits follow, and consumes nothing.
@@ -804,8 +776,8 @@ PP_DEV Seg decode_seg(const Sm &sm, uint32_t start, uint32_t limit, uint32_t *to
         const uint32_t n = ism ? len : 1u;
         if (WRITE) {
             const uint32_t p0 = o + out, p1 = p0 + n - 1u;
-            st_tok(row + k++, tok_pack(ism ? dist - 1u : e_val(e), p0, rshift), pol);
-            if ((p0 ^ p1) >> rshift) st_tok(row + k++, tok_pack(dist - 1u, (p1 >> rshift) << rshift, rshift), pol);  // only a match crosses
+            row[k++] = tok_pack(ism ? dist - 1u : e_val(e), p0, rshift);
+            if ((p0 ^ p1) >> rshift) row[k++] = tok_pack(dist - 1u, (p1 >> rshift) << rshift, rshift);  // only a match crosses
         }
         out += n;
     }
@@ -1045,9 +1017,7 @@ PP_DEV void scatter_row(const Sm &sm, const uint32_t *tok, const TileTok &tt, ui
     const uint32_t *rp = tok + row * (uint32_t)kTokRows;
     uint16_t *ent = tt.ent + buf * R;
     uint32_t *mask = tt.mask + buf * (R / 32u);
-    const TokPolicy pol = tok_policy();
 #ifdef PP_HOST_EMU
-    (void)pol;
     (void)lane;
     uint32_t k = k0;
     for (; k < nt; k++) {
@@ -1065,7 +1035,7 @@ PP_DEV void scatter_row(const Sm &sm, const uint32_t *tok, const TileTok &tt, ui
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const uint32_t k = k0 + lane + 32u * (uint32_t)u;
-            tv[u] = k < nt ? ld_tok(rp + k, pol) : ((tag ^ 1u) << 30);  // past the row's end: a tag that never matches
+            tv[u] = k < nt ? rp[k] : ((tag ^ 1u) << 30);  // past the row's end: a tag that never matches
         }
         uint32_t cnt = 0;
 #pragma unroll
@@ -1604,21 +1574,6 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         PP_PHASE(PH_OTHER);
         if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
         if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
-#ifndef PP_HOST_EMU
-        // The next window starts about T sub-sequences further on: ask L2 for those bytes now, so that the
-        // next STAGE finds them on the device instead of paying a PCIe round trip when `comp` is pinned host
-        // memory (pull mode: staging cost every CTA 2.3 ms of a 23 ms step).  Not with a pipelined upload:
-        // those bytes may still be on their way.
-        if ((!gate || !gate->mark) && threadIdx.x == 0) {
-            const uint64_t nb = (base_byte + (uint64_t)T * (kSubW * 4u)) & ~(uint64_t)15;
-            if (nb + 16u <= comp_bytes) {
-                uint64_t len = 4ull * cww + 1024u;
-                if (nb + len > comp_bytes) len = (comp_bytes - nb) & ~(uint64_t)15;
-                if (len >= 16u)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(comp + nb), "r"((uint32_t)len) : "memory");
-            }
-        }
-#endif
         PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
         if (need_header) {
