@@ -646,44 +646,16 @@ static int job_queue_pieces(pp_job *j, cudaStream_t cs, bool first_only)
     const uint32_t n = (uint32_t)j->n;
     const uint32_t waves = (n + g.rows - 1) / g.rows;
     int nm = j->marks_used;
-    static bool use_batch = true;
-    std::vector<void *> dsts, srcs;
-    std::vector<size_t> sizes;
     for (uint32_t w = 0; w < waves; w++) {
         const uint32_t k0 = w * g.rows, k1 = std::min(n, k0 + g.rows);
         for (uint32_t c = 0; c < g.ncols; c++) {
             const bool is_first = w == 0 && c == 0;
             if (first_only != is_first) continue;
-            // one BATCHED copy per column (cudaMemcpyBatchAsync: a single driver call for the ~300 pieces; issued
-            // one by one they cost ~6 us of host time each — more than the link needs to move them)
-            dsts.clear(); srcs.clear(); sizes.clear();
             for (uint32_t k = k0; k < k1; k++) {
                 const uint64_t s = j->starts[k], e = j->starts[k + 1];
                 const uint64_t lo = s + (uint64_t)c * g.col_bytes;
                 const uint64_t hi = c + 1 == g.ncols ? e : std::min<uint64_t>(e, lo + g.col_bytes);
-                if (lo < hi) {
-                    dsts.push_back(j->d_comp + lo);
-                    srcs.push_back(const_cast<uint8_t *>(src0 + lo));
-                    sizes.push_back((size_t)(hi - lo));
-                }
-            }
-            if (!dsts.empty()) {
-                bool batched = false;
-                if (use_batch && dsts.size() > 1) {
-                    cudaMemcpyAttributes at{};
-                    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-                    size_t idx0 = 0, fail = 0;
-                    if (cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, cs) ==
-                        cudaSuccess)
-                        batched = true;
-                    else {
-                        cudaGetLastError();
-                        use_batch = false;  // an older driver: fall back to one call per piece
-                    }
-                }
-                if (!batched)
-                    for (size_t i = 0; i < dsts.size(); i++)
-                        CK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, cs));
+                if (lo < hi) CK(cudaMemcpyAsync(j->d_comp + lo, src0 + lo, hi - lo, cudaMemcpyHostToDevice, cs));
             }
             const bool last = w + 1 == waves && c + 1 == g.ncols;
             j->h_marks[nm] = last ? ~0ull : (unsigned long long)w * (g.ncols + 1u) + c + 1u;
