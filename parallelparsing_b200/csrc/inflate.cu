@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
         d.in_bit += 8ull * comp_shift;
         d.in_limit += comp_shift;
-        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate, (uint32_t)k);
+        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();

@@ -1485,50 +1485,33 @@ PP_DEV void stored_copy(const Sm &sm, const uint8_t *src, uint8_t *dst, uint32_t
 
 // Whole chunk: Core.ExtractDeflateIndex for one (from, to) pair.
 // scratch: this CTA's token rows + group index (global memory, scratch_words_for(T) words).
-// Pipelined upload: the compressed range reaches the device on a copy stream while the kernel runs.
-// The resident CTAs work on `rows` consecutive chunks at once ("a wave"), all at the same modest rate,
-// and the next wave is wanted all at once when they finish — so a copy in file order leaves most of
-// them idle until "their" chunk arrives (measured: 3.3 ms per CTA of a 24 ms step, whatever the order of
-// pulls and copies, because by the end of the first wave 60 % of the bytes are wanted and the link has had
-// time for 40 %).  Instead every chunk's byte range is cut into COLUMNS of col_bytes and a wave is
-// delivered column by column (column 0 of all its chunks, then column 1, ...): every CTA gets its first
-// bytes at once and the copy engine only has to keep up with the decode.  The host publishes
-// mark = wave * (ncols + 1) + columns delivered (then "everything"); a CTA waits, window by window, for
-// the column that holds the bytes it is about to stage.
+// Pipelined upload: the compressed range reaches the device in file order, in pieces, on a copy stream
+// while the kernel runs; after every piece the host publishes the number of bytes in place (then
+// "everything").  A CTA waits, window by window, until the bytes it is about to stage are there.
+// (Tried and measured slower on 10 M reads, 24.0 ms pulled / 24.7 ms file order: delivering "waves" of
+// chunks column by column with 2-D copies so that every resident CTA gets its first bytes at once —
+// strided 64 KB rows reach only ~38 GB/s against 55 GB/s for plain copies, 27.6 ms; a first wave pulled
+// by the kernel while the copy engine brings the rest — the two halve each other's link, 24.7 ms.)
 struct ByteGate {
     const volatile unsigned long long *mark;  // device memory, written by the copy stream (null: no gate)
-    const uint64_t *starts;                    // [n + 1] first byte of every chunk's piece range; starts[n] = total
-    uint32_t rows;                             // chunks per wave (= resident CTAs)
-    uint32_t col_bytes, ncols;                 // the last column takes whatever is left of a chunk
-    uint32_t n;                                // chunks
+    uint64_t total;                            // bytes of the range
     uint64_t shift;                            // bytes the kernel's base pointer was moved down (alignment)
 };
-PP_HD unsigned long long gate_need(const ByteGate &g, uint32_t k, uint64_t b, uint64_t start_k)
-{
-    uint64_t c = b > start_k ? (b - start_k) / g.col_bytes : 0u;
-    if (c >= g.ncols) c = g.ncols - 1u;
-    return (unsigned long long)(k / g.rows) * (g.ncols + 1u) + c + 1u;
-}
-// Wait until bytes [lo, hi) (kernel coordinates) of chunk k — and of chunk k+1 where the range runs into
-// it — are in place.  One thread polls; bounded (~4 s): a copy that never arrives must not hang the GPU.
-// Returns false on time-out.
-PP_DEV bool gate_wait(const Sm &sm, const ByteGate *g, uint32_t k, uint64_t lo, uint64_t hi)
+PP_HD unsigned long long gate_need(const ByteGate &g, uint64_t hi) { return hi < g.total ? hi : g.total; }
+// Wait until bytes [lo, hi) (kernel coordinates) are in place.  One thread polls; bounded (~4 s): a copy
+// that never arrives must not hang the GPU.  Returns false on time-out.
+PP_DEV bool gate_wait(const Sm &sm, const ByteGate *g, uint64_t lo, uint64_t hi)
 {
 #ifdef PP_HOST_EMU
-    (void)sm; (void)g; (void)k; (void)lo; (void)hi;
+    (void)sm; (void)g; (void)lo; (void)hi;
     return true;
 #else
     if (!g || !g->mark) return true;
     if (threadIdx.x == 0) {
-        (void)lo;
+        lo = lo > g->shift ? lo - g->shift : 0u;
         hi = hi > g->shift ? hi - g->shift : 0u;
-        const uint64_t s = g->starts[k], e = g->starts[k + 1u];
-        const uint64_t last = hi < e ? hi : e;   // one past the last byte wanted inside this chunk's range
-        unsigned long long need = gate_need(*g, k, last ? last - 1u : 0u, s);
-        if (hi > e && k + 1u < g->n) {   // the window runs into the next chunk's first column (its first <= 128 bytes
-            const unsigned long long nx = gate_need(*g, k + 1u, e, e);   // are this chunk's last ones)
-            if (nx > need) need = nx;
-        }
+        (void)lo;
+        const unsigned long long need = gate_need(*g, hi);
         unsigned ok = 1;
         if (*g->mark < need) {
             const long long t0 = clock64();
@@ -1549,7 +1532,7 @@ PP_DEV bool gate_wait(const Sm &sm, const ByteGate *g, uint32_t k, uint64_t lo, 
 
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                           const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
-                          const ByteGate *gate = nullptr, uint32_t chunk_no = 0)
+                          const ByteGate *gate = nullptr)
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
@@ -1589,7 +1572,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
         PP_PHASE(PH_OTHER);
-        if (!gate_wait(sm, gate, chunk_no, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
+        if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
         if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
         PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
@@ -1608,7 +1591,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
                 uint32_t n = len;
                 if (n > out_len - produced) n = out_len - produced;
                 PP_SYNC();
-                if (!gate_wait(sm, gate, chunk_no, byte0, byte0 + n)) { status = -100; break; }
+                if (!gate_wait(sm, gate, byte0, byte0 + n)) { status = -100; break; }
                 stored_copy(sm, comp + byte0, out + produced, n);
                 produced += n;
                 bit = (byte0 + len) * 8u;

@@ -48,7 +48,7 @@ struct InflateLaunch {
 };
 // Optional host <-> kernel hand-shakes of the inflate kernel.
 struct InflateSync {
-    ppinf::ByteGate gate = {nullptr, nullptr, 1, 1, 1, 0, 0};  // pipelined upload: which bytes are in place (mark == null: all)
+    ppinf::ByteGate gate = {nullptr, 0, 0};  // pipelined upload: which bytes are in place (mark == null: all)
     uint32_t *done = nullptr;                             // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
 };
 int inflate_max_ctas_per_sm(int threads);

@@ -147,11 +147,7 @@ struct pp_job {
     // pipelined upload (PP_JOB_PIPELINE): pieces of the compressed range go over a copy stream while the
     // inflate kernel runs; after every piece the host publishes the bytes in place (d_avail)
     bool pipeline = false;
-    ppinf::ByteGate gate = {nullptr, nullptr, 1, 1, 1, 0, 0};  // see ByteGate
-    std::vector<uint64_t> starts;           // [n + 1] first byte of every chunk's piece range (host copy of gate.starts)
-    uint64_t *d_starts = nullptr;
-    const uint8_t *pending_src = nullptr;   // pieces still to be queued by pp_job_execute (all but wave 0 / column 0)
-    int marks_used = 0;
+    ppinf::ByteGate gate = {nullptr, 0, 0};  // see ByteGate
     unsigned long long *d_avail = nullptr;  // the gate's mark
     unsigned long long *h_marks = nullptr;  // pinned: mark values, one per column copy (+ reset, + "everything")
     int n_marks = 0;
@@ -336,7 +332,7 @@ void pp_job_free(pp_job *j)
     cudaStream_t st = j->st_alloc;
     for (void *p : {(void *)j->d_comp, (void *)j->d_lead, (void *)j->d_slots, (void *)j->d_descs, (void *)j->d_results,
                     (void *)j->d_pdesc, (void *)j->d_pout, (void *)j->d_totals, (void *)j->d_exact, (void *)j->d_lines,
-                    (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_starts, (void *)j->d_cwin,
+                    (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_cwin,
                     (void *)j->d_wdescs, (void *)j->d_wresults})
         pool_free(p, st);
     cudaFreeHost(j->h_arena);
@@ -484,25 +480,9 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
         {
             // one pinned + mapped allocation for every small host mirror (each cudaHostAlloc is a driver call)
             const size_t n1 = (size_t)std::max(n, 1);
-            // pipelined upload geometry (see ByteGate): waves of one chunk per resident CTA, every chunk's
-            // byte range cut into columns of 256 KB (at most 16: longer chunks get wider columns)
-            {
-                ppinf::ByteGate &g = j->gate;
-                g.n = (uint32_t)std::max(n, 0);
-                g.rows = (uint32_t)std::max(1, std::min(std::max(n, 1), ctx->inflate_cfg(n).grid));
-                j->starts.assign((size_t)n + 1, 0);
-                uint64_t maxlen = 1;
-                for (int k = 1; k < n; k++) j->starts[(size_t)k] = (j->descs[(size_t)k].in_bit >> 3) & ~(uint64_t)127;
-                j->starts[(size_t)n] = j->comp_copy;
-                for (int k = 0; k < n; k++) {
-                    if (j->starts[(size_t)k + 1] < j->starts[(size_t)k]) j->starts[(size_t)k + 1] = j->starts[(size_t)k];
-                    maxlen = std::max(maxlen, j->starts[(size_t)k + 1] - j->starts[(size_t)k]);
-                }
-                g.col_bytes = (uint32_t)std::max<uint64_t>(256u << 10, align_up((maxlen + 15) / 16, 64u << 10));
-                g.ncols = (uint32_t)std::max<uint64_t>(1, (maxlen + g.col_bytes - 1) / g.col_bytes);
-                const uint64_t waves = ((uint64_t)std::max(n, 1) + g.rows - 1) / g.rows;
-                j->n_marks = (int)(waves * g.ncols) + 2;
-            }
+            const uint64_t kPiece = 8ull << 20;   // pipelined upload: pieces of 8 MB
+            j->gate.total = j->comp_copy;
+            j->n_marks = (int)((j->comp_copy + kPiece - 1) / kPiece) + 2;
             auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
             const size_t o_res = 0, o_pd = o_res + up(sizeof(ChunkResult) * n1), o_po = o_pd + up(sizeof(ParseDesc) * n1),
                          o_tot = o_po + up(sizeof(ParseOut) * n1), o_wres = o_tot + up(sizeof(ScanTotals)),
@@ -540,9 +520,6 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
             // the marks (bytes in place after every piece) are filled in by pp_job_upload; until the
             // first upload nothing waits
             CK(pool_alloc(&j->d_avail, sizeof(unsigned long long), ctx->stream));
-            CK(pool_alloc(&j->d_starts, sizeof(uint64_t) * ((size_t)n + 1), ctx->stream));
-            CK(cudaMemcpyAsync(j->d_starts, j->starts.data(), sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice,
-                               ctx->stream));
             j->h_marks[0] = ~0ull;
             CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[0], sizeof(unsigned long long), cudaMemcpyHostToDevice,
                                ctx->stream));
@@ -633,42 +610,6 @@ int pp_job_create(pp_ctx *ctx, const pp_index *ix, size_t gz_len, int32_t first_
     return PP_OK;
 }
 
-}  // extern "C"
-
-// Pipelined upload: queue the copies of the compressed range, a wave of chunks at a time and column by
-// column (see ByteGate).  first_only: wave 0 / column 0 alone (pp_job_upload); else everything after it
-// (pp_job_execute, once the kernels are launched).
-static int job_queue_pieces(pp_job *j, cudaStream_t cs, bool first_only)
-{
-    const ppinf::ByteGate &g = j->gate;
-    const uint8_t *src0 = j->pending_src;
-    if (!src0 || j->n <= 0) return PP_OK;
-    const uint32_t n = (uint32_t)j->n;
-    const uint32_t waves = (n + g.rows - 1) / g.rows;
-    int nm = j->marks_used;
-    for (uint32_t w = 0; w < waves; w++) {
-        const uint32_t k0 = w * g.rows, k1 = std::min(n, k0 + g.rows);
-        for (uint32_t c = 0; c < g.ncols; c++) {
-            const bool is_first = w == 0 && c == 0;
-            if (first_only != is_first) continue;
-            for (uint32_t k = k0; k < k1; k++) {
-                const uint64_t s = j->starts[k], e = j->starts[k + 1];
-                const uint64_t lo = s + (uint64_t)c * g.col_bytes;
-                const uint64_t hi = c + 1 == g.ncols ? e : std::min<uint64_t>(e, lo + g.col_bytes);
-                if (lo < hi) CK(cudaMemcpyAsync(j->d_comp + lo, src0 + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-            }
-            const bool last = w + 1 == waves && c + 1 == g.ncols;
-            j->h_marks[nm] = last ? ~0ull : (unsigned long long)w * (g.ncols + 1u) + c + 1u;
-            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[nm++], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
-        }
-    }
-    j->marks_used = nm;
-    if (!first_only) j->pending_src = nullptr;
-    return PP_OK;
-}
-
-extern "C" {
-
 int pp_job_file_range(const pp_job *j, int64_t *file_offset, int64_t *length)
 {
     if (!j) return PP_E_ARG;
@@ -731,13 +672,13 @@ int pp_job_upload(pp_job *j, const uint8_t *gz)
             h2d += (int64_t)j->lead_bytes;
         }
         CK(cudaEventRecord(j->ev_lead, cs));
-        // wave 0 / column 0 now (every resident CTA's first bytes); the rest is queued by pp_job_execute
-        // right after the kernel launch, so that thousands of small copies do not delay the launch
-        j->pending_src = gz + j->comp_file_lo;
-        j->marks_used = nm;
-        {
-            int rc2 = job_queue_pieces(j, cs, true);
-            if (rc2 != PP_OK) return rc2;
+        const uint8_t *src0 = gz + j->comp_file_lo;
+        const uint64_t kPiece = 8ull << 20;
+        for (uint64_t off = 0; off < j->comp_copy; off += kPiece) {
+            const uint64_t len = std::min<uint64_t>(kPiece, j->comp_copy - off);
+            CK(cudaMemcpyAsync(j->d_comp + off, src0 + off, len, cudaMemcpyHostToDevice, cs));
+            j->h_marks[nm] = off + len >= j->comp_copy ? ~0ull : off + len;
+            CK(cudaMemcpyAsync(j->d_avail, &j->h_marks[nm++], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
         }
         h2d += (int64_t)j->comp_copy;
         // the kernels must not start before the mark was reset and the leads are in place
@@ -802,7 +743,6 @@ static int job_execute_locked(pp_job *j, bool stream_done)
     if (j->pipeline) {
         sy.gate = j->gate;
         sy.gate.mark = j->d_avail;
-        sy.gate.starts = j->d_starts;
     }
     if (stream_done) {
         void *dp = nullptr;
@@ -813,11 +753,6 @@ static int job_execute_locked(pp_job *j, bool stream_done)
                       st, sy));
     launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)
     CK(cudaEventRecord(j->ev[3], st));
-    if (j->pipeline && j->pending_src) {
-        // the kernel is running (or queued): now the rest of the compressed range, column by column
-        int rcp = job_queue_pieces(j, j->ctx->copy_stream, false);
-        if (rcp != PP_OK) return rcp;
-    }
     CK(cudaEventRecord(j->ev_exec_done, st));
     j->exec_pending = true;
     int rc = job_parse_stage(j, st, false, &launches);
