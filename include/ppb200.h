@@ -106,7 +106,8 @@ void pp_index_free(pp_index *ix);
 /* ----------------------------------------------------------------- Device */
 
 
-/* Open CUDA device `device`.  Fails with PP_E_NO_DEVICE when there is no GPU. */
+/* Open CUDA device `device`.  Fails with PP_E_NO_DEVICE when there is no GPU.  Free every job created
+ * on a context before closing it (a job's device memory is returned to the pool on its context's stream). */
 int pp_open(int32_t device, pp_ctx **out);
 void pp_close(pp_ctx *ctx);
 /* Pinned host memory for the compressed file (cudaHostAlloc / cudaHostRegister). */
