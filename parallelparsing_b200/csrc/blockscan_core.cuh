@@ -101,6 +101,9 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
     const uint32_t total = nlen + ndist;
     uint32_t have = 0, prev = 0;
     bool eob = false;
+    // running Kraft sums (in units of 2^-15): an over-subscribed set is rejected as soon as it overflows —
+    // at a wrong position the lengths are noise and that happens within a few dozen symbols, not after 300
+    int32_t room_l = 1 << 15, room_d = 1 << 15;
     while (have < total) {
         // one symbol of the code-length code, bit by bit (codes are MSB first, the stream LSB first)
         const uint32_t bits = bp_peek(b, p, 7);
@@ -129,9 +132,16 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
         else if (sym != 16u) prev = 0;
         for (uint32_t r = 0; r < rep; r++) {
             const uint32_t at = have + r;
-            if (at < nlen) { lcnt[val]++; if (at == 256u && val) eob = true; }
-            else dcnt[val]++;
+            if (at < nlen) {
+                lcnt[val]++;
+                if (at == 256u && val) eob = true;
+                if (val) room_l -= 1 << (15 - val);
+            } else {
+                dcnt[val]++;
+                if (val) room_d -= 1 << (15 - val);
+            }
         }
+        if (room_l < 0 || room_d < 0) return false;                  // over-subscribed
         have += rep;
     }
     if (!eob) return false;                                          // missing end-of-block code

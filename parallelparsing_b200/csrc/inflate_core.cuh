@@ -1098,56 +1098,55 @@ PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask,
     const uint32_t w0 = warp * (uint32_t)kTileB + bw;       // mask word of the lane's pair in step 0; + 2 per step
     const SAddr mask_w = saddr(mask) + 4u * w0, prev_w = saddr(wprev) + 4u * w0;
     const int32_t vq = (int32_t)(tb + qb);                  // virtual index of the lane's first byte
+    // All sixteen source loads of the lane are issued before the first one is consumed (one exposed
+    // round trip per tile instead of two): per byte only a 16-bit "what it will be" is kept meanwhile —
+    // the literal, the tile-relative index of an in-tile source, or kFar = "the byte being loaded".
+    constexpr uint32_t kFar = 0x7fffu;                      // not a tile index: R <= 16384
+    uint32_t pre[kTileB / 2];                               // two per word: bytes 64 s + 2 lane, + 1
+    uint32_t b[kTileB];
 #pragma unroll
-    for (int h = 0; h < kTileB / 2; h += 4) {
-        uint32_t e[8];
-        int32_t sv[8];
-        uint32_t b[8];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int s = h + j;
-            const uint32_t q0 = qb + 64u * (uint32_t)s;
-            const uint32_t v0 = (uint32_t)vq + 64u * (uint32_t)s;
-            const uint32_t mw = lds_u32(mask_w, 8u * (uint32_t)s);
-            const uint32_t m0 = mw & below;
-            // first byte's token: the last head at or before it — in this word, else the last one before the word
-            const uint32_t hp0 = m0 ? 32u * (w0 + 2u * (uint32_t)s) + 31u - clz32(m0) : lds_u32(prev_w, 8u * (uint32_t)s);
-            uint32_t x0 = lds_u16(ent_s, 2u * hp0);
-            uint32_t i0 = q0 - hp0;
-            // second byte: a new token if its head bit is set, else the same token one byte further
-            uint32_t x1 = x0, i1 = i0 + 1u;
-            if ((mw >> (bp + 1u)) & 1u) { x1 = lds_u16(ent_s, 2u * (q0 + 1u)); i1 = 0u; }
-            if (i0 > x0) {                                  // a match (never true for a literal: x >= 0x8000 > i) whose
-                const uint32_t dist = x0 + 1u;              // offset reached its distance: overlapping run, take the same byte
-                x0 = dist * (div_small(i0, dist) + 1u) - 1u;  // one or more periods earlier, in front of the match
-            }
-            if (i1 > x1) {
-                const uint32_t dist = x1 + 1u;
-                x1 = dist * (div_small(i1, dist) + 1u) - 1u;
-            }
-            // virtual index of the source; for a literal (0x8000 | byte) a harmless address at most 256
-            // bytes back (there is always that much in front of an output: a 32 KB window, or the
-            // spare bytes the runtime keeps in front of the first slot)
-            sv[2 * j] = (int32_t)v0 - (int32_t)(x0 & 0x7fffu) - 1;
-            sv[2 * j + 1] = (int32_t)v0 - (int32_t)(x1 & 0x7fffu);
-            e[2 * j] = x0;
-            e[2 * j + 1] = x1;
-            if (!FULL) {                                    // bytes outside the window: harmless literals
-                if (v0 < a || v0 >= vend) { e[2 * j] = 0x8000u; sv[2 * j] = safe; }
-                if (v0 + 1u < a || v0 + 1u >= vend) { e[2 * j + 1] = 0x8000u; sv[2 * j + 1] = safe; }
-            }
+    for (int s = 0; s < kTileB / 2; s++) {
+        const uint32_t q0 = qb + 64u * (uint32_t)s;
+        const uint32_t v0 = (uint32_t)vq + 64u * (uint32_t)s;
+        const uint32_t mw = lds_u32(mask_w, 8u * (uint32_t)s);
+        const uint32_t m0 = mw & below;
+        // first byte's token: the last head at or before it — in this word, else the last one before the word
+        const uint32_t hp0 = m0 ? 32u * (w0 + 2u * (uint32_t)s) + 31u - clz32(m0) : lds_u32(prev_w, 8u * (uint32_t)s);
+        uint32_t x0 = lds_u16(ent_s, 2u * hp0);
+        uint32_t i0 = q0 - hp0;
+        // second byte: a new token if its head bit is set, else the same token one byte further
+        uint32_t x1 = x0, i1 = i0 + 1u;
+        if ((mw >> (bp + 1u)) & 1u) { x1 = lds_u16(ent_s, 2u * (q0 + 1u)); i1 = 0u; }
+        if (i0 > x0) {                                      // a match (never true for a literal: x >= 0x8000 > i) whose
+            const uint32_t dist = x0 + 1u;                  // offset reached its distance: overlapping run, take the same byte
+            x0 = dist * (div_small(i0, dist) + 1u) - 1u;    // one or more periods earlier, in front of the match
         }
-        // unconditional loads (a source inside the tile reads the byte just before the tile instead), so
-        // that the eight loads of a batch are in flight together instead of one per branch
-#pragma unroll
-        for (int j = 0; j < 8; j++) b[j] = vbase[sv[j] < safe ? sv[j] : safe];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t o0 = e[2 * j], o1 = e[2 * j + 1];
-            if (!(o0 & 0x8000u)) o0 = sv[2 * j] < near_lo ? 0x8000u | b[2 * j] : (uint32_t)(sv[2 * j] - (int32_t)tb);
-            if (!(o1 & 0x8000u)) o1 = sv[2 * j + 1] < near_lo ? 0x8000u | b[2 * j + 1] : (uint32_t)(sv[2 * j + 1] - (int32_t)tb);
-            sts_u32(res_s, 128u * (uint32_t)(h + j), (o0 & 0xffffu) | (o1 << 16));
+        if (i1 > x1) {
+            const uint32_t dist = x1 + 1u;
+            x1 = dist * (div_small(i1, dist) + 1u) - 1u;
         }
+        // virtual index of the source; for a literal (0x8000 | byte) a harmless address at most 256
+        // bytes back (there is always that much in front of an output: a 32 KB window, or the
+        // spare bytes the runtime keeps in front of the first slot)
+        int32_t sv0 = (int32_t)v0 - (int32_t)(x0 & 0x7fffu) - 1;
+        int32_t sv1 = (int32_t)v0 - (int32_t)(x1 & 0x7fffu);
+        if (!FULL) {                                        // bytes outside the window: harmless literals
+            if (v0 < a || v0 >= vend) { x0 = 0x8000u; sv0 = safe; }
+            if (v0 + 1u < a || v0 + 1u >= vend) { x1 = 0x8000u; sv1 = safe; }
+        }
+        // unconditional loads (a source inside the tile reads the byte just before the tile instead)
+        b[2 * s] = vbase[sv0 < safe ? sv0 : safe];
+        b[2 * s + 1] = vbase[sv1 < safe ? sv1 : safe];
+        const uint32_t p0 = (x0 & 0x8000u) ? x0 : (sv0 < near_lo ? kFar : (uint32_t)(sv0 - (int32_t)tb));
+        const uint32_t p1 = (x1 & 0x8000u) ? x1 : (sv1 < near_lo ? kFar : (uint32_t)(sv1 - (int32_t)tb));
+        pre[s] = (p0 & 0xffffu) | (p1 << 16);
+    }
+#pragma unroll
+    for (int s = 0; s < kTileB / 2; s++) {
+        uint32_t o0 = pre[s] & 0xffffu, o1 = pre[s] >> 16;
+        if (o0 == kFar) o0 = 0x8000u | b[2 * s];
+        if (o1 == kFar) o1 = 0x8000u | b[2 * s + 1];
+        sts_u32(res_s, 128u * (uint32_t)s, o0 | (o1 << 16));
     }
 }
 
