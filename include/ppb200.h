@@ -321,6 +321,9 @@ int pp_partition_chunks(const pp_index *ix, int32_t parts, int32_t *first_chunk,
  */
 int pp_decompress_all_multi(const int32_t *devices, int32_t n_devices, const pp_index *ix, const uint8_t *gz,
                             size_t gz_len, uint32_t flags, pp_multi **out);
+/* pp_decompress_all_multi and pp_pair_decompress_all borrow their per-GPU contexts (stream, token scratch)
+ * from a process-wide cache and return them when the handle is freed; this closes the idle ones. */
+void pp_release_cached_contexts(void);
 int pp_multi_info_get(const pp_multi *m, pp_multi_info *out);
 /* Part `part`: its job (owned by the handle: do not free), its device, the global ordinal of its first record. */
 int pp_multi_part(const pp_multi *m, int32_t part, pp_job **job, int32_t *device, int64_t *record_base);

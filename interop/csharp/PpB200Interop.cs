@@ -68,6 +68,7 @@ internal static class LibPpB200
     [DllImport(L)] public static extern int pp_multi_info_get(IntPtr multi, out pp_multi_info info);
     [DllImport(L)] public static extern int pp_multi_part(IntPtr multi, int part, out IntPtr job, out int device, out long recordBase);
     [DllImport(L)] public static extern void pp_multi_free(IntPtr multi);
+    [DllImport(L)] public static extern void pp_release_cached_contexts();
 
     // paired-end R1/R2 (README.md:9)
     [DllImport(L)] public static unsafe extern int pp_pair_decompress_all(int* devices, int nDevices, IntPtr index1, byte* gz1, nuint gz1Len, IntPtr index2, byte* gz2, nuint gz2Len, uint flags, out IntPtr pair);

@@ -105,6 +105,7 @@ SYMBOLS = [
     ("pp_multi_info_get", C.c_int, [_p, C.POINTER(PPMultiInfo)]),
     ("pp_multi_part", C.c_int, [_p, _i32, _PP, C.POINTER(_i32), C.POINTER(_i64)]),
     ("pp_multi_free", None, [_p]),
+    ("pp_release_cached_contexts", None, []),
     ("pp_pair_decompress_all", C.c_int, [_p, _i32, _p, _p, _sz, _p, _p, _sz, _u32, _PP]),
     ("pp_pair_info_get", C.c_int, [_p, C.POINTER(PPPairInfo)]),
     ("pp_pair_part", C.c_int, [_p, _i32, _PP, C.POINTER(_i64), C.POINTER(_i32)]),

@@ -59,6 +59,28 @@ PP_HD uint32_t bp_peek(const BitPeek &b, uint64_t pos, uint32_t n)  // n <= 25
     return (uint32_t)(v >> s) & ((1u << n) - 1u);
 }
 
+// The cheap front of the probe: block type, symbol counts, and a COMPLETE code-length code (zlib
+// inflate_table, type CODES).  About 1 % of random bit positions pass.
+PP_HD bool probe_cheap(const BitPeek &b, uint64_t pos)
+{
+    const uint32_t h = bp_peek(b, pos, 17);
+    if (((h >> 1) & 3u) != 2u) return false;                         // BTYPE
+    const uint32_t nlen = ((h >> 3) & 31u) + 257u, ndist = ((h >> 8) & 31u) + 1u, ncode = ((h >> 13) & 15u) + 4u;
+    if (nlen > 286u || ndist > 30u) return false;
+    uint64_t p = pos + 17u;
+    int32_t left = 1 << 7;                                           // Kraft sum in units of 2^-7
+    for (uint32_t i = 0; i < ncode; i += 8u) {                       // eight 3-bit lengths per peek
+        const uint32_t m = ncode - i < 8u ? ncode - i : 8u;
+        const uint32_t v = bp_peek(b, p, 3u * m);
+        p += 3u * m;
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t l = (v >> (3u * k)) & 7u;
+            if (l) left -= 1 << (7 - l);
+        }
+    }
+    return left == 0;
+}
+
 // Is `pos` the first bit of a VALID dynamic-Huffman block header (RFC 1951 3.2.7 under zlib's checks)?
 PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
 {
@@ -158,6 +180,15 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
     return true;
 }
 
+PP_DEV uint32_t atomic_inc_u32(uint32_t *p)   // returns the old value
+{
+#ifdef PP_HOST_EMU
+    return (*p)++;
+#else
+    return atomicAdd(p, 1u);
+#endif
+}
+
 // ---- WALK: the CTA follows the blocks of one segment -------------------------------------------
 PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp, uint64_t comp_bytes, uint64_t shift_bits,
                          BlockRec *recs, ScanSegOut &out, uint32_t &stage_phase)
@@ -171,17 +202,46 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
         bp.nw = comp_bytes / 4u;
         bp.shift = shift_bits;
         uint64_t found = ~0ull;
-        for (uint64_t base = in.start_bit; base < in.end_bit && found == ~0ull; base += (uint64_t)T) {
+        // Rounds of T x kSpan positions.  Pass 1: every thread runs the cheap filter over kSpan positions
+        // and appends the survivors (~1 %) to a list in shared memory; pass 2: one survivor per THREAD
+        // through the full probe (a serial decode of up to ~300 code lengths) — all lanes busy with
+        // their own candidate instead of one lane per warp grinding while the others wait.
+        constexpr uint32_t kSpan = 32, kCap = 4096;                  // list: kCap u32 in the resolve tile buffer (>= 16 KB at T >= 512)
+        uint32_t *cand = reinterpret_cast<uint32_t *>(sm.res);
+        const uint32_t cap = (uint32_t)T * kTileB / 2u < kCap ? (uint32_t)T * kTileB / 2u : kCap;
+        for (uint64_t base = in.start_bit; base < in.end_bit && found == ~0ull; base += (uint64_t)T * kSpan) {
             PP_T0_BEGIN
-            sm.u[8] = 0xffffffffu;
+            sm.u[8] = 0xffffffffu;   // smallest valid position of the round (relative to base)
+            sm.u[9] = 0;             // survivors
             PP_T0_END
             PP_SYNC();
             PP_FOR_T(t)
-            {
-                const uint64_t p = base + (uint64_t)t;
-                if (p < in.end_bit && probe_dynamic_header(bp, p)) PP_ATOMIC_MIN(&sm.u[8], (uint32_t)t);
+            for (uint32_t i = 0; i < kSpan; i++) {
+                const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
+                const uint64_t p = base + rel;
+                if (p < in.end_bit && probe_cheap(bp, p)) {
+                    const uint32_t at = atomic_inc_u32(&sm.u[9]);
+                    if (at < cap) cand[at] = rel;
+                }
             }
             PP_END_T
+            PP_SYNC();
+            const uint32_t nc = sm.u[9];
+            if (nc <= cap) {
+                PP_FOR_T(t)
+                for (uint32_t i = (uint32_t)t; i < nc; i += (uint32_t)T) {
+                    const uint32_t rel = cand[i];
+                    if (probe_dynamic_header(bp, base + rel)) PP_ATOMIC_MIN(&sm.u[8], rel);
+                }
+                PP_END_T
+            } else {   // the list overflowed (adversarial input): every position through the full probe
+                PP_FOR_T(t)
+                for (uint32_t i = 0; i < kSpan; i++) {
+                    const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
+                    if (base + rel < in.end_bit && probe_dynamic_header(bp, base + rel)) PP_ATOMIC_MIN(&sm.u[8], rel);
+                }
+                PP_END_T
+            }
             PP_SYNC();
             if (sm.u[8] != 0xffffffffu) found = base + sm.u[8];
             PP_SYNC();

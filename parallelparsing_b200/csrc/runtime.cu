@@ -1027,6 +1027,45 @@ int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t
 }
 
 
+// ------------------------------------------------------------ cached contexts
+// The one-call entry points over several GPUs / paired files need a context (stream, 600 MB of token
+// scratch, occupancy queries) per GPU and per concurrent job; opening one costs tens of milliseconds,
+// more than the decode of 10 M reads.  They borrow contexts from a process-wide cache instead and give
+// them back when the handle is freed; pp_release_cached_contexts() closes the idle ones.
+static std::mutex g_ctx_cache_mu;
+static std::vector<pp_ctx *> g_ctx_cache;
+
+static int ctx_acquire(int32_t device, pp_ctx **out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_cache_mu);
+        for (size_t i = 0; i < g_ctx_cache.size(); i++)
+            if (g_ctx_cache[i]->device == device) {
+                *out = g_ctx_cache[i];
+                g_ctx_cache.erase(g_ctx_cache.begin() + (long)i);
+                return PP_OK;
+            }
+    }
+    return pp_open(device, out);
+}
+
+static void ctx_release(pp_ctx *c)
+{
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(g_ctx_cache_mu);
+    g_ctx_cache.push_back(c);
+}
+
+void pp_release_cached_contexts(void)
+{
+    std::vector<pp_ctx *> idle;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_cache_mu);
+        idle.swap(g_ctx_cache);
+    }
+    for (pp_ctx *c : idle) pp_close(c);
+}
+
 // ------------------------------------------------------------ multi-GPU DecompressAll
 //
 // Index chunks are independent (chunk k needs index[k], index[k+1] and the file bytes
@@ -1073,7 +1112,7 @@ void pp_multi_free(pp_multi *m)
 {
     if (!m) return;
     for (pp_job *j : m->jobs) pp_job_free(j);
-    for (pp_ctx *c : m->ctxs) pp_close(c);
+    for (pp_ctx *c : m->ctxs) ctx_release(c);
     delete m;
 }
 
@@ -1102,7 +1141,7 @@ int pp_decompress_all_multi(const int32_t *devices, int32_t n_devices, const pp_
             std::vector<std::thread> th;
             for (int32_t r = 0; r < n_devices; r++)
                 th.emplace_back([&, r]() {
-                    int e = pp_open(devices[r], &m->ctxs[(size_t)r]);
+                    int e = ctx_acquire(devices[r], &m->ctxs[(size_t)r]);
                     if (e == PP_OK)
                         e = pp_decompress_all(m->ctxs[(size_t)r], ix, gz, gz_len, first[(size_t)r], cnt[(size_t)r], flags,
                                               &m->jobs[(size_t)r]);
@@ -1180,8 +1219,8 @@ void pp_pair_free(pp_pair *p)
     for (pp_job *j : p->r1) pp_job_free(j);
     for (auto &v : p->r2)
         for (pp_job *j : v) pp_job_free(j);
-    for (pp_ctx *c : p->ctx1) pp_close(c);
-    for (pp_ctx *c : p->ctx2) pp_close(c);
+    for (pp_ctx *c : p->ctx1) ctx_release(c);
+    for (pp_ctx *c : p->ctx2) ctx_release(c);
     delete p;
 }
 
@@ -1235,12 +1274,12 @@ int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_i
             std::vector<std::thread> th;
             for (size_t g = 0; g < P; g++) {
                 th.emplace_back([&, g]() {
-                    int e = pp_open(devices[g], &p->ctx1[g]);
+                    int e = ctx_acquire(devices[g], &p->ctx1[g]);
                     if (e == PP_OK) e = pp_decompress_all(p->ctx1[g], ix1, gz1, gz1_len, f1[g], n1[g], flags, &p->r1[g]);
                     e1[g] = e;
                 });
                 th.emplace_back([&, g]() {
-                    int e = pp_open(devices[g], &p->ctx2[g]);
+                    int e = ctx_acquire(devices[g], &p->ctx2[g]);
                     if (e == PP_OK) e = pp_decompress_all(p->ctx2[g], ix2, gz2, gz2_len, f2[g], n2[g], flags, &main2[g]);
                     e2[g] = e;
                 });
