@@ -54,12 +54,19 @@ pe.free()
 for _ in range(2):
     one().free()
 t0 = time.perf_counter()
+t_call = t_free = 0.0
 for _ in range(steps):
-    one().free()
+    a = time.perf_counter()
+    h = one()
+    b = time.perf_counter()
+    h.free()
+    t_call += b - a
+    t_free += time.perf_counter() - b
 dt = (time.perf_counter() - t0) / steps
 print(json.dumps({
     "metric": "paired DecompressAll (R1 + R2) uncompressed GB/s", "value": (ubytes + ubytes2) / dt / 1e9, "unit": "GB/s",
     "pairs_per_s": pairs / dt, "ms_per_step": dt * 1e3, "n_gpus": ngpu, "steps": steps,
     "config": {"workload": f"Generator seeds 0/1, {pairs} pairs x 150bp, gzip -6, chunk 10000, paired by ordinal (PP_JOB_STRICT)",
                "topup_chunks": topup, "uncompressed_bytes": ubytes + ubytes2},
+    "call_ms": t_call / steps * 1e3, "free_ms": t_free / steps * 1e3,
     "what": "cold pp_pair_decompress_all + pp_pair_free per step, pull mode, host wall clock"}))
