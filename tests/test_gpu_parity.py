@@ -987,3 +987,32 @@ def test_paired_end_mates_are_co_resident(device, parts):
         seen += n1
     assert seen == nreads
     pe.free()
+
+
+def test_scan_blocks_on_damaged_and_foreign_input(device):
+    """pp_scan_blocks must end cleanly, never hang: on a damaged stream, on a file that is not gzip at all
+    (rejected by the header check) and on a stream cut short (no final block: an error)."""
+    import parallelparsing_b200 as pp
+    gz = corpus.gz_member(corpus.fastq(30000, fixed=150), 6)
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    bad = gz.copy()
+    mid = int(bits[len(bits) // 2] // 8) + 2000
+    bad[mid: mid + 4000] = np.random.default_rng(1).integers(0, 256, 4000, dtype=np.uint8)
+    # damage in the middle: Huffman garbage is mostly decodable (zlib itself only notices through the CRC-32 of
+    # the trailer, which a scan that produces no bytes cannot check), so the scan may end either way — but it
+    # must END, with an error code or with a block list that agrees with the true one up to the damage
+    try:
+        gb, go, gend, gtot, ms, passes = pp.Core.ScanBlocks(bad, device, 65536)
+        nb = int(np.searchsorted(bits, mid * 8))
+        assert np.array_equal(gb[:nb], bits[:nb]) and np.array_equal(go[:nb], outs[:nb])
+    except pp.ZException as e:
+        assert e.Code in (-3, -5)
+    with pytest.raises(pp.ZException) as e:          # cut short: no final block
+        pp.Core.ScanBlocks(gz[: gz.size // 2], device, 65536)
+    assert e.value.Code in (-3, -5)
+    with pytest.raises(pp.ZException) as e:
+        pp.Core.ScanBlocks(np.frombuffer(b"this is not a gzip file, not even close" * 100, np.uint8), device)
+    assert e.value.Code == -3
+    # and the undamaged stream still scans
+    gb, go, gend, gtot, ms, passes = pp.Core.ScanBlocks(gz, device, 65536)
+    assert np.array_equal(gb, bits) and gtot == tot
