@@ -122,8 +122,9 @@ extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int
         const uint64_t stream_bits = (uint64_t)gz_len * 8u;
         const int nseg = (int)std::max<uint64_t>(1, (gz_len - hdr + (uint64_t)segment_bytes - 1) / (uint64_t)segment_bytes);
         const uint32_t rec_cap = (uint32_t)std::max<int64_t>(256, segment_bytes / 64);  // blocks average >= 64 compressed bytes, else PP_BUF_ERROR
-        CKS(cudaMalloc(&d_comp, ((gz_len + 15) & ~(size_t)15) + 4096));
-        CKS(cudaMemsetAsync(d_comp + (gz_len & ~(size_t)15), 0, 4096 + 16, st));
+        const size_t comp_base = gz_len & ~(size_t)15, comp_pad = 4096 + 16;   // zeroed tail: reads past the end see zeros
+        CKS(cudaMalloc(&d_comp, comp_base + comp_pad));
+        CKS(cudaMemsetAsync(d_comp + comp_base, 0, comp_pad, st));
         CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
         CKS(cudaMalloc(&d_segs, sizeof(ScanSegIn) * (size_t)nseg));
         CKS(cudaMalloc(&d_outs, sizeof(ScanSegOut) * (size_t)nseg));
