@@ -53,6 +53,7 @@ extern "C" {
 #define PP_E_IO (-103)              /* file open/read/write failed */
 #define PP_E_RECORD_TOO_LONG (-104) /* Core.cs:93 IndexOutOfRangeException: record > 32768 B */
 #define PP_E_FORMAT (-105)          /* malformed IndexIO file */
+#define PP_E_UNSUPPORTED (-106)     /* input outside what this entry point handles (see the entry point) */
 
 typedef struct pp_index pp_index; /* Common/Index.cs:5  Index  */
 typedef struct pp_ctx pp_ctx;     /* one GPU + stream + scratch */
@@ -288,6 +289,44 @@ int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t
 int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int64_t segment_bytes, int64_t *start_bits,
                    int64_t *out_offsets, int64_t cap, int64_t *count, int64_t *end_bit, int64_t *total_out,
                    float *kernel_ms, int32_t *passes);
+
+/* ------------------------------------------------------------- CreateIndex on the GPU */
+
+typedef struct pp_create_stats {  /* where pp_index_create_gpu's time went (CUDA events, ms) */
+    float h2d_ms;          /* the file to the device                                        */
+    float scan_ms;         /* block scan incl. stitching on the host (scan_kernel_ms: kernels only) */
+    float scan_kernel_ms;
+    float plan_ms;         /* segment planning, allocations                                  */
+    float inflate_ms;      /* the inflate kernel over every segment, twice                   */
+    float chain_ms;        /* window behind every segment                                    */
+    float resolve_ms;      /* dictionary-derived bytes replaced                              */
+    float count_crc_ms;    /* '@' statistics per block, CRC-32                               */
+    float gather_ms;       /* host: point selection; device: windows + offsets; D2H          */
+    float total_ms;
+    int64_t blocks;        /* deflate blocks = Z_BLOCK stops                                 */
+    int64_t total_out;     /* inflated length                                                */
+    int32_t segments;      /* decode segments                                                */
+    int32_t scan_passes;
+    int32_t points;
+    int32_t pad;
+} pp_create_stats;
+
+/*
+ * Core.BuildDeflateIndex (Decompressor/Core.cs:14-131) on the GPU: the same index, point for point and
+ * byte for byte, as pp_index_create — which stays the general path — without the serial inflate pass.
+ * The block scan (pp_scan_blocks) finds the Z_BLOCK stops; runs of blocks are inflated by the inflate
+ * kernel twice, each time with a dictionary that encodes its own positions instead of data, which tells
+ * for every output byte whether it is final or which byte of the preceding 32 KB it copies; the windows
+ * are then chained through the segments and the bytes resolved; '@' statistics per block (Core.cs:86)
+ * feed the reference's own checkpoint rule (Core.cs:98-125), and the windows / offsets of the chosen
+ * points are gathered on the device.  ISIZE and CRC-32 of the trailer are verified (zlib: -3).
+ * gz: one complete gzip member; more members or trailing bytes: PP_E_UNSUPPORTED, use
+ * pp_index_create.  PP_E_RECORD_TOO_LONG / PP_INDEX_LIFT_RECORD_CAP as pp_index_create.  A stream that is
+ * both damaged and holds an over-long record may report the other of the two errors.  Device memory:
+ * about twice the inflated size.  stats may be NULL.
+ */
+int pp_index_create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t chunksize, uint32_t flags,
+                        pp_index **out, pp_create_stats *stats);
 
 /* ------------------------------------------------------ DecompressAll on several GPUs */
 

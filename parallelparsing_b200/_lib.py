@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libppb200.so")
 WINSIZE = 32768
 
 PP_OK = 0
-PP_E_CUDA, PP_E_NO_DEVICE, PP_E_ARG, PP_E_IO, PP_E_RECORD_TOO_LONG, PP_E_FORMAT = -100, -101, -102, -103, -104, -105
+PP_E_CUDA, PP_E_NO_DEVICE, PP_E_ARG, PP_E_IO, PP_E_RECORD_TOO_LONG, PP_E_FORMAT, PP_E_UNSUPPORTED = -100, -101, -102, -103, -104, -105, -106
 PP_INDEX_LIFT_RECORD_CAP = 1
 PP_JOB_STRICT, PP_JOB_ZEROCOPY, PP_JOB_PIPELINE, PP_JOB_COMPACT_WINDOWS = 1, 2, 4, 8
 
@@ -57,6 +57,14 @@ _lib = None
 # every symbol include/ppb200.h declares: (name, restype, argtypes)
 _p, _i32, _i64, _u32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
 _PP = C.POINTER(_p)
+class PPCreateStats(C.Structure):
+    """include/ppb200.h pp_create_stats."""
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "scan_ms", "scan_kernel_ms", "plan_ms", "inflate_ms", "chain_ms",
+                                         "resolve_ms", "count_crc_ms", "gather_ms", "total_ms")] + \
+               [("blocks", C.c_int64), ("total_out", C.c_int64), ("segments", C.c_int32), ("scan_passes", C.c_int32),
+                ("points", C.c_int32), ("pad", C.c_int32)]
+
+
 SYMBOLS = [
     ("pp_abi_version", C.c_int, []),
     ("pp_strerror", C.c_char_p, [C.c_int]),
@@ -100,6 +108,7 @@ SYMBOLS = [
     ("pp_decompress_all", C.c_int, [_p, _p, _p, _sz, _i32, _i32, _u32, _PP]),
     ("pp_scan_blocks", C.c_int, [_p, _p, _sz, _i64, _p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                                  C.POINTER(C.c_float), C.POINTER(_i32)]),
+    ("pp_index_create_gpu", C.c_int, [_p, _p, _sz, _u32, _u32, _PP, C.POINTER(PPCreateStats)]),
     ("pp_partition_chunks", C.c_int, [_p, _i32, _p, _p]),
     ("pp_decompress_all_multi", C.c_int, [_p, _i32, _p, _p, _sz, _u32, _PP]),
     ("pp_multi_info_get", C.c_int, [_p, C.POINTER(PPMultiInfo)]),

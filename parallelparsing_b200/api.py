@@ -165,6 +165,21 @@ class Core:
         return Index(_handle=h)
 
     @staticmethod
+    def BuildDeflateIndexGpu(file, chunksize: int, device=None, lift_record_cap=False, want_stats=False):
+        """CreateIndex on the GPU (pp_index_create_gpu): the same Index as BuildDeflateIndex, without the
+        serial inflate pass of Core.cs:41-127.  One gzip member; anything else raises ZException with
+        PP_E_UNSUPPORTED (-106) and BuildDeflateIndex remains the way.  want_stats: (Index, dict of ms)."""
+        dev = device or Device.default()
+        gz = _as_u8(np.fromfile(file, np.uint8) if isinstance(file, str) else file)
+        h = C.c_void_p()
+        st = _lib.PPCreateStats()
+        flags = _lib.PP_INDEX_LIFT_RECORD_CAP if lift_record_cap else 0
+        check(lib().pp_index_create_gpu(dev.h, _ptr(gz), gz.size, chunksize, flags, C.byref(h), C.byref(st)),
+              "Core.BuildDeflateIndexGpu")
+        ix = Index(_handle=h)
+        return (ix, {n: getattr(st, n) for n, _ in st._fields_ if n != "pad"}) if want_stats else ix
+
+    @staticmethod
     def ScanBlocks(file, device=None, segment_bytes=0):
         """GPU-assisted CreateIndex, first slice (pp_scan_blocks): (start_bits[], out_offsets[], end_bit,
         total_out, kernel_ms, passes) — every deflate block's first bit and output offset, the stops

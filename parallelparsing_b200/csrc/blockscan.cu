@@ -93,39 +93,28 @@ static size_t gzip_header_len(const uint8_t *gz, size_t n)
 
 extern "C" int pp_internal_ctx_device(const pp_ctx *ctx, int *device, int *sm_count, cudaStream_t *stream);
 
-extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int64_t segment_bytes, int64_t *start_bits,
-                              int64_t *out_offsets, int64_t cap, int64_t *count, int64_t *end_bit, int64_t *total_out,
-                              float *kernel_ms, int32_t *passes)
+namespace pp {
+
+// The scan proper on a stream that is already resident in device memory (d_comp: the whole gzip file,
+// at least 4096 + 16 zero bytes behind it).  Appends every block start to `chain` (output offsets
+// global), sets land (bit after the final block) and total_out.
+int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, size_t gz_len, size_t hdr,
+                         int64_t segment_bytes, std::vector<BlockRec> &chain, uint64_t &land_out, uint64_t &total_out,
+                         float &ms_total, int &npass)
 {
-    using namespace pp;
-    if (!ctx || !gz || !count) return PP_E_ARG;
-    *count = 0;
-    const size_t hdr = gzip_header_len(gz, gz_len);
-    if (!hdr) return PP_DATA_ERROR;
-    int device = 0, sm_count = 0;
-    cudaStream_t st = nullptr;
-    if (pp_internal_ctx_device(ctx, &device, &sm_count, &st) != PP_OK) return PP_E_ARG;
     if (segment_bytes <= 0) segment_bytes = 512 << 10;
     if (segment_bytes < 4096) segment_bytes = 4096;
     int rc = PP_OK;
-    uint8_t *d_comp = nullptr;
     ScanSegIn *d_segs = nullptr;
     ScanSegOut *d_outs = nullptr;
     BlockRec *d_recs = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    float ms_total = 0.f;
-    int npass = 0;
-    std::vector<BlockRec> chain;      // accepted block starts, output offsets global
     try {
         CKS(cudaSetDevice(device));
         const uint64_t comp_bytes = gz_len;   // the gzip trailer (8 bytes) is simply never reached
         const uint64_t stream_bits = (uint64_t)gz_len * 8u;
         const int nseg = (int)std::max<uint64_t>(1, (gz_len - hdr + (uint64_t)segment_bytes - 1) / (uint64_t)segment_bytes);
         const uint32_t rec_cap = (uint32_t)std::max<int64_t>(256, segment_bytes / 64);  // blocks average >= 64 compressed bytes, else PP_BUF_ERROR
-        const size_t comp_base = gz_len & ~(size_t)15, comp_pad = 4096 + 16;   // zeroed tail: reads past the end see zeros
-        CKS(cudaMalloc(&d_comp, comp_base + comp_pad));
-        CKS(cudaMemsetAsync(d_comp + comp_base, 0, comp_pad, st));
-        CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
         CKS(cudaMalloc(&d_segs, sizeof(ScanSegIn) * (size_t)nseg));
         CKS(cudaMalloc(&d_outs, sizeof(ScanSegOut) * (size_t)nseg));
         CKS(cudaMalloc(&d_recs, sizeof(BlockRec) * (size_t)nseg * rec_cap));
@@ -207,13 +196,58 @@ extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int
             if (npass > nseg + 2) { rc = PP_E_CUDA; goto done; }   // cannot happen: every pass verifies a segment
         }
         if (!final_seen) { rc = PP_DATA_ERROR; goto done; }        // the stream ended without a final block
+        land_out = land;
+        total_out = out_base;
+    } catch (...) {
+        rc = PP_MEM_ERROR;
+    }
+done:
+    cudaFree(d_segs);
+    cudaFree(d_outs);
+    cudaFree(d_recs);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+size_t gzip_member_header_len(const uint8_t *gz, size_t n) { return gzip_header_len(gz, n); }
+
+}  // namespace pp
+
+extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int64_t segment_bytes, int64_t *start_bits,
+                              int64_t *out_offsets, int64_t cap, int64_t *count, int64_t *end_bit, int64_t *total_out,
+                              float *kernel_ms, int32_t *passes)
+{
+    using namespace pp;
+    if (!ctx || !gz || !count) return PP_E_ARG;
+    *count = 0;
+    const size_t hdr = gzip_header_len(gz, gz_len);
+    if (!hdr) return PP_DATA_ERROR;
+    int device = 0, sm_count = 0;
+    cudaStream_t st = nullptr;
+    if (pp_internal_ctx_device(ctx, &device, &sm_count, &st) != PP_OK) return PP_E_ARG;
+    int rc = PP_OK;
+    uint8_t *d_comp = nullptr;
+    float ms_total = 0.f;
+    int npass = 0;
+    uint64_t land = 0, out_total = 0;
+    std::vector<BlockRec> chain;      // accepted block starts, output offsets global
+    try {
+        CKS(cudaSetDevice(device));
+        const size_t comp_base = gz_len & ~(size_t)15, comp_pad = 4096 + 16;   // zeroed tail: reads past the end see zeros
+        CKS(cudaMalloc(&d_comp, comp_base + comp_pad));
+        CKS(cudaMemsetAsync(d_comp + comp_base, 0, comp_pad, st));
+        CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
+        rc = scan_blocks_resident(device, sm_count, st, d_comp, gz_len, hdr, segment_bytes, chain, land, out_total, ms_total,
+                                  npass);
+        if (rc != PP_OK) goto done;
         *count = (int64_t)chain.size();
         for (int64_t i = 0; i < (int64_t)chain.size() && i < cap; i++) {
             if (start_bits) start_bits[i] = (int64_t)chain[(size_t)i].bit;
             if (out_offsets) out_offsets[i] = (int64_t)chain[(size_t)i].out;
         }
         if (end_bit) *end_bit = (int64_t)land;
-        if (total_out) *total_out = (int64_t)out_base;
+        if (total_out) *total_out = (int64_t)out_total;
         if ((int64_t)chain.size() > cap && (start_bits || out_offsets)) rc = PP_BUF_ERROR;
     } catch (...) {
         rc = PP_MEM_ERROR;
@@ -222,10 +256,5 @@ done:
     if (kernel_ms) *kernel_ms = ms_total;
     if (passes) *passes = npass;
     cudaFree(d_comp);
-    cudaFree(d_segs);
-    cudaFree(d_outs);
-    cudaFree(d_recs);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
     return rc;
 }

@@ -123,6 +123,58 @@ static void add_point(pp_index *ix, int32_t bits, int64_t input, int64_t output,
     }
 }
 
+int index_plan_points(const CiBlockStat *b, size_t nb, uint64_t total_out, uint64_t total_in, uint32_t chunksize,
+                      uint32_t flags, std::vector<CiPointPlan> &plan)
+{
+    const bool lift = (flags & PP_INDEX_LIFT_RECORD_CAP) != 0;
+    const int64_t threshold = (int64_t)(uint32_t)(chunksize - 8u);  // Core.cs:105, uint arithmetic
+    int64_t records = 0;
+    uint64_t run_start = 0;  // where offsetBeforePoint starts: the last '@' so far, or the stream's first byte
+    plan.clear();
+    for (size_t i = 0; i < nb; i++) {
+        // the stop in front of block i: the output of blocks < i has been seen (Core.cs:78-95)
+        if (i) {
+            const CiBlockStat &p = b[i - 1];
+            if (p.ats) {
+                if (!lift && ((p.out + p.first) - run_start > (uint64_t)PP_WINSIZE || p.maxgap > (uint32_t)PP_WINSIZE))
+                    return PP_E_RECORD_TOO_LONG;  // Core.cs:93
+                run_start = p.out + p.last;
+                records += p.ats;
+            }
+            if (!lift && b[i].out - run_start > (uint64_t)PP_WINSIZE) return PP_E_RECORD_TOO_LONG;
+        }
+        const int32_t bits = (int32_t)((8u - (uint32_t)(b[i].bit & 7u)) & 7u);
+        const int64_t input = (int64_t)((b[i].bit + 7u) >> 3);
+        if (b[i].out == 0) {  // Core.cs:99-102
+            plan.push_back({bits, input, 0, 0});
+        } else if (records > threshold) {  // Core.cs:105-109
+            plan.push_back({bits, input, (int64_t)b[i].out, (int64_t)run_start});
+            records = 0;
+        }
+    }
+    if (nb) {
+        const CiBlockStat &p = b[nb - 1];
+        if (p.ats) {
+            if (!lift && ((p.out + p.first) - run_start > (uint64_t)PP_WINSIZE || p.maxgap > (uint32_t)PP_WINSIZE))
+                return PP_E_RECORD_TOO_LONG;
+            run_start = p.out + p.last;
+        }
+    }
+    if (!lift && total_out - run_start > (uint64_t)PP_WINSIZE) return PP_E_RECORD_TOO_LONG;
+    plan.push_back({0, (int64_t)total_in, (int64_t)total_out, (int64_t)total_out});  // Core.cs:114-125, Z_STREAM_END
+    return PP_OK;
+}
+
+void index_from_plan(pp_index *ix, const std::vector<CiPointPlan> &plan)
+{
+    for (const CiPointPlan &p : plan) {
+        const int64_t n = p.output - p.off_from;
+        add_point(ix, p.bits, p.input, p.output, 0, nullptr, nullptr, 0);
+        ix->off_len.back() = (int32_t)n;
+        ix->offsets.resize(ix->offsets.size() + (size_t)n);
+    }
+}
+
 extern "C" {
 
 int pp_abi_version(void) { return PP_ABI_VERSION; }
@@ -145,6 +197,7 @@ const char *pp_strerror(int code)
         case PP_E_IO: return "I/O error";
         case PP_E_RECORD_TOO_LONG: return "record longer than 32768 bytes (reference: IndexOutOfRangeException)";
         case PP_E_FORMAT: return "malformed index file";
+        case PP_E_UNSUPPORTED: return "input not supported by this entry point";
         default: return "unknown error";
     }
 }
@@ -182,6 +235,32 @@ int pp_index_add(pp_index *ix, int32_t bits, int64_t input, int64_t output, cons
     }
     ix->chunk_max_bytes = keep;
     return PP_OK;
+}
+
+// Test hook (not part of the ABI): index_plan_points over flat arrays.  stats = nb x {ats, first, last, maxgap},
+// plan = cap x {bits, input, output, off_from}.
+int pp_internal_plan_points(const uint64_t *bit, const uint64_t *out, const uint32_t *stats, int64_t nb, uint64_t total_out,
+                            uint64_t total_in, uint32_t chunksize, uint32_t flags, int64_t *plan, int64_t cap, int64_t *count)
+{
+    if (nb < 0 || !count) return PP_E_ARG;
+    try {
+        std::vector<CiBlockStat> b((size_t)nb);
+        for (int64_t i = 0; i < nb; i++)
+            b[(size_t)i] = {bit[i], out[i], stats[4 * i], stats[4 * i + 1], stats[4 * i + 2], stats[4 * i + 3]};
+        std::vector<CiPointPlan> pl;
+        const int rc = index_plan_points(b.data(), (size_t)nb, total_out, total_in, chunksize, flags, pl);
+        if (rc != PP_OK) return rc;
+        *count = (int64_t)pl.size();
+        for (int64_t i = 0; i < (int64_t)pl.size() && i < cap; i++) {
+            plan[4 * i] = pl[(size_t)i].bits;
+            plan[4 * i + 1] = pl[(size_t)i].input;
+            plan[4 * i + 2] = pl[(size_t)i].output;
+            plan[4 * i + 3] = pl[(size_t)i].off_from;
+        }
+        return PP_OK;
+    } catch (...) {
+        return PP_MEM_ERROR;
+    }
 }
 
 int32_t pp_index_count(const pp_index *ix) { return ix ? ix->count() : 0; }

@@ -46,3 +46,28 @@ extern "C" void pp_internal_unpin_index(const pp_index *ix);
 extern "C" void pp_internal_unpin_cwin(const pp_index *ix);
 // Build (once; thread safe) the compact windows.  Returns false when out of memory.
 bool index_build_compact_windows(const pp_index *ix);
+
+// ---- GPU CreateIndex (createindex.cu): the host half of Core.BuildDeflateIndex over per-block statistics ----
+// One deflate block as the device reports it: where it starts (bit, output offset) and what its output
+// holds in '@' bytes (Core.cs:86 counts every byte 0x40 as a record start).
+struct CiBlockStat {
+    uint64_t bit;      // first bit of the block header = the Z_BLOCK stop in front of the block
+    uint64_t out;      // output offset of the block's first byte
+    uint32_t ats;      // '@' bytes in the block's output
+    uint32_t first;    // first / last '@', relative to the block's first byte (0xffffffff: none)
+    uint32_t last;
+    uint32_t maxgap;   // largest distance between two consecutive '@' inside the block
+};
+// One checkpoint to take: Point.Bits / Input / Output, and where its `offset` bytes start in the output
+// (off_from == output: no offset).
+struct CiPointPlan {
+    int32_t bits;
+    int64_t input, output, off_from;
+};
+// Core.cs:98-125 over the block list: which stops become points.  PP_E_RECORD_TOO_LONG as Core.cs:93 would
+// throw (unless PP_INDEX_LIFT_RECORD_CAP).  total_in = the member's length in bytes (header .. trailer).
+int index_plan_points(const CiBlockStat *b, size_t nb, uint64_t total_out, uint64_t total_in, uint32_t chunksize,
+                      uint32_t flags, std::vector<CiPointPlan> &plan);
+// Size `ix` for the planned points (scalars filled in, windows zeroed, offsets sized); the caller then
+// writes the bytes into ix->windows / ix->offsets.
+void index_from_plan(pp_index *ix, const std::vector<CiPointPlan> &plan);

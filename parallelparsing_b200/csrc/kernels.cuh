@@ -3,7 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "inflate_core.cuh"
+
+namespace ppinf {
+struct BlockRec;  // blockscan_core.cuh
+}
 
 namespace pp {
 
@@ -80,5 +86,13 @@ cudaError_t launch_exact_emit(const uint8_t *slots, const ParseDesc *pdesc, int 
 cudaError_t launch_digests(const uint8_t *slots, const ChunkDesc *descs, const ChunkResult *results,
                            const ParseDesc *pdesc, const ParseOut *pout, int n, const uint32_t *lines,
                            int64_t line_stride, unsigned long long *out, cudaStream_t st);
+
+
+// blockscan.cu: the block scan on a stream already resident in device memory (used by pp_scan_blocks and
+// pp_index_create_gpu), and the length of a gzip member header (0: not gzip).
+int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, size_t gz_len, size_t hdr,
+                         int64_t segment_bytes, std::vector<ppinf::BlockRec> &chain, uint64_t &land, uint64_t &total_out,
+                         float &ms_total, int &npass);
+size_t gzip_member_header_len(const uint8_t *gz, size_t n);
 
 }  // namespace pp

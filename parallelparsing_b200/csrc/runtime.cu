@@ -192,6 +192,21 @@ extern "C" int pp_internal_ctx_device(const pp_ctx *ctx, int *device, int *sm_co
     return PP_OK;
 }
 
+// pp_index_create_gpu (createindex.cu) drives the inflate kernel itself: the launch geometry for n chunks,
+// and the context lock that serialises users of the context's token scratch.
+extern "C" int pp_internal_ctx_inflate(pp_ctx *ctx, int n_chunks, pp::InflateLaunch *cfg)
+{
+    if (!ctx || !cfg) return PP_E_ARG;
+    *cfg = ctx->inflate_cfg(n_chunks);
+    return PP_OK;
+}
+extern "C" void pp_internal_ctx_lock(pp_ctx *ctx, int lock)
+{
+    if (!ctx) return;
+    if (lock) ctx->mu.lock();
+    else ctx->mu.unlock();
+}
+
 extern "C" void pp_internal_unpin_index(const pp_index *ix)
 {
     if (ix && ix->pinned_base) {

@@ -307,3 +307,79 @@ def test_cxx_partitioner_equals_python_partitioner():
                 assert f1 == f0 + n0
     empty = pp.Index()
     assert pp.partition_chunks(empty, 3) == [(0, 0)] * 3
+
+
+def _block_stats(data: np.ndarray, outs, total):
+    """What pp_ci_count_kernel reports per deflate block: '@' count, first, last, largest gap (numpy)."""
+    st = np.zeros((len(outs), 4), np.uint32)
+    ends = list(outs[1:]) + [total]
+    for i, (a, b) in enumerate(zip(outs, ends)):
+        at = np.flatnonzero(data[int(a): int(b)] == 64)
+        if at.size:
+            st[i] = (at.size, at[0], at[-1], int(np.diff(at).max()) if at.size > 1 else 0)
+        else:
+            st[i] = (0, 0xFFFFFFFF, 0xFFFFFFFF, 0)
+    return st
+
+
+def _plan_points(gz, chunksize, flags=0):
+    import zlib
+    from parallelparsing_b200._lib import lib
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    data = np.frombuffer(zlib.decompress(gz.tobytes(), 47), np.uint8)
+    st = np.ascontiguousarray(_block_stats(data, outs, tot))
+    b, o = np.ascontiguousarray(bits, np.uint64), np.ascontiguousarray(outs, np.uint64)
+    plan = np.zeros((len(bits) + 2, 4), np.int64)
+    n = C.c_int64()
+    L = lib()
+    L.pp_internal_plan_points.restype = C.c_int
+    L.pp_internal_plan_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                          C.c_uint32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    rc = L.pp_internal_plan_points(b.ctypes.data, o.ctypes.data, st.ctypes.data, len(bits), tot, gz.size, chunksize, flags,
+                                   plan.ctypes.data, plan.shape[0], C.byref(n))
+    return rc, plan[: n.value], data
+
+
+@pytest.mark.parametrize("kind", ["zlib6", "zlib1", "syncflush", "stored", "tiny"])
+def test_gpu_create_index_host_half_chooses_the_oracles_points(kind):
+    """index_plan_points — the host half of pp_index_create_gpu, Core.cs:98-125 over per-block '@' statistics —
+    picks exactly the oracle's points (Input, Bits, Output) and offsets, given the statistics the device
+    would report (computed here with numpy from zlib's output)."""
+    if kind == "syncflush":
+        gz, cs = corpus.gz_member(corpus.fastq(3000, fixed=150), 6, flush_every=50000), 100
+    elif kind == "stored":
+        gz, cs = corpus.gz_member(corpus.fastq(2000, fixed=150), 0), 50
+    elif kind == "tiny":
+        gz, cs = corpus.gz_member(corpus.fastq(3, fixed=150), 6), 1000
+    else:
+        gz, cs = corpus.gz_member(corpus.fastq(8000, fixed=150), int(kind[-1])), 1000
+    ox = O.OracleIndex.build(gz, cs)
+    rc, plan, data = _plan_points(gz, cs)
+    assert rc == 0 and len(plan) == ox.count
+    for i in range(ox.count):
+        p = ox.point(i)
+        assert (int(plan[i, 0]), int(plan[i, 1]), int(plan[i, 2])) == (p["bits"], p["input"], p["output"]), i
+        assert np.array_equal(data[int(plan[i, 3]): int(plan[i, 2])], p["offset"]), i
+
+
+def test_gpu_create_index_host_half_record_cap():
+    """... and gives the oracle's verdict on records around the 32 768-byte limit (Core.cs:93)."""
+    rng = np.random.default_rng(3)
+    verdicts = set()
+    for seq_len in (16300, 16370, 16376, 16377, 16380, 17000):
+        recs = []
+        for i in range(6):
+            n = seq_len if i == 3 else int(rng.integers(50, 4000))
+            seq = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+            recs.append(b"@r%d\n" % i + seq + b"\n+\n" + b"?" * n + b"\n")
+        gz = corpus.gz_member(b"".join(recs), 6)
+        try:
+            O.OracleIndex.build(gz, 2)
+            want = 0
+        except RuntimeError:
+            want = -104
+        rc, plan, _ = _plan_points(gz, 2)
+        assert rc == want, (seq_len, rc, want)
+        assert _plan_points(gz, 2, 1)[0] == 0          # PP_INDEX_LIFT_RECORD_CAP
+        verdicts.add(want)
+    assert verdicts == {0, -104}

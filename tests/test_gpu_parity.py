@@ -1017,3 +1017,116 @@ def test_scan_blocks_on_damaged_and_foreign_input(device):
     # and the undamaged stream still scans
     gb, go, gend, gtot, ms, passes = pp.Core.ScanBlocks(gz, device, 65536)
     assert np.array_equal(gb, bits) and gtot == tot
+
+
+# ----------------------------------------------------------------------------------------------
+# CreateIndex on the GPU (pp_index_create_gpu) == the oracle's Core.BuildDeflateIndex, byte for byte
+# ----------------------------------------------------------------------------------------------
+
+def _same_index_file(pp, ix, ox, tmp_path, tag):
+    """Both indexes through the reference's own file format (IndexIO.Serialize): identical bytes."""
+    a, b = str(tmp_path / f"{tag}_gpu.gzi"), str(tmp_path / f"{tag}_ora.gzi")
+    pp.IndexIO.Serialize(ix, a)
+    ox.serialize(b)
+    fa, fb = np.fromfile(a, np.uint8), np.fromfile(b, np.uint8)
+    assert fa.size == fb.size and np.array_equal(fa, fb), tag
+    assert ix.ChunkMaxBytes == ox.chunk_max_bytes
+
+
+@pytest.mark.parametrize("mode,chunk", [("dynamic6", 1000), ("dynamic6", 100), ("dynamic1", 1000), ("dynamic9", 5000),
+                                        ("syncflush", 100), ("fixed", 1000), ("stored", 200), ("huffman", 1000),
+                                        ("native_lengths", 1000), ("tiny", 1000), ("chunk_lt8", 5), ("lognormal", 20)])
+def test_gpu_create_index_equals_oracle(device, tmp_path, mode, chunk):
+    """Points (Input, Bits, Output), 32 KB windows, offsets and ChunkMaxBytes of the index built on the GPU
+    equal the oracle's serial inflate(Z_BLOCK) pass: the serialized files are identical.  Streams of dynamic,
+    fixed and stored blocks, sync-flush seams (empty stored blocks), files shorter than one window, chunksize
+    < 8 (the uint wrap of Core.cs:105), and long lognormal reads with the record cap lifted."""
+    import parallelparsing_b200 as pp
+    kw = dict(dynamic6=dict(level=6), dynamic1=dict(level=1), dynamic9=dict(level=9), fixed=dict(level=6, strategy=zlib.Z_FIXED),
+              stored=dict(level=0), huffman=dict(level=6, strategy=zlib.Z_HUFFMAN_ONLY), syncflush=dict(level=6, flush_every=70000),
+              native_lengths=dict(level=6), tiny=dict(level=6), chunk_lt8=dict(level=6), lognormal=dict(level=6))[mode]
+    lift = mode == "lognormal"
+    if mode == "native_lengths":
+        data = corpus.fastq(30000)
+    elif mode == "tiny":
+        data = corpus.fastq(20, fixed=150)
+    elif mode == "lognormal":
+        data = corpus.fastq(600, lognormal=(10000, 0.5))
+    else:
+        data = corpus.fastq(40000, fixed=150)
+    gz = corpus.gz_member(data, **kw)
+    ox = O.OracleIndex.build(gz, chunk, lift)
+    ix, st = pp.Core.BuildDeflateIndexGpu(gz, chunk, device, lift_record_cap=lift, want_stats=True)
+    assert st["total_out"] == len(data) and st["points"] == ox.count
+    _same_index_file(pp, ix, ox, tmp_path, mode)
+
+
+def test_gpu_create_index_then_decompress_all(device):
+    """The index built on the GPU drives DecompressAll: every chunk's bytes and records equal the oracle's."""
+    import parallelparsing_b200 as pp
+    gz = corpus.gz_member(corpus.fastq(40000, fixed=150), 6)
+    ix = pp.Core.BuildDeflateIndexGpu(gz, 1000, device)
+    ox = O.OracleIndex.build(gz, 1000)
+    job = pp.Job(device, ix, gz.size)
+    job.run(gz)
+    gb, gf = job.digests()
+    ob, of, orec = O.chunk_digests(gz, ox)
+    assert np.array_equal(gb, ob) and np.array_equal(gf, of)
+    job.free()
+
+
+def test_gpu_create_index_baseline_config1_file(device, tmp_path):
+    """BASELINE config 1's file (1 M reads x 150 bp, system gzip -6, chunk 10 000): 99 points, identical file."""
+    import parallelparsing_b200 as pp
+    gz = np.fromfile(_generator_file(1_000_000, system_gzip=True), np.uint8)
+    ox = O.OracleIndex.build(gz, 10_000)
+    ix, st = pp.Core.BuildDeflateIndexGpu(gz, 10_000, device, want_stats=True)
+    assert ox.count == 99 and st["blocks"] == 1559 and st["total_out"] == 381_111_160
+    _same_index_file(pp, ix, ox, tmp_path, "c1")
+
+
+def test_gpu_create_index_errors_like_zlib(device):
+    """What zlib reports as Z_DATA_ERROR in the reference's pass is reported here too: a wrong CRC-32, a wrong
+    ISIZE, a cut file, a distance that reaches in front of the stream.  An over-long record: -104 as the host
+    CreateIndex.  A second member: PP_E_UNSUPPORTED (-106), the host path handles it."""
+    import parallelparsing_b200 as pp
+    data = corpus.fastq(20000, fixed=150)
+    gz = corpus.gz_member(data, 6)
+
+    def code(buf, chunk=1000, **kw):
+        try:
+            pp.Core.BuildDeflateIndexGpu(buf, chunk, device, **kw)
+            return 0
+        except pp.ZException as e:
+            return e.Code
+
+    assert code(gz) == 0
+    bad = gz.copy(); bad[-6] ^= 1                        # CRC-32
+    assert code(bad) == -3
+    bad = gz.copy(); bad[-2] ^= 1                        # ISIZE
+    assert code(bad) == -3
+    bad = gz.copy(); bad[gz.size // 2] ^= 0x10           # one bit in the middle: decodes to other bytes or breaks the stream
+    assert code(bad) in (-3, -5)
+    assert code(gz[: gz.size // 2]) in (-3, -5)
+    assert code(gz[:-1]) in (-3, -5)
+    assert code(np.concatenate([gz, gz])) == -106
+    assert code(np.concatenate([gz, np.zeros(3, np.uint8)])) == -106
+    assert code(np.frombuffer(b"not a gzip file at all, just text" * 10, np.uint8)) == -3
+    # a fixed-codes block whose first symbol is a match: distance 1 with nothing in front of it
+    hdr = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"
+    # bits: BFINAL=1, BTYPE=01, length code 257 (len 3) = 0000001, distance code 0 = 00000, EOB = 0000000
+    bits = "1" + "10" + "0000001" + "00000" + "0000000"
+    val = 0
+    for i, ch in enumerate(bits):
+        val |= int(ch) << i
+    body = val.to_bytes((len(bits) + 7) // 8, "little")
+    import struct
+    far = np.frombuffer(hdr + body + struct.pack("<II", 0, 3), np.uint8)
+    with pytest.raises(zlib.error, match="too far back"):
+        zlib.decompress(far.tobytes(), 47)
+    assert code(far) == -3
+    # the record cap
+    long_rec = b"@r\n" + b"A" * 20000 + b"\n+\n" + b"?" * 20000 + b"\n"
+    gzl = corpus.gz_member(data[:3000] + long_rec + data[:3000], 6)
+    assert code(gzl, 10) == -104
+    assert code(gzl, 10, lift_record_cap=True) == 0
