@@ -278,7 +278,7 @@ int pp_decompress_all(pp_ctx *ctx, const pp_index *ix, const uint8_t *gz, size_t
  * The first bit and the output offset of every deflate block of the gzip member `gz` — the stops
  * Core.BuildDeflateIndex gets from a serial inflate(Z_BLOCK) pass (Decompressor/Core.cs:64) and the only
  * places where Core.cs:98-109 may drop a checkpoint — found on the GPU: the compressed stream is cut into
- * segments of `segment_bytes` (<= 0: 512 KiB), every segment searches for its first block header
+ * segments of `segment_bytes` (<= 0: one segment per resident CTA, 128 KiB .. 8 MiB), every segment searches for its first block header
  * speculatively and walks its blocks with the inflate kernel's Huffman passes (no history needed),
  * and the segments are stitched on the host (a seam that does not close is re-walked; `passes` counts
  * the kernel launches).  start_bits[i] = 8*Input - Bits of a checkpoint taken at block i (Common/Index.cs

@@ -98,11 +98,14 @@ namespace pp {
 // The scan proper on a stream that is already resident in device memory (d_comp: the whole gzip file,
 // at least 4096 + 16 zero bytes behind it).  Appends every block start to `chain` (output offsets
 // global), sets land (bit after the final block) and total_out.
-int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, size_t gz_len, size_t hdr,
-                         int64_t segment_bytes, std::vector<BlockRec> &chain, uint64_t &land_out, uint64_t &total_out,
+int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_gz, size_t gz_len,
+                         size_t hdr, int64_t segment_bytes, std::vector<BlockRec> &chain, uint64_t &land_out, uint64_t &total_out,
                          float &ms_total, int &npass)
 {
-    if (segment_bytes <= 0) segment_bytes = 512 << 10;
+    // Every segment pays one search (about half a block of bit positions probed) before its walk, and a CTA
+    // walks one segment: the default is one segment per resident CTA — as few searches as keep every SM busy.
+    if (segment_bytes <= 0)
+        segment_bytes = (int64_t)std::min<uint64_t>(8u << 20, std::max<uint64_t>(128u << 10, gz_len / (2u * (uint64_t)std::max(sm_count, 1))));
     if (segment_bytes < 4096) segment_bytes = 4096;
     int rc = PP_OK;
     ScanSegIn *d_segs = nullptr;
@@ -115,15 +118,16 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
         const uint64_t stream_bits = (uint64_t)gz_len * 8u;
         const int nseg = (int)std::max<uint64_t>(1, (gz_len - hdr + (uint64_t)segment_bytes - 1) / (uint64_t)segment_bytes);
         const uint32_t rec_cap = (uint32_t)std::max<int64_t>(256, segment_bytes / 64);  // blocks average >= 64 compressed bytes, else PP_BUF_ERROR
-        CKS(cudaMalloc(&d_segs, sizeof(ScanSegIn) * (size_t)nseg));
-        CKS(cudaMalloc(&d_outs, sizeof(ScanSegOut) * (size_t)nseg));
-        CKS(cudaMalloc(&d_recs, sizeof(BlockRec) * (size_t)nseg * rec_cap));
+        CKS(cudaMallocAsync((void **)&d_segs, sizeof(ScanSegIn) * (size_t)nseg, st));
+        CKS(cudaMallocAsync((void **)&d_outs, sizeof(ScanSegOut) * (size_t)nseg, st));
+        CKS(cudaMallocAsync((void **)&d_recs, sizeof(BlockRec) * (size_t)nseg * rec_cap, st));
         CKS(cudaEventCreate(&e0));
         CKS(cudaEventCreate(&e1));
         // pass 0: every segment searches (but the first) and walks
         std::vector<ScanSegIn> segs((size_t)nseg);
         std::vector<ScanSegOut> outs((size_t)nseg);
-        std::vector<BlockRec> recs;
+        std::vector<std::vector<BlockRec>> recs((size_t)nseg);  // per segment, only the records it wrote
+        std::vector<BlockRec> stage;
         for (int s = 0; s < nseg; s++) {
             ScanSegIn &g = segs[(size_t)s];
             g.start_bit = s ? ((uint64_t)hdr + (uint64_t)s * (uint64_t)segment_bytes) * 8u : (uint64_t)hdr * 8u;
@@ -136,7 +140,6 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
         std::vector<int> todo((size_t)nseg);
         for (int s = 0; s < nseg; s++) todo[(size_t)s] = s;
         std::vector<ScanSegIn> batch;
-        recs.resize((size_t)nseg * rec_cap);
         int verified = 0;            // segments [0, verified) are in the chain
         uint64_t land = 0, out_base = 0;
         bool final_seen = false;
@@ -155,12 +158,29 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
             cudaEventElapsedTime(&ms, e0, e1);
             ms_total += ms;
             npass++;
-            for (size_t i = 0; i < todo.size(); i++) {
-                const int s = todo[i];
-                outs[(size_t)s] = bo[i];
-                if (bo[i].nrec)
-                    CKS(cudaMemcpy(recs.data() + segs[(size_t)s].rec_off, d_recs + segs[(size_t)s].rec_off,
-                                   sizeof(BlockRec) * bo[i].nrec, cudaMemcpyDeviceToHost));
+            if (npass == 1) {
+                // all segments, record areas at a regular pitch: ONE 2-D copy of the used head of every area
+                uint32_t maxn = 0;
+                for (const ScanSegOut &o : bo) maxn = std::max(maxn, o.nrec);
+                if (maxn) {
+                    stage.resize((size_t)maxn * bo.size());
+                    CKS(cudaMemcpy2DAsync(stage.data(), sizeof(BlockRec) * maxn, d_recs, sizeof(BlockRec) * rec_cap,
+                                          sizeof(BlockRec) * maxn, bo.size(), cudaMemcpyDeviceToHost, st));
+                    CKS(cudaStreamSynchronize(st));
+                }
+                for (size_t i = 0; i < todo.size(); i++) {
+                    outs[(size_t)todo[i]] = bo[i];
+                    recs[(size_t)todo[i]].assign(stage.begin() + (size_t)i * maxn, stage.begin() + (size_t)i * maxn + bo[i].nrec);
+                }
+            } else {
+                for (size_t i = 0; i < todo.size(); i++) {
+                    const int s = todo[i];
+                    outs[(size_t)s] = bo[i];
+                    recs[(size_t)s].resize(bo[i].nrec);
+                    if (bo[i].nrec)
+                        CKS(cudaMemcpy(recs[(size_t)s].data(), d_recs + segs[(size_t)s].rec_off, sizeof(BlockRec) * bo[i].nrec,
+                                       cudaMemcpyDeviceToHost));
+                }
             }
             // stitch: extend the chain while each segment's walk starts where the chain landed
             todo.clear();
@@ -170,7 +190,33 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
                 const bool anchored = (s == 0 && segs[0].search == 0) || segs[(size_t)s].search == 0;
                 if (o.status < 0 && o.status != -5 && (anchored || o.first_bit == land)) { rc = PP_DATA_ERROR; goto done; }
                 if (o.status == -5) { rc = PP_BUF_ERROR; goto done; }
-                if (s > 0 && !anchored && o.first_bit != land) {
+                bool bridged = false;
+                if (s > 0 && !anchored && o.first_bit != land && land < o.first_bit && o.status >= 0 && h_gz) {
+                    // Stored blocks between where the chain landed and the first block the segment's search saw (the
+                    // search sees dynamic headers only): the empty stored block of a sync flush, as parallel gzip
+                    // writers leave one at every seam.  Their headers are walked here, on the host copy.
+                    uint64_t p = land, add = 0;
+                    size_t keep = chain.size();
+                    while (p < o.first_bit) {
+                        const uint64_t by = p >> 3;
+                        const uint32_t h3 = (((uint32_t)h_gz[by] | ((uint32_t)(by + 1 < gz_len ? h_gz[by + 1] : 0) << 8)) >> (p & 7u)) & 7u;
+                        if (h3 != 0u) break;  // not a non-final stored block
+                        const uint64_t lb = (p + 3u + 7u) >> 3;
+                        if (lb + 4u > gz_len) break;
+                        const uint32_t len = (uint32_t)h_gz[lb] | ((uint32_t)h_gz[lb + 1] << 8);
+                        const uint32_t nlen = (uint32_t)h_gz[lb + 2] | ((uint32_t)h_gz[lb + 3] << 8);
+                        if ((len ^ 0xffffu) != nlen) break;
+                        chain.push_back({p, out_base + add});
+                        add += len;
+                        p = (lb + 4u + len) * 8u;
+                    }
+                    if (p == o.first_bit) {
+                        out_base += add;
+                        land = p;
+                        bridged = true;
+                    } else chain.resize(keep);
+                }
+                if (s > 0 && !anchored && !bridged && o.first_bit != land) {
                     if (land >= segs[(size_t)s].end_bit) {   // the chain already walked past this whole segment
                         verified++;
                         continue;
@@ -183,7 +229,7 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
                     break;
                 }
                 for (uint32_t r = 0; r < o.nrec; r++) {
-                    BlockRec br = recs[segs[(size_t)s].rec_off + r];
+                    BlockRec br = recs[(size_t)s][r];
                     br.out += out_base;
                     chain.push_back(br);
                 }
@@ -202,9 +248,9 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
         rc = PP_MEM_ERROR;
     }
 done:
-    cudaFree(d_segs);
-    cudaFree(d_outs);
-    cudaFree(d_recs);
+    if (d_segs) cudaFreeAsync(d_segs, st);
+    if (d_outs) cudaFreeAsync(d_outs, st);
+    if (d_recs) cudaFreeAsync(d_recs, st);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;
@@ -238,8 +284,8 @@ extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int
         CKS(cudaMalloc(&d_comp, comp_base + comp_pad));
         CKS(cudaMemsetAsync(d_comp + comp_base, 0, comp_pad, st));
         CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
-        rc = scan_blocks_resident(device, sm_count, st, d_comp, gz_len, hdr, segment_bytes, chain, land, out_total, ms_total,
-                                  npass);
+        rc = scan_blocks_resident(device, sm_count, st, d_comp, gz, gz_len, hdr, segment_bytes, chain, land, out_total,
+                                  ms_total, npass);
         if (rc != PP_OK) goto done;
         *count = (int64_t)chain.size();
         for (int64_t i = 0; i < (int64_t)chain.size() && i < cap; i++) {

@@ -206,7 +206,9 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
         // and appends the survivors (~1 %) to a list in shared memory; pass 2: one survivor per THREAD
         // through the full probe (a serial decode of up to ~300 code lengths) — all lanes busy with
         // their own candidate instead of one lane per warp grinding while the others wait.
-        constexpr uint32_t kSpan = 32, kCap = 4096;                  // list: kCap u32 in the resolve tile buffer (>= 16 KB at T >= 512)
+        // kSpan 128: a block start is ~half a block away (a few hundred thousand positions), so a round of
+        // T x 128 positions costs little extra search and quarters the barriers and full-probe tails.
+        constexpr uint32_t kSpan = 128, kCap = 4096;                 // list: kCap u32 in the resolve tile buffer (>= 16 KB at T >= 512)
         uint32_t *cand = reinterpret_cast<uint32_t *>(sm.res);
         const uint32_t cap = (uint32_t)T * kTileB / 2u < kCap ? (uint32_t)T * kTileB / 2u : kCap;
         for (uint64_t base = in.start_bit; base < in.end_bit && found == ~0ull; base += (uint64_t)T * kSpan) {

@@ -14,8 +14,8 @@
 //               this segment (or a copy of one) and final.  A byte that differs is a copy, through any
 //               number of hops, of dictionary position i = a + 256 ((b - a - 1) mod 256): its value is
 //               byte i of the 32 KB of output in front of the segment, whatever they turn out to be.
-//   3. CHAIN    one CTA walks the segments in order with the running window in shared memory and
-//               resolves just the last 32 KB of every segment: the true window behind each of them.
+//   3. CHAIN    the true 32 KB window behind every segment: each segment's tail is a function of the
+//               window in front of it, and the functions are composed by a parallel scan over the segments.
 //   4. RESOLVE  every differing byte of run A is replaced by its window byte (all segments in parallel);
 //               run A now is the inflated file.
 //   5. COUNT    per block: the number of '@', the first and the last one, the largest gap between two.
@@ -29,6 +29,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -46,7 +47,9 @@ extern "C" void pp_internal_ctx_lock(pp_ctx *ctx, int lock);
 namespace pp {
 
 constexpr uint32_t kWin = PP_WINSIZE;
-constexpr uint32_t kPiece = 65536;   // bytes of one RESOLVE / CRC work item
+constexpr uint32_t kPiece = 65536;   // bytes of one RESOLVE work item
+constexpr uint32_t kCrcPart = 4096;  // bytes one thread runs the CRC over
+constexpr uint32_t kCrcPiece = 256u * kCrcPart;  // ... and one CTA
 constexpr uint32_t kNone = 0xffffffffu;
 
 // One decode segment: a run of consecutive deflate blocks.
@@ -75,78 +78,97 @@ struct CiCopy {
 __device__ __forceinline__ uint32_t ci_pos(uint32_t a, uint32_t b) { return a + 256u * ((b - a - 1u) & 0xffu); }
 
 // ---- CHAIN -----------------------------------------------------------------------------------------
-// Bytes [j0, j0+32) of the window BEHIND segment s, as far as they come from the segment itself (its last
-// min(len, 32768) bytes): run A and run B, four bytes per word.
-__device__ __forceinline__ void ci_tail_load(const CiSeg *segs, int s, int S, const uint8_t *slots, uint32_t j0,
-                                             uint32_t a[8], uint32_t b[8])
+// The window behind segment s is a function of the window in front of it: M_s[j] = a final byte, or "byte p
+// of the window in front" (0x8000 | p) — for the segment's last min(len, 32768) bytes straight from the two
+// runs, for the rest (a segment shorter than a window) the old window sliding down.  Functions of this
+// kind compose — (M_s o M_{s-1})[j] = M_s[j] if final, else M_{s-1}[p] — and composition is associative,
+// so the windows behind ALL segments come out of an inclusive scan over s: log2(S) rounds of gathers
+// (Hillis-Steele), every round over all segments in parallel, instead of a walk through the segments in
+// order.  What still points in front of segment 0 afterwards points at nothing and reads as zero (RESOLVE
+// flags the bytes for which that is an error).
+__device__ __forceinline__ uint32_t ci_ld_unaligned(const uint8_t *base, int64_t off)
 {
-#pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = b[k] = 0u;
-    if (s >= S) return;
+    const uint8_t *p = base + off;
+    const uintptr_t q = (uintptr_t)p & ~(uintptr_t)3;
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(q), w1 = *reinterpret_cast<const uint32_t *>(q + 4);
+    return __funnelshift_r(w0, w1, sh);
+}
+
+// maps[s][j], j = 0 .. 32767 (u16): grid.x = S, every thread four entries at a time
+__global__ void __launch_bounds__(256)
+    pp_ci_tailmap_kernel(const CiSeg *__restrict__ segs, const uint8_t *__restrict__ slots, uint16_t *__restrict__ maps,
+                         uint32_t *bad)
+{
+    const int s = (int)blockIdx.x;
     const CiSeg g = segs[s];
     const uint32_t n = g.out_len < kWin ? g.out_len : kWin;
     const uint8_t *pa = slots + g.a_off, *pb = slots + g.b_off;
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        const uint32_t j = j0 + (uint32_t)k;
-        if (j >= kWin - n) {
-            const uint32_t i = g.out_len + j - kWin;
-            a[k >> 2] |= (uint32_t)pa[i] << (8 * (k & 3));
-            b[k >> 2] |= (uint32_t)pb[i] << (8 * (k & 3));
+    uint2 *dst = reinterpret_cast<uint2 *>(maps + (size_t)s * kWin);
+    for (uint32_t w = threadIdx.x; w < kWin / 4u; w += blockDim.x) {
+        const uint32_t j = 4u * w;
+        const int64_t i0 = (int64_t)g.out_len + (int64_t)j - (int64_t)kWin;  // segment offset of window byte j
+        uint32_t a = 0, b = 0;
+        if (i0 > -4) {  // the word holds segment bytes (what lies in front of the segment is its lead area: ignored)
+            a = ci_ld_unaligned(pa, i0);
+            b = ci_ld_unaligned(pb, i0);
         }
+        uint32_t e[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t jb = j + (uint32_t)q;
+            if (jb >= kWin - n) {
+                const uint32_t av = (a >> (8 * q)) & 0xffu, bv = (b >> (8 * q)) & 0xffu;
+                if (av == bv) e[q] = av;
+                else {
+                    const uint32_t pos = ci_pos(av, bv);
+                    if (pos >= kWin) atomicOr(bad, 1u);
+                    e[q] = pos >= kWin ? 0u : 0x8000u | pos;
+                }
+            } else e[q] = 0x8000u | (jb + n);  // the old window slides
+        }
+        dst[w] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
     }
 }
 
-__global__ void __launch_bounds__(1024, 1)
-    pp_ci_chain_kernel(const CiSeg *__restrict__ segs, int S, const uint8_t *__restrict__ slots, uint8_t *__restrict__ wall,
-                       uint32_t *bad)
+// One scan round: dst[s] = src[s] o src[s-d]  (s >= d), dst[s] = src[s] (s < d).  grid.x = S.
+__global__ void __launch_bounds__(256)
+    pp_ci_compose_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int d)
 {
-    extern __shared__ __align__(16) uint8_t ci_sm[];  // two windows: the one in front of segment s, the one behind it
-    const uint32_t t = threadIdx.x, j0 = 32u * t;
-    for (uint32_t i = t; i < kWin / 16u; i += 1024u) reinterpret_cast<uint4 *>(ci_sm)[i] = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t a[8], b[8], an[8], bn[8];
-    ci_tail_load(segs, 0, S, slots, j0, a, b);
-    __syncthreads();
-    uint32_t cur = 0;
-    for (int s = 0; s < S; s++) {
-        const uint32_t len = segs[s].out_len, n = len < kWin ? len : kWin;
-        ci_tail_load(segs, s + 1, S, slots, j0, an, bn);  // in flight while this segment resolves
-        const uint8_t *wo = ci_sm + cur * kWin;
-        uint8_t *wn = ci_sm + (cur ^ 1u) * kWin;
-        uint32_t v[8];
+    const int s = (int)blockIdx.x;
+    const uint4 *in = reinterpret_cast<const uint4 *>(src + (size_t)s * kWin);
+    uint4 *out = reinterpret_cast<uint4 *>(dst + (size_t)s * kWin);
+    const uint16_t *prev = s >= d ? src + (size_t)(s - d) * kWin : nullptr;
+    for (uint32_t w = threadIdx.x; w < kWin / 8u; w += blockDim.x) {
+        uint4 v = in[w];
+        if (prev && ((v.x | v.y | v.z | v.w) & 0x80008000u)) {
+            uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = 0u;
-#pragma unroll
-        for (int k = 0; k < 32; k++) {
-            const uint32_t j = j0 + (uint32_t)k;
-            uint32_t x;
-            if (j >= kWin - n) {
-                const uint32_t av = (a[k >> 2] >> (8 * (k & 3))) & 0xffu, bv = (b[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                if (av == bv) x = av;
-                else {
-                    uint32_t pos = ci_pos(av, bv);
-                    if (pos >= kWin) {
-                        atomicOr(bad, 1u);
-                        pos = 0;
-                    }
-                    x = wo[pos];
-                }
-            } else x = wo[j + n];  // the segment is shorter than a window: the old one slides
-            v[k >> 2] |= x << (8 * (k & 3));
+            for (int q = 0; q < 4; q++) {
+                uint32_t lo = x[q] & 0xffffu, hi = x[q] >> 16;
+                if (lo & 0x8000u) lo = prev[lo & 0x7fffu];
+                if (hi & 0x8000u) hi = prev[hi & 0x7fffu];
+                x[q] = lo | (hi << 16);
+            }
+            v = make_uint4(x[0], x[1], x[2], x[3]);
         }
-        const uint4 lo = make_uint4(v[0], v[1], v[2], v[3]), hi = make_uint4(v[4], v[5], v[6], v[7]);
-        reinterpret_cast<uint4 *>(wn + j0)[0] = lo;
-        reinterpret_cast<uint4 *>(wn + j0)[1] = hi;
-        uint4 *gw = reinterpret_cast<uint4 *>(wall + (size_t)s * kWin + j0);
-        gw[0] = lo;
-        gw[1] = hi;
-        __syncthreads();
-        cur ^= 1u;
+        out[w] = v;
+    }
+}
+
+// The windows as bytes: wall[s][j] = maps[s][j], what still points in front of the stream = 0.
+__global__ void __launch_bounds__(256) pp_ci_wall_kernel(const uint16_t *__restrict__ maps, uint8_t *__restrict__ wall)
+{
+    const int s = (int)blockIdx.x;
+    const uint2 *in = reinterpret_cast<const uint2 *>(maps + (size_t)s * kWin);
+    uint32_t *out = reinterpret_cast<uint32_t *>(wall + (size_t)s * kWin);
+    for (uint32_t w = threadIdx.x; w < kWin / 4u; w += blockDim.x) {
+        const uint2 v = in[w];
+        const uint32_t e[4] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16};
+        uint32_t r = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            a[k] = an[k];
-            b[k] = bn[k];
-        }
+        for (int q = 0; q < 4; q++) r |= ((e[q] & 0x8000u) ? 0u : (e[q] & 0xffu)) << (8 * q);
+        out[w] = r;
     }
 }
 
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(256)
 // ---- CRC-32 (the gzip trailer's, RFC 1952 8.) -------------------------------------------------------
 // CRC-32 is linear: crc(X ++ Y) = crc(X) * x^(8|Y|) + crc(Y) over GF(2)[x] mod the CRC polynomial (bit-reflected
 // representation, x^0 = 0x80000000 — the identity zlib's crc32_combine is built on).  Every thread runs the
-// byte-wise table method over 256 consecutive bytes of a 64 KB piece, shifts its value by the bytes that
+// byte-wise table method over 4 KB of a 1 MB piece, shifts its value by the bytes that
 // follow it in the piece, and the CTA xors the 256 contributions into the piece's CRC; the host chains the
 // pieces with crc32_combine.
 __device__ __forceinline__ uint32_t ci_mulmod(uint32_t a, uint32_t b)
@@ -316,26 +338,24 @@ __global__ void __launch_bounds__(256)
     pp_ci_crc_kernel(const CiSeg *__restrict__ segs, const uint32_t *__restrict__ piece_base, int S, uint32_t npieces,
                      const uint8_t *__restrict__ slots, uint32_t *__restrict__ crcs)
 {
-    __shared__ uint32_t tab[256], shift_parts[256], shift_bytes[257], red[8];
+    __shared__ uint32_t tab[256], shift_parts[256], red[8];
     const uint32_t t = threadIdx.x;
     {
         uint32_t c = t;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
         tab[t] = c;
-        shift_parts[t] = ci_xpow(2048u * t);  // m parts of 256 bytes further on
-        shift_bytes[t] = ci_xpow(8u * t);     // r bytes further on
-        if (t == 0) shift_bytes[256] = ci_xpow(2048u);
+        shift_parts[t] = ci_xpow(8u * kCrcPart * t);  // t parts further on
     }
     __syncthreads();
     for (uint32_t piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
         const int s = ci_piece_seg(piece_base, S, piece);
         const CiSeg g = segs[s];
-        const uint32_t pfrom = (piece - piece_base[s]) * kPiece;
-        const uint32_t plen = g.out_len - pfrom < kPiece ? g.out_len - pfrom : kPiece;
-        const uint32_t K = (plen + 255u) / 256u, r = plen - 256u * (K - 1u);
+        const uint32_t pfrom = (piece - piece_base[s]) * kCrcPiece;
+        const uint32_t plen = g.out_len - pfrom < kCrcPiece ? g.out_len - pfrom : kCrcPiece;
+        const uint32_t K = (plen + kCrcPart - 1u) / kCrcPart, r = plen - kCrcPart * (K - 1u);  // r: bytes of the last part
         uint32_t c = 0;
         if (t < K) {
-            const uint32_t from = pfrom + 256u * t, n = t + 1u < K ? 256u : r;
+            const uint32_t from = pfrom + kCrcPart * t, n = t + 1u < K ? kCrcPart : r;
             const uint4 *src = reinterpret_cast<const uint4 *>(slots + g.a_off + from);
             c = 0xffffffffu;
             for (uint32_t i = 0; i < n / 16u; i++) {
@@ -349,7 +369,8 @@ __global__ void __launch_bounds__(256)
             const uint8_t *p = slots + g.a_off + from;
             for (uint32_t i = n & ~15u; i < n; i++) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
             c ^= 0xffffffffu;
-            if (t + 1u < K) c = ci_mulmod(ci_mulmod(c, shift_parts[K - 2u - t]), shift_bytes[r]);
+            // K-2-t whole parts and the last part's r bytes follow this one
+            if (t + 1u < K) c = ci_mulmod(ci_mulmod(c, shift_parts[K - 2u - t]), r == kCrcPart ? shift_parts[1] : ci_xpow(8u * r));
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
@@ -364,10 +385,18 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-struct Dev {
+struct Dev {  // stream-ordered allocation from the device's pool (release threshold lifted by pp_open)
     void *p = nullptr;
-    ~Dev() { cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    cudaStream_t st = nullptr;
+    ~Dev()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t n, cudaStream_t stream)
+    {
+        st = stream;
+        return cudaMallocAsync(&p, n ? n : 1, stream);
+    }
     template <class T> T *as() const { return (T *)p; }
 };
 
@@ -395,6 +424,20 @@ struct Ev {
 };
 }  // namespace
 
+namespace {
+struct HostTrace {  // PPB200_CI_TRACE=1: where the host side of the last stage spends its time (stderr)
+    bool on = getenv("PPB200_CI_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "ppb200 create_gpu: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+}  // namespace
+
 static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t chunksize, uint32_t flags, pp_index *ix,
                       pp_create_stats *stt)
 {
@@ -413,7 +456,7 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     // 0. the file
     Dev comp;
     const size_t comp_base = gz_len & ~(size_t)15, comp_pad = 4096 + 16;
-    CKI(comp.alloc(comp_base + comp_pad));
+    CKI(comp.alloc(comp_base + comp_pad, st));
     mark();  // 0
     CKI(cudaMemsetAsync(comp.as<uint8_t>() + comp_base, 0, comp_pad, st));
     CKI(cudaMemcpyAsync(comp.p, gz, gz_len, cudaMemcpyHostToDevice, st));
@@ -424,7 +467,7 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     uint64_t land = 0, total_out = 0;
     float scan_kernel_ms = 0.f;
     int passes = 0;
-    int rc = scan_blocks_resident(device, sm_count, st, comp.as<uint8_t>(), gz_len, hdr, 0, chain, land, total_out,
+    int rc = scan_blocks_resident(device, sm_count, st, comp.as<uint8_t>(), gz, gz_len, hdr, 0, chain, land, total_out,
                                   scan_kernel_ms, passes);
     if (rc != PP_OK) return rc;
     mark();  // 2
@@ -478,6 +521,13 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
         npieces += (segs[(size_t)s].out_len + kPiece - 1u) / kPiece;
     }
     piece_base[(size_t)S] = npieces;
+    std::vector<uint32_t> crc_base((size_t)S + 1);
+    uint32_t ncrc = 0;
+    for (int s = 0; s < S; s++) {
+        crc_base[(size_t)s] = ncrc;
+        ncrc += (segs[(size_t)s].out_len + kCrcPiece - 1u) / kCrcPiece;
+    }
+    crc_base[(size_t)S] = ncrc;
 
     // 3. DECODE twice
     std::vector<uint8_t> coded(2 * kWin);
@@ -485,19 +535,21 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
         coded[i] = (uint8_t)i;
         coded[kWin + i] = (uint8_t)((i >> 8) + 1u + (i & 0xffu));
     }
-    Dev slots, lead, d_descs, d_res, d_segs, d_pb, d_bad, wall;
-    CKI(slots.alloc(slot_off + 512));
-    CKI(lead.alloc(2 * kWin));
-    CKI(d_descs.alloc(sizeof(ChunkDesc) * descs.size()));
-    CKI(d_res.alloc(sizeof(ChunkResult) * descs.size()));
-    CKI(d_segs.alloc(sizeof(CiSeg) * (size_t)S));
-    CKI(d_pb.alloc(sizeof(uint32_t) * piece_base.size()));
-    CKI(d_bad.alloc(sizeof(uint32_t)));
-    CKI(wall.alloc((size_t)S * kWin));
+    Dev slots, lead, d_descs, d_res, d_segs, d_pb, d_cb, d_bad, wall;
+    CKI(slots.alloc(slot_off + 512, st));
+    CKI(lead.alloc(2 * kWin, st));
+    CKI(d_descs.alloc(sizeof(ChunkDesc) * descs.size(), st));
+    CKI(d_res.alloc(sizeof(ChunkResult) * descs.size(), st));
+    CKI(d_segs.alloc(sizeof(CiSeg) * (size_t)S, st));
+    CKI(d_pb.alloc(sizeof(uint32_t) * piece_base.size(), st));
+    CKI(d_cb.alloc(sizeof(uint32_t) * crc_base.size(), st));
+    CKI(d_bad.alloc(sizeof(uint32_t), st));
+    CKI(wall.alloc((size_t)S * kWin, st));
     CKI(cudaMemcpyAsync(lead.p, coded.data(), coded.size(), cudaMemcpyHostToDevice, st));
     CKI(cudaMemcpyAsync(d_descs.p, descs.data(), sizeof(ChunkDesc) * descs.size(), cudaMemcpyHostToDevice, st));
     CKI(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(CiSeg) * (size_t)S, cudaMemcpyHostToDevice, st));
     CKI(cudaMemcpyAsync(d_pb.p, piece_base.data(), sizeof(uint32_t) * piece_base.size(), cudaMemcpyHostToDevice, st));
+    CKI(cudaMemcpyAsync(d_cb.p, crc_base.data(), sizeof(uint32_t) * crc_base.size(), cudaMemcpyHostToDevice, st));
     CKI(cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), st));
     InflateLaunch cfg;
     if (pp_internal_ctx_inflate(ctx, 2 * S, &cfg) != PP_OK) return PP_E_ARG;
@@ -507,14 +559,21 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     mark();  // 4
 
     // 4. CHAIN, RESOLVE
-    static bool chain_attr[64];
-    if (!chain_attr[device & 63]) {
-        CKI(cudaFuncSetAttribute(pp_ci_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kWin)));
-        chain_attr[device & 63] = true;
+    {
+        Dev maps0, maps1;
+        CKI(maps0.alloc((size_t)S * kWin * sizeof(uint16_t), st));
+        CKI(maps1.alloc((size_t)S * kWin * sizeof(uint16_t), st));
+        uint16_t *src = maps0.as<uint16_t>(), *dst = maps1.as<uint16_t>();
+        pp_ci_tailmap_kernel<<<S, 256, 0, st>>>(d_segs.as<CiSeg>(), slots.as<uint8_t>(), src, d_bad.as<uint32_t>());
+        CKI(cudaGetLastError());
+        for (int d = 1; d < S; d *= 2) {
+            pp_ci_compose_kernel<<<S, 256, 0, st>>>(src, dst, d);
+            CKI(cudaGetLastError());
+            std::swap(src, dst);
+        }
+        pp_ci_wall_kernel<<<S, 256, 0, st>>>(src, wall.as<uint8_t>());
+        CKI(cudaGetLastError());
     }
-    pp_ci_chain_kernel<<<1, 1024, 2 * kWin, st>>>(d_segs.as<CiSeg>(), S, slots.as<uint8_t>(), wall.as<uint8_t>(),
-                                                  d_bad.as<uint32_t>());
-    CKI(cudaGetLastError());
     mark();  // 5
     const int wide = sm_count * 8;
     if (npieces) {
@@ -537,44 +596,47 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
         }
     }
     Dev d_bin, d_bout, d_crc;
-    CKI(d_bin.alloc(sizeof(CiBlkIn) * nb));
-    CKI(d_bout.alloc(sizeof(CiBlkOut) * nb));
-    CKI(d_crc.alloc(sizeof(uint32_t) * (size_t)npieces));
+    CKI(d_bin.alloc(sizeof(CiBlkIn) * nb, st));
+    CKI(d_bout.alloc(sizeof(CiBlkOut) * nb, st));
+    CKI(d_crc.alloc(sizeof(uint32_t) * (size_t)ncrc, st));
     CKI(cudaMemcpyAsync(d_bin.p, bin.data(), sizeof(CiBlkIn) * nb, cudaMemcpyHostToDevice, st));
     pp_ci_count_kernel<<<(int)std::min<size_t>(nb, (size_t)wide), 256, 0, st>>>(d_bin.as<CiBlkIn>(), (int)nb, slots.as<uint8_t>(),
                                                                                  d_bout.as<CiBlkOut>());
     CKI(cudaGetLastError());
-    if (npieces) {
-        pp_ci_crc_kernel<<<(int)std::min<uint32_t>(npieces, (uint32_t)wide), 256, 0, st>>>(
-            d_segs.as<CiSeg>(), d_pb.as<uint32_t>(), S, npieces, slots.as<uint8_t>(), d_crc.as<uint32_t>());
+    if (ncrc) {
+        pp_ci_crc_kernel<<<(int)std::min<uint32_t>(ncrc, (uint32_t)wide), 256, 0, st>>>(
+            d_segs.as<CiSeg>(), d_cb.as<uint32_t>(), S, ncrc, slots.as<uint8_t>(), d_crc.as<uint32_t>());
         CKI(cudaGetLastError());
     }
     mark();  // 7
+    HostTrace tr;
     std::vector<ChunkResult> res(descs.size());
     std::vector<CiBlkOut> bout(nb);
-    std::vector<uint32_t> crcs((size_t)npieces);
+    std::vector<uint32_t> crcs((size_t)ncrc);
     uint32_t bad = 0;
     CKI(cudaMemcpyAsync(res.data(), d_res.p, sizeof(ChunkResult) * res.size(), cudaMemcpyDeviceToHost, st));
     CKI(cudaMemcpyAsync(bout.data(), d_bout.p, sizeof(CiBlkOut) * nb, cudaMemcpyDeviceToHost, st));
     CKI(cudaMemcpyAsync(crcs.data(), d_crc.p, sizeof(uint32_t) * crcs.size(), cudaMemcpyDeviceToHost, st));
     CKI(cudaMemcpyAsync(&bad, d_bad.p, sizeof bad, cudaMemcpyDeviceToHost, st));
     CKI(cudaStreamSynchronize(st));
+    tr.lap("statistics to the host");
     for (size_t i = 0; i < res.size(); i++)
         if (res[i].status < 0 || res[i].produced != descs[i].out_len) return res[i].status < 0 ? res[i].status : PP_DATA_ERROR;
     if (bad) return PP_DATA_ERROR;  // a distance that reaches in front of the stream ("invalid distance too far back")
     {
         // CRC of the whole output from the pieces, in stream order
         uLong crc = crc32(0L, Z_NULL, 0);
-        const uLong op_full = crc32_combine_gen((z_off_t)kPiece);
+        const uLong op_full = crc32_combine_gen((z_off_t)kCrcPiece);
         for (int s = 0; s < S; s++) {
             const uint32_t len = segs[(size_t)s].out_len;
-            for (uint32_t p = piece_base[(size_t)s]; p < piece_base[(size_t)s + 1]; p++) {
-                const uint32_t plen = std::min(kPiece, len - (p - piece_base[(size_t)s]) * kPiece);
-                crc = plen == kPiece ? crc32_combine_op(crc, crcs[p], op_full) : crc32_combine(crc, crcs[p], (z_off_t)plen);
+            for (uint32_t p = crc_base[(size_t)s]; p < crc_base[(size_t)s + 1]; p++) {
+                const uint32_t plen = std::min(kCrcPiece, len - (p - crc_base[(size_t)s]) * kCrcPiece);
+                crc = plen == kCrcPiece ? crc32_combine_op(crc, crcs[p], op_full) : crc32_combine(crc, crcs[p], (z_off_t)plen);
             }
         }
         if ((uint32_t)crc != want_crc) return PP_DATA_ERROR;  // "incorrect data check"
     }
+    tr.lap("crc combine");
 
     // 6. the points (Core.cs:98-125), then their windows and offsets
     std::vector<CiBlockStat> bs(nb);
@@ -582,7 +644,9 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     std::vector<CiPointPlan> plan;
     rc = index_plan_points(bs.data(), nb, total_out, gz_len, chunksize, flags, plan);
     if (rc != PP_OK) return rc;
+    tr.lap("plan points");
     index_from_plan(ix, plan);
+    tr.lap("size the index");
     const size_t np = plan.size();
     std::vector<CiCopy> items;
     uint64_t off_bytes = 0;
@@ -600,8 +664,8 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
         off_bytes += olen;
     }
     Dev d_items, d_gather;
-    CKI(d_items.alloc(sizeof(CiCopy) * items.size()));
-    CKI(d_gather.alloc(np * (size_t)kWin + off_bytes));
+    CKI(d_items.alloc(sizeof(CiCopy) * items.size(), st));
+    CKI(d_gather.alloc(np * (size_t)kWin + off_bytes, st));
     CKI(cudaMemsetAsync(d_gather.p, 0, np * (size_t)kWin, st));
     if (!items.empty()) {
         CKI(cudaMemcpyAsync(d_items.p, items.data(), sizeof(CiCopy) * items.size(), cudaMemcpyHostToDevice, st));
@@ -613,6 +677,7 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     if (off_bytes) CKI(cudaMemcpyAsync(ix->offsets.data(), d_gather.as<uint8_t>() + np * (size_t)kWin, off_bytes, cudaMemcpyDeviceToHost, st));
     mark();  // 8
     CKI(cudaStreamSynchronize(st));
+    tr.lap("gather + D2H");
     if (stt) {
         float ms[8] = {};
         for (int i = 0; i < 8; i++) cudaEventElapsedTime(&ms[i], ev[i].e, ev[i + 1].e);

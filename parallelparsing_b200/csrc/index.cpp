@@ -11,6 +11,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <memory>
@@ -73,6 +74,20 @@ bool index_build_compact_windows(const pp_index *ix)
         return false;
     }
     return true;
+}
+
+void pp_index::reserve_windows(size_t points)
+{
+    if (points <= win_cap) return;
+    void *p = nullptr;
+    if (posix_memalign(&p, 4096, points * (size_t)PP_WINSIZE) != 0) throw std::bad_alloc();
+    if (windows) {
+        pp_internal_unpin_index(this);
+        memcpy(p, windows, std::min(win_cap, output.size()) * (size_t)PP_WINSIZE);
+        free(windows);
+    }
+    windows = (uint8_t *)p;
+    win_cap = points;
 }
 
 uint8_t *pp_index::append_window()
@@ -167,6 +182,7 @@ int index_plan_points(const CiBlockStat *b, size_t nb, uint64_t total_out, uint6
 
 void index_from_plan(pp_index *ix, const std::vector<CiPointPlan> &plan)
 {
+    ix->reserve_windows(ix->output.size() + plan.size());
     for (const CiPointPlan &p : plan) {
         const int64_t n = p.output - p.off_from;
         add_point(ix, p.bits, p.input, p.output, 0, nullptr, nullptr, 0);

@@ -89,9 +89,9 @@ cudaError_t launch_digests(const uint8_t *slots, const ChunkDesc *descs, const C
 
 
 // blockscan.cu: the block scan on a stream already resident in device memory (used by pp_scan_blocks and
-// pp_index_create_gpu), and the length of a gzip member header (0: not gzip).
-int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, size_t gz_len, size_t hdr,
-                         int64_t segment_bytes, std::vector<ppinf::BlockRec> &chain, uint64_t &land, uint64_t &total_out,
+// pp_index_create_gpu; h_gz: the host copy, may be null), and the length of a gzip member header (0: not gzip).
+int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_gz, size_t gz_len,
+                         size_t hdr, int64_t segment_bytes, std::vector<ppinf::BlockRec> &chain, uint64_t &land, uint64_t &total_out,
                          float &ms_total, int &npass);
 size_t gzip_member_header_len(const uint8_t *gz, size_t n);
 

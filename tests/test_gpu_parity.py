@@ -1067,12 +1067,7 @@ def test_gpu_create_index_then_decompress_all(device):
     gz = corpus.gz_member(corpus.fastq(40000, fixed=150), 6)
     ix = pp.Core.BuildDeflateIndexGpu(gz, 1000, device)
     ox = O.OracleIndex.build(gz, 1000)
-    job = pp.Job(device, ix, gz.size)
-    job.run(gz)
-    gb, gf = job.digests()
-    ob, of, orec = O.chunk_digests(gz, ox)
-    assert np.array_equal(gb, ob) and np.array_equal(gf, of)
-    job.free()
+    _digest_parity(pp, device, gz, ix, ox)
 
 
 def test_gpu_create_index_baseline_config1_file(device, tmp_path):
