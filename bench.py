@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-oracle-gate", action="store_true", help="skip the per-chunk oracle digest gate (N = 1)")
+    ap.add_argument("--no-create-index", action="store_true", help="skip the GPU CreateIndex leg (N = 1)")
     ap.add_argument("--lognormal", type=float, nargs=2, metavar=("MEAN", "SIGMA"),
                     help="read lengths lognormal with this mean (BASELINE config 4: --lognormal 10000 0.5 --chunk 1000)")
     ap.add_argument("--cap", type=int, default=0, help="clamp read lengths (16000 keeps records reference-legal, H2)")
@@ -594,6 +595,33 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if world == 1 and U <= (16 << 30) and not args.no_create_index:
+            # CreateIndex on the GPU (pp_index_create_gpu) for the same file: wall clock from pinned host memory,
+            # everything included; the result must serialize to the very index file this run decoded with
+            # (built by the host pass, pp_index_create = Core.BuildDeflateIndex on zlib, one thread)
+            gz_all, gz_all_ptr = pp.pinned_copy(np.fromfile(gz_path, np.uint8))
+            ci = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                gix, st = pp.Core.BuildDeflateIndexGpu(gz_all, args.chunk, dev, lift_record_cap=lift_cap(), want_stats=True)
+                ci.append(((time.perf_counter() - t0) * 1e3, st))
+            tmp = idx_path + f".gpu{os.getpid()}"
+            pp.IndexIO.Serialize(gix, tmp)
+            with open(tmp, "rb") as fa, open(idx_path, "rb") as fb:
+                same = fa.read() == fb.read()
+            os.remove(tmp)
+            L.pp_host_free(gz_all_ptr)
+            if not same:
+                raise SystemExit("bench.py: the index built on the GPU differs from the host-built index file")
+            ms, st = min(ci, key=lambda x: x[0])
+            t0 = time.perf_counter()
+            pp.Core.BuildDeflateIndex(gz_path, args.chunk, lift_record_cap=lift_cap())
+            host_s = time.perf_counter() - t0
+            line["create_index"] = {"value": U / ms / 1e6, "unit": "GB/s", "ms": ms, "points": st["points"],
+                                    "blocks": st["blocks"], "identical_to_host_index_file": same,
+                                    "stages_ms": {k: round(v, 3) for k, v in st.items() if k.endswith("_ms")},
+                                    "host_zlib_1thread": {"value": U / host_s / 1e9, "unit": "GB/s", "s": host_s},
+                                    "what": "pp_index_create_gpu, host buffer in, index out (best of 3 cold calls)"}
         if not args.no_cpu_baseline and world == 1:
             O = oracle()
             gz_np = np.fromfile(gz_path, np.uint8)

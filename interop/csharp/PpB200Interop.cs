@@ -79,6 +79,8 @@ internal static class LibPpB200
     [DllImport(L)] public static extern void pp_pair_free(IntPtr pair);
 
     // GPU-assisted CreateIndex, first slice: every deflate block's first bit and output offset
+    [StructLayout(LayoutKind.Sequential)] public struct PpCreateStats { public float H2dMs, ScanMs, ScanKernelMs, PlanMs, InflateMs, ChainMs, ResolveMs, CountCrcMs, GatherMs, TotalMs; public long Blocks, TotalOut; public int Segments, ScanPasses, Points, Pad; }
+    [DllImport(L)] public static unsafe extern int pp_index_create_gpu(IntPtr ctx, byte* gz, nuint gzLen, uint chunksize, uint flags, out IntPtr index, out PpCreateStats stats);
     [DllImport(L)] public static unsafe extern int pp_scan_blocks(IntPtr ctx, byte* gz, nuint gzLen, long segmentBytes, long* startBits, long* outOffsets, long cap, out long count, out long endBit, out long totalOut, out float kernelMs, out int passes);
 }
 

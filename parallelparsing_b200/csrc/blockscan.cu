@@ -81,6 +81,49 @@ static size_t gzip_header_len(const uint8_t *gz, size_t n)
     return p < n ? p : 0;
 }
 
+// ---- host walk of one fixed-codes block (RFC 1951 3.2.6), for bridging seams the search cannot see ----
+// p: first bit after the 3 header bits.  Counts the bytes the block produces; false: invalid or too long.
+static bool host_walk_fixed(const uint8_t *gz, size_t n, uint64_t &p, uint64_t &out, uint64_t max_bits)
+{
+    static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    const uint64_t end = std::min<uint64_t>((uint64_t)n * 8u, p + max_bits);
+    auto bit = [&](uint64_t i) -> uint32_t { return (gz[i >> 3] >> (i & 7u)) & 1u; };
+    for (;;) {
+        if (p + 9u + 5u + 5u + 13u > end) return false;
+        uint32_t code = 0, sym = 0xffffu;
+        for (int len = 1; len <= 9 && sym == 0xffffu; len++) {
+            code = (code << 1) | bit(p++);
+            if (len == 7 && code <= 0x17u) sym = 256u + code;
+            else if (len == 8 && code >= 0x30u && code <= 0xbfu) sym = code - 0x30u;
+            else if (len == 8 && code >= 0xc0u && code <= 0xc7u) sym = 280u + (code - 0xc0u);
+            else if (len == 9 && code >= 0x190u) sym = 144u + (code - 0x190u);
+        }
+        if (sym == 0xffffu) return false;
+        if (sym < 256u) { out++; continue; }
+        if (sym == 256u) return true;
+        if (sym > 285u) return false;
+        uint32_t length = lbase[sym - 257u];
+        for (uint32_t k = 0; k < lext[sym - 257u]; k++) length += bit(p++) << k;
+        uint32_t dc = 0;
+        for (int k = 0; k < 5; k++) dc = (dc << 1) | bit(p++);
+        if (dc > 29u) return false;
+        p += dext[dc];
+        out += length;
+    }
+}
+
+// Test hook (not part of the ABI): the host walk of the fixed-codes block whose header starts at `bit`.
+extern "C" int pp_internal_walk_fixed(const uint8_t *gz, size_t n, uint64_t bit, uint64_t *next_bit, uint64_t *out_bytes)
+{
+    uint64_t p = bit + 3u, o = 0;
+    if (!host_walk_fixed(gz, n, p, o, ~0ull >> 1)) return PP_DATA_ERROR;
+    *next_bit = p;
+    *out_bytes = o;
+    return PP_OK;
+}
+
 #define CKS(call)                                                                                 \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \
@@ -192,14 +235,23 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
                 if (o.status == -5) { rc = PP_BUF_ERROR; goto done; }
                 bool bridged = false;
                 if (s > 0 && !anchored && o.first_bit != land && land < o.first_bit && o.status >= 0 && h_gz) {
-                    // Stored blocks between where the chain landed and the first block the segment's search saw (the
-                    // search sees dynamic headers only): the empty stored block of a sync flush, as parallel gzip
-                    // writers leave one at every seam.  Their headers are walked here, on the host copy.
+                    // Stored and fixed-codes blocks between where the chain landed and the first block the segment's
+                    // search saw (the search sees dynamic headers only): the short fixed block and the empty stored
+                    // block of a sync flush that parallel gzip writers leave at every seam.  They are walked here, on
+                    // the host copy (up to 1 Mbit of fixed-codes data; beyond that the segment is walked again).
                     uint64_t p = land, add = 0;
                     size_t keep = chain.size();
                     while (p < o.first_bit) {
                         const uint64_t by = p >> 3;
                         const uint32_t h3 = (((uint32_t)h_gz[by] | ((uint32_t)(by + 1 < gz_len ? h_gz[by + 1] : 0) << 8)) >> (p & 7u)) & 7u;
+                        if (h3 == 2u) {  // fixed codes, not final
+                            uint64_t q = p + 3u, o2 = 0;
+                            if (!host_walk_fixed(h_gz, gz_len, q, o2, 1u << 20)) break;
+                            chain.push_back({p, out_base + add});
+                            add += o2;
+                            p = q;
+                            continue;
+                        }
                         if (h3 != 0u) break;  // not a non-final stored block
                         const uint64_t lb = (p + 3u + 7u) >> 3;
                         if (lb + 4u > gz_len) break;

@@ -8,7 +8,8 @@
 //   1. SCAN     pp_blockscan_kernel (blockscan_core.cuh) finds every block start and its output offset
 //               without producing a byte: all the Z_BLOCK stops.
 //   2. DECODE   consecutive blocks are grouped into segments and every segment is inflated by the
-//               product's inflate kernel — TWICE, each time with a 32 KB dictionary that holds no data but
+//               product's inflate kernel (dual-output variant: one Huffman decode, the tokens resolved
+//               twice) into TWO outputs, each against a 32 KB dictionary that holds no data but
 //               a code of its own positions: A[i] = i mod 256, B[i] = (i/256 + 1 + i mod 256) mod 256.  A
 //               byte that comes out equal in both runs never touched the dictionary: it is a literal of
 //               this segment (or a copy of one) and final.  A byte that differs is a copy, through any
@@ -499,21 +500,24 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
         i = j;
     }
     const int S = (int)segs.size();
-    std::vector<ChunkDesc> descs((size_t)2 * S);
+    // run A's slots, then run B's in the same layout: chunk s of run B = chunk s of run A + slot_delta
+    std::vector<ChunkDesc> descs((size_t)S);
     uint64_t slot_off = 512;
-    for (int r = 0; r < 2; r++)
-        for (int s = 0; s < S; s++) {
-            ChunkDesc &d = descs[(size_t)r * S + s];
-            d.in_bit = chain[seg_first[(size_t)s]].bit;
-            d.in_limit = gz_len;
-            d.slot_off = slot_off;
-            d.lead_src = (uint64_t)r * kWin;
-            d.lead_len = kWin;
-            d.out_len = segs[(size_t)s].out_len;
-            d.prefix_len = d.prefix_nl = 0;
-            (r ? segs[(size_t)s].b_off : segs[(size_t)s].a_off) = slot_off + kWin;
-            slot_off += ((uint64_t)kWin + d.out_len + 1u + 127u) & ~127ull;
-        }
+    for (int s = 0; s < S; s++) {
+        ChunkDesc &d = descs[(size_t)s];
+        d.in_bit = chain[seg_first[(size_t)s]].bit;
+        d.in_limit = gz_len;
+        d.slot_off = slot_off;
+        d.lead_src = 0;
+        d.lead_len = kWin;
+        d.out_len = segs[(size_t)s].out_len;
+        d.prefix_len = d.prefix_nl = 0;
+        segs[(size_t)s].a_off = slot_off + kWin;
+        slot_off += ((uint64_t)kWin + d.out_len + 1u + 127u) & ~127ull;
+    }
+    const uint64_t slot_delta = slot_off - 512;
+    for (int s = 0; s < S; s++) segs[(size_t)s].b_off = segs[(size_t)s].a_off + slot_delta;
+    slot_off += slot_delta;
     std::vector<uint32_t> piece_base((size_t)S + 1);
     uint32_t npieces = 0;
     for (int s = 0; s < S; s++) {
@@ -552,10 +556,10 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     CKI(cudaMemcpyAsync(d_cb.p, crc_base.data(), sizeof(uint32_t) * crc_base.size(), cudaMemcpyHostToDevice, st));
     CKI(cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), st));
     InflateLaunch cfg;
-    if (pp_internal_ctx_inflate(ctx, 2 * S, &cfg) != PP_OK) return PP_E_ARG;
+    if (pp_internal_ctx_inflate(ctx, S, &cfg) != PP_OK) return PP_E_ARG;
     mark();  // 3
-    CKI(launch_inflate(d_descs.as<ChunkDesc>(), 2 * S, comp.as<uint8_t>(), gz_len, slots.as<uint8_t>(), lead.as<uint8_t>(),
-                       d_res.as<ChunkResult>(), cfg, st));
+    CKI(launch_inflate_dual(d_descs.as<ChunkDesc>(), S, comp.as<uint8_t>(), gz_len, slots.as<uint8_t>(), lead.as<uint8_t>(),
+                            d_res.as<ChunkResult>(), cfg, slot_delta, kWin, st));
     mark();  // 4
 
     // 4. CHAIN, RESOLVE

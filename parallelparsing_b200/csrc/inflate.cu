@@ -7,10 +7,12 @@
 
 namespace pp {
 
-__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
-    pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
-                      uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
-                      uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy)
+template <bool DUAL>
+__device__ __forceinline__ void inflate_kernel_body(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp,
+                                                    uint64_t comp_bytes, uint8_t *slots, const uint8_t *__restrict__ lead,
+                                                    ChunkResult *__restrict__ results, uint32_t *scratch, size_t scratch_words,
+                                                    int *next_chunk, uint32_t comp_shift, const InflateSync &sy,
+                                                    ppinf::DualOut dual)
 {
     extern __shared__ __align__(128) uint8_t pp_smem_raw[];
     ppinf::Sm sm;
@@ -32,13 +34,33 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
         // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
         d.in_bit += 8ull * comp_shift;
         d.in_limit += comp_shift;
-        ppinf::inflate_chunk(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate);
+        ppinf::inflate_chunk<DUAL>(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate, dual);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();
             *((volatile uint32_t *)sy.done + k) = 1u;
         }
     }
+}
+
+__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
+    pp_inflate_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
+                      uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
+                      uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy)
+{
+    inflate_kernel_body<false>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
+                               comp_shift, sy, ppinf::DualOut{0, 0});
+}
+
+// GPU CreateIndex: every chunk decoded once and resolved twice, against two histories (createindex.cu).
+__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
+    pp_inflate_dual_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
+                           uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
+                           uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy,
+                           ppinf::DualOut dual)
+{
+    inflate_kernel_body<true>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
+                              comp_shift, sy, dual);
 }
 
 // Debug aid: cycles thread 0 of every CTA spent per phase since the last call (and reset).
@@ -57,7 +79,10 @@ extern "C" int pp_internal_phase_cycles(unsigned long long *out, int n)
 // changed per launch (two contexts launching different CTA sizes would otherwise race on it).
 cudaError_t inflate_set_max_smem(int threads)
 {
-    return cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ppinf::sm_bytes_for(threads));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pp_inflate_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ppinf::sm_bytes_for(threads));
 }
 
@@ -90,6 +115,29 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     const int grid = n < cfg.grid ? n : cfg.grid;
     pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
                                                         ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy);
+    return cudaGetLastError();
+}
+
+// One decode, two outputs: chunk k also lands slot_delta bytes further on in `slots`, resolved against the
+// history lead_delta bytes further on in `lead` (same geometry and scratch as launch_inflate).
+cudaError_t launch_inflate_dual(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
+                                const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, uint64_t slot_delta,
+                                uint64_t lead_delta, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    if ((slot_delta & 127u) || (lead_delta & 15u)) return cudaErrorInvalidValue;
+    const uint32_t comp_shift = (uint32_t)((uintptr_t)comp & 15u);
+    comp -= comp_shift;
+    comp_bytes += comp_shift;
+    InflateSync sy;
+    sy.gate.shift = comp_shift;
+    cudaError_t e = cudaMemsetAsync(cfg.counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const size_t smem = ppinf::sm_bytes_for(cfg.threads);
+    const int grid = n < cfg.grid ? n : cfg.grid;
+    pp_inflate_dual_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
+                                                             ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy,
+                                                             ppinf::DualOut{slot_delta, lead_delta});
     return cudaGetLastError();
 }
 

@@ -1430,7 +1430,11 @@ PP_DEV WindowCount count_window(const Sm &sm, uint32_t s0, uint32_t room)
 }
 
 // One window of a Huffman block: GUESS, SYNC, SCAN (count_window), then EMIT and RESOLVE.
-PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room)
+// outp2 (dual output, GPU CreateIndex): the same tokens resolved a second time against a second history —
+// one Huffman decode, two LZ77 resolves.  outp2 has outp's alignment modulo 16.
+template <bool DUAL = false>
+PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room,
+                                uint8_t *outp2 = nullptr)
 {
     const int T = PP_NT;
     const WindowCount c = count_window(sm, s0, room);
@@ -1452,6 +1456,7 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_PHASE(PH_EMIT);
     // RESOLVE
     resolve_window(sm, tok, outp, a, produced, nlive, rshift);
+    if (DUAL) resolve_window(sm, tok, outp2, a, produced, nlive, rshift);
     PP_PHASE(PH_RESOLVE);
     WindowOut w;
     w.next_bit = c.next_bit;
@@ -1529,12 +1534,27 @@ PP_DEV bool gate_wait(const Sm &sm, const ByteGate *g, uint64_t lo, uint64_t hi)
 #endif
 }
 
+// Dual output (GPU CreateIndex, createindex.cu): every chunk is written a second time, dual.slot_delta bytes
+// further on in the slots buffer, against the history dual.lead_delta bytes further on in the lead buffer.
+struct DualOut {
+    uint64_t slot_delta;  // multiple of 128
+    uint64_t lead_delta;  // multiple of 16
+};
+template <bool DUAL = false>
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                           const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
-                          const ByteGate *gate = nullptr)
+                          const ByteGate *gate = nullptr, DualOut dual = DualOut{0, 0})
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
+    if (DUAL) {  // the second history in front of the second output
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(lead_src + d.lead_src + dual.lead_delta);
+        uint4 *d4 = reinterpret_cast<uint4 *>(slot + dual.slot_delta);
+        const uint32_t n4 = d.lead_len / 16u;
+        PP_FOR_T(t)
+        for (uint32_t i = (uint32_t)t; i < n4; i += (uint32_t)T) d4[i] = s4[i];
+        PP_END_T
+    }
     // 1. history: copy the checkpoint window (Core.cs:158 inflateSetDictionary) in front of the output
     {
         // (lead_src == kLeadInPlace: the history is already there — the checkpoint windows were inflated
@@ -1592,6 +1612,7 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
                 PP_SYNC();
                 if (!gate_wait(sm, gate, byte0, byte0 + n)) { status = -100; break; }
                 stored_copy(sm, comp + byte0, out + produced, n);
+                if (DUAL) stored_copy(sm, comp + byte0, out + dual.slot_delta + produced, n);
                 produced += n;
                 bit = (byte0 + len) * 8u;
                 PP_PHASE(PH_STORED);
@@ -1607,7 +1628,8 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
             PP_PHASE(PH_HEADER);
             need_header = false;
         }
-        const WindowOut w = huffman_window(sm, s0, tok, rshift, out + produced, out_len - produced);
+        const WindowOut w = huffman_window<DUAL>(sm, s0, tok, rshift, out + produced, out_len - produced,
+                                                 DUAL ? out + dual.slot_delta + produced : nullptr);
         produced += w.produced;
         bit = base_byte * 8u + w.next_bit;
         // Core.cs:174: the reference throws DATA_ERROR when zlib wants input past the end of fileBuffer
@@ -1630,7 +1652,10 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     {
         const uint32_t to = ((d.lead_len + d.out_len + 1u + 127u) & ~127u) - d.lead_len;
         PP_FOR_T(t)
-        for (uint32_t i = produced + (uint32_t)t; i < to; i += (uint32_t)T) out[i] = 0;
+        for (uint32_t i = produced + (uint32_t)t; i < to; i += (uint32_t)T) {
+            out[i] = 0;
+            if (DUAL) out[dual.slot_delta + i] = 0;
+        }
         PP_END_T
     }
     // 4. results

@@ -63,6 +63,9 @@ size_t inflate_scratch_bytes(int threads, int grid);
 cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                            const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, cudaStream_t st,
                            InflateSync sy = InflateSync());
+cudaError_t launch_inflate_dual(const ChunkDesc *descs, int n, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
+                                const uint8_t *lead, ChunkResult *results, const InflateLaunch &cfg, uint64_t slot_delta,
+                                uint64_t lead_delta, cudaStream_t st);
 cudaError_t launch_bytes_stats(const uint8_t *slots, const ChunkDesc *descs, ChunkResult *results, int n,
                                cudaStream_t st);
 cudaError_t launch_scan(const ChunkDesc *descs, const ChunkResult *results, const int64_t *exact_counts, int n,

@@ -53,6 +53,26 @@ def inflate_chunk(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window
     return st, slot[lead_len: lead_len + int(res[0])], int(res[1]), int(res[2]), int(res[3])
 
 
+def inflate_chunk_dual(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window_a: np.ndarray, window_b: np.ndarray,
+                       out_len: int, T=64, subw=31):
+    """One decode, two resolves (inflate_chunk<DUAL>): returns (status, bytes against window_a, bytes against window_b)."""
+    L = lib(subw)
+    L.emu_inflate_chunk_dual.restype = C.c_int
+    L.emu_inflate_chunk_dual.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    pad = (-gz.size) % 16
+    comp = np.concatenate([gz, np.zeros(pad + 64, np.uint8)])
+    lead_len = window_a.size
+    delta = (lead_len + out_len + 1 + 127) // 128 * 128
+    slot = np.zeros(2 * delta + 256, np.uint8)
+    lead = np.ascontiguousarray(np.concatenate([window_a, window_b]))
+    res = (C.c_uint64 * 4)()
+    st = L.emu_inflate_chunk_dual(T, comp.ctypes.data, comp.size - 64, in_byte * 8 - bits, in_limit, slot.ctypes.data, delta,
+                                  lead.ctypes.data, lead_len, out_len, res)
+    n = int(res[0])
+    return st, slot[lead_len: lead_len + n], slot[delta + lead_len: delta + lead_len + n]
+
+
 def stats(subw=31, reset=True):
     out = (C.c_uint64 * 8)()
     lib(subw).emu_stats(out, int(reset))

@@ -146,3 +146,57 @@ def test_emulated_block_search_lands_on_a_true_block_start():
         if want_land is not None:
             assert land == want_land and np.array_equal(recs[:, 0], bits[i:j])
             assert ob == int(outs[j] - outs[i]) and np.array_equal(recs[:, 1], outs[i:j] - outs[i])
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU CreateIndex, DECODE step: one Huffman decode resolved against two position-coded dictionaries
+# ----------------------------------------------------------------------------------------------
+
+def _coded_windows():
+    i = np.arange(32768, dtype=np.uint32)
+    return (i & 0xFF).astype(np.uint8), (((i >> 8) + 1 + (i & 0xFF)) & 0xFF).astype(np.uint8)
+
+
+@pytest.mark.parametrize("kind,T", [("dynamic", 64), ("dynamic", 512), ("syncflush", 128), ("fixed", 64), ("stored", 64)])
+def test_dual_inflate_with_position_coded_windows_reconstructs_the_stream(kind, T):
+    """createindex.cu's method on the emulated kernel: segments of consecutive blocks are inflated with
+    two dictionaries that encode their own positions (inflate_chunk<DUAL>: one decode, two resolves); equal
+    bytes are final, differing bytes name the window position they copy; chaining the windows through the
+    segments gives back zlib's output exactly.  Also: the dual call equals two single calls."""
+    kw = dict(dynamic=dict(level=6), syncflush=dict(level=6, flush_every=30000), fixed=dict(level=6, strategy=zlib.Z_FIXED),
+              stored=dict(level=0))[kind]
+    data = corpus.fastq(2500, fixed=150, seed=4)
+    gz = corpus.gz_member(data, **kw)
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    ref = np.frombuffer(zlib.decompress(gz.tobytes(), 47), np.uint8)
+    wa, wb = _coded_windows()
+    step = max(1, len(bits) // 5)
+    firsts = list(range(0, len(bits), step))
+    got = np.zeros(tot, np.uint8)
+    win = np.zeros(32768, np.uint8)
+    dependent = 0
+    for si, b0 in enumerate(firsts):
+        b1 = firsts[si + 1] if si + 1 < len(firsts) else len(bits)
+        sb = int(bits[b0])
+        o0 = int(outs[b0])
+        o1 = int(outs[b1]) if b1 < len(bits) else int(tot)
+        in_byte, nb = (sb + 7) // 8, (8 - sb % 8) % 8
+        st, a, b = E.inflate_chunk_dual(gz, in_byte, nb, gz.size, wa, wb, o1 - o0, T, 27)
+        assert st == 0 and a.size == o1 - o0
+        if si == 1:   # the dual call is two single calls
+            ra = E.inflate_chunk(gz, in_byte, nb, gz.size, wa, o1 - o0, T, 27)
+            rb = E.inflate_chunk(gz, in_byte, nb, gz.size, wb, o1 - o0, T, 27)
+            assert np.array_equal(ra[1], a) and np.array_equal(rb[1], b)
+        a32, b32 = a.astype(np.uint32), b.astype(np.uint32)
+        dep = a32 != b32
+        pos = a32 + 256 * ((b32 - a32 - 1) & 0xFF)
+        assert (pos[dep] < 32768).all()
+        if si == 0:
+            assert not dep.any()
+        seg = np.where(dep, win[np.minimum(pos, 32767)], a)
+        got[o0:o1] = seg
+        win = np.concatenate([win, seg])[-32768:]
+        dependent += int(dep.sum())
+    assert np.array_equal(got, ref)
+    if kind == "dynamic":
+        assert dependent > 0

@@ -383,3 +383,32 @@ def test_gpu_create_index_host_half_record_cap():
         assert _plan_points(gz, 2, 1)[0] == 0          # PP_INDEX_LIFT_RECORD_CAP
         verdicts.add(want)
     assert verdicts == {0, -104}
+
+
+def test_host_walk_of_fixed_code_blocks_equals_zlib():
+    """The block scan bridges the short fixed-codes blocks at sync-flush seams on the host
+    (blockscan.cu host_walk_fixed): next block start and bytes produced equal zlib's Z_BLOCK stops."""
+    import zlib
+    from parallelparsing_b200._lib import lib
+    L = lib()
+    L.pp_internal_walk_fixed.restype = C.c_int
+    L.pp_internal_walk_fixed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    walked = 0
+    for data, kw in ((corpus.fastq(300, fixed=150), dict(strategy=zlib.Z_FIXED, flush_every=7000)),
+                     (corpus.fastq(50), dict(strategy=zlib.Z_FIXED)),
+                     (bytes(np.random.default_rng(5).integers(0, 256, 5000, dtype=np.uint8)), dict(strategy=zlib.Z_FIXED, flush_every=999))):
+        gz = corpus.gz_member(data, 6, **kw)
+        bits, outs, kinds, end, tot = O.block_stops(gz)
+        for i in range(len(bits)):
+            hdr3 = (int.from_bytes(gz[int(bits[i]) // 8: int(bits[i]) // 8 + 2].tobytes(), "little") >> (int(bits[i]) % 8)) & 7
+            if hdr3 >> 1 != 1:
+                continue
+            nxt, ob = C.c_uint64(), C.c_uint64()
+            assert L.pp_internal_walk_fixed(gz.ctypes.data, gz.size, int(bits[i]), C.byref(nxt), C.byref(ob)) == 0
+            want_next = int(bits[i + 1]) if i + 1 < len(bits) else None
+            want_out = (int(outs[i + 1]) if i + 1 < len(bits) else int(tot)) - int(outs[i])
+            assert ob.value == want_out, i
+            if want_next is not None:
+                assert nxt.value == want_next, i
+            walked += 1
+    assert walked > 10
