@@ -121,7 +121,7 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
     uint32_t lcnt[16], dcnt[16];
     for (int l = 0; l < 16; l++) lcnt[l] = dcnt[l] = 0;
     const uint32_t total = nlen + ndist;
-    uint32_t have = 0, prev = 0;
+    uint32_t have = 0, prev = 0, lensyms = 0;
     bool eob = false;
     // running Kraft sums (in units of 2^-15): an over-subscribed set is rejected as soon as it overflows —
     // at a wrong position the lengths are noise and that happens within a few dozen symbols, not after 300
@@ -157,6 +157,7 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
             if (at < nlen) {
                 lcnt[val]++;
                 if (at == 256u && val) eob = true;
+                if (at > 256u && val) lensyms++;
                 if (val) room_l -= 1 << (15 - val);
             } else {
                 dcnt[val]++;
@@ -176,6 +177,10 @@ PP_HD bool probe_dynamic_header(const BitPeek &b, uint64_t pos)
             if (left < 0) return false;                              // over-subscribed
         }
         if (left > 0 && maxlen != 1 && !(set == 1 && maxlen == 0)) return false;  // incomplete
+        // Stricter than zlib, which is fine for a SEARCH (a true start that is turned down only costs a re-walk
+        // of its seam): length symbols with a code but not one distance code — zlib would accept the header and
+        // fail at the first match; no compressor writes it, noise does (seen on the 10 M-read corpus).
+        if (set == 1 && maxlen == 0 && lensyms) return false;
     }
     return true;
 }
@@ -221,7 +226,9 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
             for (uint32_t i = 0; i < kSpan; i++) {
                 const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
                 const uint64_t p = base + rel;
-                if (p < in.end_bit && probe_cheap(bp, p)) {
+                // (BFINAL set: only the stream's last block may say so, and a search that skips it costs one short
+                // re-walk at the very end; half of the false candidates go with it)
+                if (p < in.end_bit && bp_peek(bp, p, 1) == 0u && probe_cheap(bp, p)) {
                     const uint32_t at = atomic_inc_u32(&sm.u[9]);
                     if (at < cap) cand[at] = rel;
                 }
@@ -240,7 +247,8 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
                 PP_FOR_T(t)
                 for (uint32_t i = 0; i < kSpan; i++) {
                     const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
-                    if (base + rel < in.end_bit && probe_dynamic_header(bp, base + rel)) PP_ATOMIC_MIN(&sm.u[8], rel);
+                    if (base + rel < in.end_bit && bp_peek(bp, base + rel, 1) == 0u && probe_dynamic_header(bp, base + rel))
+                        PP_ATOMIC_MIN(&sm.u[8], rel);
                 }
                 PP_END_T
             }

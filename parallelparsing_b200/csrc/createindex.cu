@@ -200,27 +200,40 @@ __global__ void __launch_bounds__(256)
         const uint32_t valid_from = g.out_off >= kWin ? 0u : kWin - (uint32_t)g.out_off;
         uint4 *A = reinterpret_cast<uint4 *>(slots + g.a_off);
         const uint4 *B = reinterpret_cast<const uint4 *>(slots + g.b_off);
-        for (uint32_t i = from / 16u + threadIdx.x; i * 16u < to; i += blockDim.x) {
-            uint4 a = A[i];
-            const uint4 b = B[i];
-            if (a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w) continue;  // sixteen final bytes
-            uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+        // four 16-byte groups per thread and trip: eight independent loads in flight
+        for (uint32_t i0 = from / 16u + threadIdx.x; i0 * 16u < to; i0 += 4u * blockDim.x) {
+            uint4 av[4], bv4[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (aw[q] == bw[q]) continue;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t av = (aw[q] >> (8 * k)) & 0xffu, bv = (bw[q] >> (8 * k)) & 0xffu;
-                    if (av == bv || i * 16u + 4u * q + k >= g.out_len) continue;
-                    const uint32_t pos = ci_pos(av, bv);
-                    uint32_t x = 0;
-                    if (pos >= kWin || pos < valid_from || !w) atomicOr(bad, 2u);
-                    else x = w[pos];
-                    aw[q] = (aw[q] & ~(0xffu << (8 * k))) | (x << (8 * k));
-                }
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                if (i * 16u < to) {
+                    av[u] = A[i];
+                    bv4[u] = B[i];
+                } else av[u] = bv4[u] = make_uint4(0u, 0u, 0u, 0u);
             }
-            A[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                const uint4 a = av[u], b = bv4[u];
+                if (a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w) continue;  // sixteen final bytes
+                uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (aw[q] == bw[q]) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t x0 = (aw[q] >> (8 * k)) & 0xffu, x1 = (bw[q] >> (8 * k)) & 0xffu;
+                        if (x0 == x1 || i * 16u + 4u * q + k >= g.out_len) continue;
+                        const uint32_t pos = ci_pos(x0, x1);
+                        uint32_t x = 0;
+                        if (pos >= kWin || pos < valid_from || !w) atomicOr(bad, 2u);
+                        else x = w[pos];
+                        aw[q] = (aw[q] & ~(0xffu << (8 * k))) | (x << (8 * k));
+                    }
+                }
+                A[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+            }
         }
     }
 }

@@ -1033,9 +1033,35 @@ def _same_index_file(pp, ix, ox, tmp_path, tag):
     assert ix.ChunkMaxBytes == ox.chunk_max_bytes
 
 
+def _mixed_block_stream(data: bytes) -> np.ndarray:
+    """One gzip member whose deflate blocks alternate between stored, fixed-codes and dynamic every few KB
+    (raw deflate pieces joined with full flushes; the last piece carries BFINAL)."""
+    import struct
+    rng = np.random.default_rng(7)
+    out = [b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"]
+    pos, k = 0, 0
+    comp = None
+    while pos < len(data):
+        n = int(rng.integers(2000, 90000))
+        piece = data[pos: pos + n]
+        pos += n
+        level, strategy = [(0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (6, zlib.Z_DEFAULT_STRATEGY)][k % 3]
+        k += 1
+        # one compressor per piece would lose the history: use ONE compressor and switch its parameters is not in
+        # Python's zlib, so pieces are independent streams with an empty history -> legal in one member as long as
+        # no piece is final before the last: Z_FULL_FLUSH ends each on a byte boundary without BFINAL
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        body = c.compress(piece) + (c.flush(zlib.Z_FINISH) if pos >= len(data) else c.flush(zlib.Z_FULL_FLUSH))
+        out.append(body)
+    out.append(struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF))
+    return np.frombuffer(b"".join(out), np.uint8)
+
+
 @pytest.mark.parametrize("mode,chunk", [("dynamic6", 1000), ("dynamic6", 100), ("dynamic1", 1000), ("dynamic9", 5000),
                                         ("syncflush", 100), ("fixed", 1000), ("stored", 200), ("huffman", 1000),
-                                        ("native_lengths", 1000), ("tiny", 1000), ("chunk_lt8", 5), ("lognormal", 20)])
+                                        ("native_lengths", 1000), ("tiny", 1000), ("chunk_lt8", 5), ("lognormal", 20),
+                                        ("empty", 1000), ("one_byte", 1000), ("zeros_lift", 1000), ("repeat32k", 50),
+                                        ("binary_at", 300), ("mixed_members_of_blocks", 40)])
 def test_gpu_create_index_equals_oracle(device, tmp_path, mode, chunk):
     """Points (Input, Bits, Output), 32 KB windows, offsets and ChunkMaxBytes of the index built on the GPU
     equal the oracle's serial inflate(Z_BLOCK) pass: the serialized files are identical.  Streams of dynamic,
@@ -1044,9 +1070,23 @@ def test_gpu_create_index_equals_oracle(device, tmp_path, mode, chunk):
     import parallelparsing_b200 as pp
     kw = dict(dynamic6=dict(level=6), dynamic1=dict(level=1), dynamic9=dict(level=9), fixed=dict(level=6, strategy=zlib.Z_FIXED),
               stored=dict(level=0), huffman=dict(level=6, strategy=zlib.Z_HUFFMAN_ONLY), syncflush=dict(level=6, flush_every=70000),
-              native_lengths=dict(level=6), tiny=dict(level=6), chunk_lt8=dict(level=6), lognormal=dict(level=6))[mode]
-    lift = mode == "lognormal"
-    if mode == "native_lengths":
+              native_lengths=dict(level=6), tiny=dict(level=6), chunk_lt8=dict(level=6), lognormal=dict(level=6)).get(mode, dict(level=6))
+    lift = mode in ("lognormal", "zeros_lift", "repeat32k", "binary_at", "mixed_members_of_blocks")
+    rng = np.random.default_rng(11)
+    if mode == "empty":
+        data = b""
+    elif mode == "one_byte":
+        data = b"@"
+    elif mode == "zeros_lift":                      # ratio ~1000:1: a few blocks of many megabytes, no '@' at all
+        data = bytes(12_000_000)
+    elif mode == "repeat32k":                       # matches at the far end of the window, across every segment seam
+        unit = b"@" + bytes(rng.integers(65, 91, 32767, dtype=np.uint8))
+        data = unit * 40 + corpus.fastq(500, fixed=150) + unit * 10
+    elif mode == "binary_at":                       # incompressible bytes ('@' is 1 in 256 of them) between text
+        data = corpus.fastq(3000, fixed=150) + bytes(rng.integers(0, 256, 3_000_000, dtype=np.uint8)) + corpus.fastq(3000, fixed=150)
+    elif mode == "mixed_members_of_blocks":         # stored, fixed and dynamic blocks alternating every few KB
+        data = corpus.fastq(20000, fixed=150)
+    elif mode == "native_lengths":
         data = corpus.fastq(30000)
     elif mode == "tiny":
         data = corpus.fastq(20, fixed=150)
@@ -1054,7 +1094,10 @@ def test_gpu_create_index_equals_oracle(device, tmp_path, mode, chunk):
         data = corpus.fastq(600, lognormal=(10000, 0.5))
     else:
         data = corpus.fastq(40000, fixed=150)
-    gz = corpus.gz_member(data, **kw)
+    if mode == "mixed_members_of_blocks":
+        gz = _mixed_block_stream(data)
+    else:
+        gz = corpus.gz_member(data, **kw)
     ox = O.OracleIndex.build(gz, chunk, lift)
     ix, st = pp.Core.BuildDeflateIndexGpu(gz, chunk, device, lift_record_cap=lift, want_stats=True)
     assert st["total_out"] == len(data) and st["points"] == ox.count
