@@ -178,7 +178,7 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
             g.search = s ? 1u : 0u;
             g.rec_off = (uint32_t)s * rec_cap;
             g.rec_cap = rec_cap;
-            g.pad = 0;
+            g.pad = s + 1 == nseg ? 1u : 0u;   // bit 0: the search may take a block with BFINAL set (last segment only)
         }
         std::vector<int> todo((size_t)nseg);
         for (int s = 0; s < nseg; s++) todo[(size_t)s] = s;

@@ -207,6 +207,7 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
         bp.nw = comp_bytes / 4u;
         bp.shift = shift_bits;
         uint64_t found = ~0ull;
+        const bool allow_final = (in.pad & 1u) != 0u;
         // Rounds of T x kSpan positions.  Pass 1: every thread runs the cheap filter over kSpan positions
         // and appends the survivors (~1 %) to a list in shared memory; pass 2: one survivor per THREAD
         // through the full probe (a serial decode of up to ~300 code lengths) — all lanes busy with
@@ -226,9 +227,9 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
             for (uint32_t i = 0; i < kSpan; i++) {
                 const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
                 const uint64_t p = base + rel;
-                // (BFINAL set: only the stream's last block may say so, and a search that skips it costs one short
-                // re-walk at the very end; half of the false candidates go with it)
-                if (p < in.end_bit && bp_peek(bp, p, 1) == 0u && probe_cheap(bp, p)) {
+                // (BFINAL set: only the stream's last block may say so, so only the last segment's search takes such
+                // a candidate — in.pad bit 0; half of the false candidates go with it)
+                if (p < in.end_bit && (allow_final || bp_peek(bp, p, 1) == 0u) && probe_cheap(bp, p)) {
                     const uint32_t at = atomic_inc_u32(&sm.u[9]);
                     if (at < cap) cand[at] = rel;
                 }
@@ -247,7 +248,7 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
                 PP_FOR_T(t)
                 for (uint32_t i = 0; i < kSpan; i++) {
                     const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
-                    if (base + rel < in.end_bit && bp_peek(bp, base + rel, 1) == 0u && probe_dynamic_header(bp, base + rel))
+                    if (base + rel < in.end_bit && (allow_final || bp_peek(bp, base + rel, 1) == 0u) && probe_dynamic_header(bp, base + rel))
                         PP_ATOMIC_MIN(&sm.u[8], rel);
                 }
                 PP_END_T
