@@ -178,7 +178,9 @@ int scan_blocks_resident(int device, int sm_count, cudaStream_t st, const uint8_
             g.search = s ? 1u : 0u;
             g.rec_off = (uint32_t)s * rec_cap;
             g.rec_cap = rec_cap;
-            g.pad = s + 1 == nseg ? 1u : 0u;   // bit 0: the search may take a block with BFINAL set (last segment only)
+            // bit 0: the search may take a block with BFINAL set — where the stream's last block can start: the last segment
+            // and whatever lies within 1 MiB of the end (a longer final block costs a re-walk of its seam, no more)
+            g.pad = (s + 1 == nseg || g.end_bit + (8u << 20) >= stream_bits) ? 1u : 0u;
         }
         std::vector<int> todo((size_t)nseg);
         for (int s = 0; s < nseg; s++) todo[(size_t)s] = s;

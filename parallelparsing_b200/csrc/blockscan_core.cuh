@@ -227,8 +227,8 @@ PP_DEV void scan_segment(const Sm &sm, const ScanSegIn &in, const uint8_t *comp,
             for (uint32_t i = 0; i < kSpan; i++) {
                 const uint32_t rel = i * (uint32_t)T + (uint32_t)t;
                 const uint64_t p = base + rel;
-                // (BFINAL set: only the stream's last block may say so, so only the last segment's search takes such
-                // a candidate — in.pad bit 0; half of the false candidates go with it)
+                // (BFINAL set: only the stream's last block may say so, so only searches near the stream's end take
+                // such a candidate — in.pad bit 0; half of the false candidates go with it)
                 if (p < in.end_bit && (allow_final || bp_peek(bp, p, 1) == 0u) && probe_cheap(bp, p)) {
                     const uint32_t at = atomic_inc_u32(&sm.u[9]);
                     if (at < cap) cand[at] = rel;

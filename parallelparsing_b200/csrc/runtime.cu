@@ -49,6 +49,10 @@ static void pool_free(void *p, cudaStream_t st)
     if (p) cudaFreeAsync(p, st);
 }
 
+struct pp_ctx;
+static cudaError_t ctx_arena_get(pp_ctx *c, size_t bytes, uint8_t **out, size_t *cap);  // caller holds c->mu
+static void ctx_arena_put(pp_ctx *c, uint8_t *p, size_t cap);                            // takes c->mu
+
 // Small RAII helper for the single-call entry points.
 struct DevBuf {
     void *p = nullptr;
@@ -69,6 +73,9 @@ struct pp_ctx {
     uint32_t *d_map = nullptr;
     int *d_counter = nullptr;
     int parse_per_sm = 0;  // resident CTAs of the parse kernel per SM (its look-back needs a resident grid)
+    // pinned + mapped host arenas of finished jobs, kept for the next job of this context: cudaHostAlloc and
+    // cudaFreeHost are driver calls that map into every device of the process (1-2 ms each with several GPUs)
+    std::vector<std::pair<uint8_t *, size_t>> arenas;
     const InflateLaunch &inflate_cfg(int n_chunks) const { return n_chunks <= wide.grid ? wide : dense; }
 };
 
@@ -101,6 +108,44 @@ static int ctx_setup_inflate(pp_ctx *c)
         return PP_E_CUDA;
     }
     return PP_OK;
+}
+
+static cudaError_t ctx_arena_get(pp_ctx *c, size_t bytes, uint8_t **out, size_t *cap)
+{
+    size_t best = c->arenas.size();
+    for (size_t i = 0; i < c->arenas.size(); i++)
+        if (c->arenas[i].second >= bytes && (best == c->arenas.size() || c->arenas[i].second < c->arenas[best].second)) best = i;
+    if (best != c->arenas.size()) {
+        *out = c->arenas[best].first;
+        *cap = c->arenas[best].second;
+        c->arenas.erase(c->arenas.begin() + (long)best);
+        return cudaSuccess;
+    }
+    size_t want = 64 << 10;
+    while (want < bytes) want *= 2;
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);
+    if (e != cudaSuccess) return e;
+    *out = (uint8_t *)p;
+    *cap = want;
+    return cudaSuccess;
+}
+static void ctx_arena_put(pp_ctx *c, uint8_t *p, size_t cap)
+{
+    if (!p) return;
+    uint8_t *drop = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->arenas.emplace_back(p, cap);
+        if (c->arenas.size() > 8) {  // keep the eight largest
+            size_t small = 0;
+            for (size_t i = 1; i < c->arenas.size(); i++)
+                if (c->arenas[i].second < c->arenas[small].second) small = i;
+            drop = c->arenas[small].first;
+            c->arenas.erase(c->arenas.begin() + (long)small);
+        }
+    }
+    if (drop) cudaFreeHost(drop);
 }
 
 static constexpr uint64_t kTile = 2048;  // padding granule of the compressed buffers
@@ -136,6 +181,8 @@ struct pp_job {
     cudaStream_t st_alloc = nullptr;  // stream the pooled allocations are ordered on (the context's)
     int device = 0;
     uint8_t *h_arena = nullptr;       // ONE pinned, mapped allocation behind every small host mirror below
+    size_t h_arena_cap = 0;
+    pp_ctx *arena_owner = nullptr;    // the context whose arena cache h_arena goes back to
     // pinned host mirrors
     ChunkResult *h_results = nullptr;
     ParseDesc *h_pdesc = nullptr;
@@ -300,6 +347,7 @@ void pp_close(pp_ctx *ctx)
         }
     cudaFree(ctx->d_map);
     cudaFree(ctx->d_counter);
+    for (auto &a : ctx->arenas) cudaFreeHost(a.first);
     delete ctx;
 }
 
@@ -350,7 +398,8 @@ void pp_job_free(pp_job *j)
                     (void *)j->d_tile_base, (void *)j->d_parse_work, (void *)j->d_avail, (void *)j->d_cwin,
                     (void *)j->d_wdescs, (void *)j->d_wresults})
         pool_free(p, st);
-    cudaFreeHost(j->h_arena);
+    if (j->arena_owner) ctx_arena_put(j->arena_owner, j->h_arena, j->h_arena_cap);
+    else cudaFreeHost(j->h_arena);
     for (cudaEvent_t e : {j->ev_reset, j->ev_lead, j->ev_exec_done})
         if (e) cudaEventDestroy(e);
     cudaFreeHost(j->h_lead);
@@ -504,7 +553,8 @@ static int job_create_inner(pp_job *j, pp_ctx *ctx, const pp_index *ix, size_t g
                          o_marks = o_wres + up(sizeof(ChunkResult) * n1),
                          o_done = o_marks + up(sizeof(unsigned long long) * ((size_t)j->n_marks + 2)),
                          total = o_done + up(sizeof(uint32_t) * n1);
-            CK(cudaHostAlloc(&j->h_arena, total, cudaHostAllocMapped));
+            CK(ctx_arena_get(ctx, total, &j->h_arena, &j->h_arena_cap));
+            j->arena_owner = ctx;
             memset(j->h_arena, 0, total);
             j->h_results = (ChunkResult *)(j->h_arena + o_res);
             j->h_pdesc = (ParseDesc *)(j->h_arena + o_pd);
@@ -1281,6 +1331,16 @@ int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_i
         pin_index_windows(ix1);
         pin_index_windows(ix2);
         if (flags & PP_JOB_COMPACT_WINDOWS) { pin_index_cwin(ix1); pin_index_cwin(ix2); }
+        // R2 parts are widened by one chunk on either side: checkpoints fall at different records in the two files,
+        // so the mates of a part's first and last R1 records usually sit in the neighbour's boundary chunk — decoding
+        // that chunk here from the start (two chunks among hundreds) spares a second, serial round of top-up jobs
+        const int32_t nch2 = ix2->count() - 1;
+        std::vector<int32_t> x2(P), m2(P);
+        for (size_t g = 0; g < P; g++) {
+            x2[g] = n2[g] > 0 ? std::max(f2[g] - 1, 0) : f2[g];
+            m2[g] = n2[g] > 0 ? std::min(f2[g] + n2[g] + 1, nch2) - x2[g] : 0;
+            p->info.topup_chunks += m2[g] - n2[g];
+        }
         // phase 1: every GPU decodes its part of R1 and of R2 concurrently (two contexts = two streams:
         // the second job's CTAs fill the SMs the first one's last, thin wave leaves idle)
         std::vector<pp_job *> main2(P, nullptr);
@@ -1295,7 +1355,7 @@ int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_i
                 });
                 th.emplace_back([&, g]() {
                     int e = ctx_acquire(devices[g], &p->ctx2[g]);
-                    if (e == PP_OK) e = pp_decompress_all(p->ctx2[g], ix2, gz2, gz2_len, f2[g], n2[g], flags, &main2[g]);
+                    if (e == PP_OK) e = pp_decompress_all(p->ctx2[g], ix2, gz2, gz2_len, x2[g], m2[g], flags, &main2[g]);
                     e2[g] = e;
                 });
             }
@@ -1309,26 +1369,35 @@ int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_i
             if (e1[g] < 0 && p->info.status == 0) p->info.status = e1[g];
             if (e2[g] < 0 && p->info.status == 0) p->info.status = e2[g];
         }
-        // global ordinals: per part, and per chunk of R2 (for the top-up ranges)
-        std::vector<int64_t> b1(P + 1, 0), b2(P + 1, 0);
+        // global ordinals: per part of R1, and per chunk of R2 (a chunk's record count does not depend on the job
+        // that decoded it: under PP_JOB_STRICT the H1 duplicate is a property of the checkpoint)
+        std::vector<int64_t> b1(P + 1, 0);
+        for (size_t g = 0; g < P; g++) b1[g + 1] = b1[g] + p->r1[g]->info.total_records;
+        std::vector<int64_t> cb2((size_t)nch2 + 1, 0);   // first-record ordinal of every R2 chunk, total at the end
         for (size_t g = 0; g < P; g++) {
-            b1[g + 1] = b1[g] + p->r1[g]->info.total_records;
-            b2[g + 1] = b2[g] + main2[g]->info.total_records;
+            const pp_job *j = main2[g];
+            for (int32_t c = f2[g]; c < f2[g] + n2[g]; c++) {   // the part's own chunks
+                const int k = c - x2[g];
+                const int64_t hi = k + 1 < j->n ? j->h_pdesc[k + 1].rec_base : j->info.total_records;
+                cb2[(size_t)c + 1] = hi - j->h_pdesc[k].rec_base;
+            }
         }
-        std::vector<int64_t> cb2;   // first-record ordinal of every R2 chunk, total at the end
-        for (size_t g = 0; g < P; g++)
-            for (int k = 0; k < main2[g]->n; k++) cb2.push_back(b2[g] + main2[g]->h_pdesc[k].rec_base);
-        cb2.push_back(b2[P]);
+        for (int32_t c = 0; c < nch2; c++) cb2[(size_t)c + 1] += cb2[(size_t)c];
+        std::vector<int64_t> lo2(P), hi2(P);               // ordinals the widened R2 job of part g holds
+        for (size_t g = 0; g < P; g++) {
+            lo2[g] = cb2[(size_t)x2[g]];
+            hi2[g] = cb2[(size_t)(x2[g] + m2[g])];
+        }
         p->info.records_r1 = b1[P];
-        p->info.records_r2 = b2[P];
-        p->info.pairs = std::min(b1[P], b2[P]);
+        p->info.records_r2 = cb2[(size_t)nch2];
+        p->info.pairs = std::min(b1[P], cb2[(size_t)nch2]);
         // phase 2: mates of this part's R1 records that a neighbour's R2 part holds
         std::vector<std::thread> th;
         std::vector<int> e3(2 * P, PP_OK);
         std::vector<pp_job *> left(P, nullptr), right(P, nullptr);
         std::vector<int64_t> lbase(P, 0), rbase(P, 0);
         for (size_t g = 0; g < P; g++) {
-            const int64_t a1 = b1[g], z1 = std::min(b1[g + 1], b2[P]), a2 = b2[g], z2 = b2[g + 1];
+            const int64_t a1 = b1[g], z1 = std::min(b1[g + 1], cb2[(size_t)nch2]), a2 = lo2[g], z2 = hi2[g];
             struct Gap { int64_t lo, hi; pp_job **dst; int64_t *base; int slot; };
             const Gap gaps[2] = {{a1, std::min(z1, a2), &left[g], &lbase[g], (int)(2 * g)},
                                  {std::max(a1, z2), z1, &right[g], &rbase[g], (int)(2 * g + 1)}};
@@ -1351,7 +1420,7 @@ int pp_pair_decompress_all(const int32_t *devices, int32_t n_devices, const pp_i
             p->r1_base[g] = b1[g];
             if (left[g]) { p->r2[g].push_back(left[g]); p->r2_base[g].push_back(lbase[g]); }
             p->r2[g].push_back(main2[g]);
-            p->r2_base[g].push_back(b2[g]);
+            p->r2_base[g].push_back(lo2[g]);
             if (right[g]) { p->r2[g].push_back(right[g]); p->r2_base[g].push_back(rbase[g]); }
         }
         for (int e : e3)
