@@ -87,6 +87,10 @@ int main(int argc, char **argv)
         const int rm = pp_decompress_all_multi(devs, 1, ix, dummy, sizeof dummy, 0, &m);
         const int rp = pp_pair_decompress_all(devs, 1, ix, dummy, sizeof dummy, ix, dummy, sizeof dummy, 0, &pr);
         printf("multi_nodata %d\npair_nodata %d\n", rm, rp);
+        /* CreateIndex on the GPU needs a context: without one it is an argument error, the host pass stays available */
+        pp_index *gi = NULL;
+        pp_create_stats cs;
+        printf("create_gpu_noctx %d\n", pp_index_create_gpu(NULL, dummy, sizeof dummy, 1000, 0, &gi, &cs));
         if (m) pp_multi_free(m);
         if (pr) pp_pair_free(pr);
     }

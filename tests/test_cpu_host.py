@@ -260,6 +260,7 @@ def test_c_abi_from_plain_c(tmp_path):
     assert code == (0 if torch.cuda.is_available() else -101), kv["open"]
     if not torch.cuda.is_available():   # no device: the multi-GPU and paired calls say so, they never fall back
         assert int(kv["multi_nodata"]) == -101 and int(kv["pair_nodata"]) == -101
+        assert int(kv["create_gpu_noctx"]) == -102
 
 
 def test_record_cap_verdict_matches_oracle_around_the_limit():
