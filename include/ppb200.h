@@ -323,7 +323,8 @@ typedef struct pp_create_stats {  /* where pp_index_create_gpu's time went (CUDA
  * gz: one complete gzip member; more members or trailing bytes: PP_E_UNSUPPORTED, use
  * pp_index_create.  PP_E_RECORD_TOO_LONG / PP_INDEX_LIFT_RECORD_CAP as pp_index_create.  A stream that is
  * both damaged and holds an over-long record may report the other of the two errors.  Device memory:
- * about twice the inflated size.  stats may be NULL.
+ * about twice the inflated size; PP_MEM_ERROR when the device cannot provide it (pp_index_create then is
+ * the way).  stats may be NULL.
  */
 int pp_index_create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t chunksize, uint32_t flags,
                         pp_index **out, pp_create_stats *stats);

@@ -419,6 +419,10 @@ struct Dev {  // stream-ordered allocation from the device's pool (release thres
 #define CKI(call)                                                                                                   \
     do {                                                                                                            \
         cudaError_t e_ = (call);                                                                                    \
+        if (e_ == cudaErrorMemoryAllocation) { /* not enough device memory: the caller has the host pass */          \
+            (void)cudaGetLastError();                                                                               \
+            return PP_MEM_ERROR;                                                                                    \
+        }                                                                                                           \
         if (e_ != cudaSuccess) {                                                                                    \
             fprintf(stderr, "ppb200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
             return PP_E_CUDA;                                                                                       \
