@@ -90,7 +90,7 @@ void pp_index::reserve_windows(size_t points)
     win_cap = points;
 }
 
-uint8_t *pp_index::append_window()
+uint8_t *pp_index::append_window(bool zero)
 {
     cwin_points = -1;  // the compact windows no longer cover every point
     size_t n = output.size();  // caller has already pushed the scalar fields
@@ -108,7 +108,7 @@ uint8_t *pp_index::append_window()
         win_cap = cap;
     }
     uint8_t *w = windows + (n - 1) * (size_t)PP_WINSIZE;
-    memset(w, 0, PP_WINSIZE);
+    if (zero) memset(w, 0, PP_WINSIZE);
     return w;
 }
 
@@ -183,12 +183,24 @@ int index_plan_points(const CiBlockStat *b, size_t nb, uint64_t total_out, uint6
 void index_from_plan(pp_index *ix, const std::vector<CiPointPlan> &plan)
 {
     ix->reserve_windows(ix->output.size() + plan.size());
-    for (const CiPointPlan &p : plan) {
-        const int64_t n = p.output - p.off_from;
-        add_point(ix, p.bits, p.input, p.output, 0, nullptr, nullptr, 0);
-        ix->off_len.back() = (int32_t)n;
-        ix->offsets.resize(ix->offsets.size() + (size_t)n);
+    size_t off_total = ix->offsets.size();
+    for (const CiPointPlan &p : plan) {   // add_point's bookkeeping (Index.cs:24-48) without touching the window bytes:
+        const int64_t n = p.output - p.off_from;  // the caller overwrites every one of them
+        if (ix->count() == 0) {
+            ix->chunk_max_bytes = (int32_t)p.output;
+        } else {
+            const int32_t sz = (int32_t)p.output - (int32_t)ix->output.back();
+            if (sz > ix->chunk_max_bytes) ix->chunk_max_bytes = sz;
+        }
+        ix->output.push_back(p.output);
+        ix->input.push_back(p.input);
+        ix->bits.push_back(p.bits);
+        ix->off_pos.push_back((int64_t)off_total);
+        ix->off_len.push_back((int32_t)n);
+        off_total += (size_t)n;
+        ix->append_window(false);
     }
+    ix->offsets.resize(off_total);
 }
 
 extern "C" {

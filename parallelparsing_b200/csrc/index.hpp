@@ -36,7 +36,7 @@ struct pp_index {
     int32_t count() const { return (int32_t)output.size(); }
     const uint8_t *window(int32_t i) const { return windows + (size_t)i * PP_WINSIZE; }
     const uint8_t *offset(int32_t i) const { return offsets.data() + off_pos[(size_t)i]; }
-    uint8_t *append_window();  // returns the (zeroed) window slot of the point being added
+    uint8_t *append_window(bool zero = true);  // returns the (zeroed) window slot of the point being added
     void reserve_windows(size_t points);  // capacity for that many points in one allocation
     ~pp_index();
 };
