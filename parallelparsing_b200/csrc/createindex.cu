@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256)
         const uint32_t valid_from = g.out_off >= kWin ? 0u : kWin - (uint32_t)g.out_off;
         uint4 *A = reinterpret_cast<uint4 *>(slots + g.a_off);
         const uint4 *B = reinterpret_cast<const uint4 *>(slots + g.b_off);
+        const bool fast = w != nullptr && valid_from == 0u;  // a whole window in front of the segment: every position is legal
         // four 16-byte groups per thread and trip: eight independent loads in flight
         for (uint32_t i0 = from / 16u + threadIdx.x; i0 * 16u < to; i0 += 4u * blockDim.x) {
             uint4 av[4], bv4[4];
@@ -218,18 +219,37 @@ __global__ void __launch_bounds__(256)
                 if (a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w) continue;  // sixteen final bytes
                 uint32_t aw[4] = {a.x, a.y, a.z, a.w};
                 const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                if (fast && i * 16u + 16u <= g.out_len) {
+                    // four bytes at a time: hi = (b - a - 1) per byte is the position's high byte, a its low byte
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (aw[q] == bw[q]) continue;
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t eq = __vcmpeq4(aw[q], bw[q]);  // 0xff in every byte that is final
+                        if (eq == 0xffffffffu) continue;
+                        const uint32_t hi = __vsub4(__vsub4(bw[q], aw[q]), 0x01010101u);
+                        if (hi & ~eq & 0x80808080u) atomicOr(bad, 2u);  // a position >= 32768: no such dictionary byte
+                        uint32_t r = aw[q];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t x0 = (aw[q] >> (8 * k)) & 0xffu, x1 = (bw[q] >> (8 * k)) & 0xffu;
-                        if (x0 == x1 || i * 16u + 4u * q + k >= g.out_len) continue;
-                        const uint32_t pos = ci_pos(x0, x1);
-                        uint32_t x = 0;
-                        if (pos >= kWin || pos < valid_from || !w) atomicOr(bad, 2u);
-                        else x = w[pos];
-                        aw[q] = (aw[q] & ~(0xffu << (8 * k))) | (x << (8 * k));
+                        for (int k = 0; k < 4; k++) {
+                            if ((eq >> (8 * k)) & 1u) continue;
+                            const uint32_t pos = __byte_perm(aw[q], hi, (uint32_t)((4 + k) << 4 | k)) & 0x7fffu;
+                            r = __byte_perm(r, (uint32_t)w[pos], k == 0 ? 0x3214 : k == 1 ? 0x3240 : k == 2 ? 0x3410 : 0x4210);
+                        }
+                        aw[q] = r;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (aw[q] == bw[q]) continue;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t x0 = (aw[q] >> (8 * k)) & 0xffu, x1 = (bw[q] >> (8 * k)) & 0xffu;
+                            if (x0 == x1 || i * 16u + 4u * q + k >= g.out_len) continue;
+                            const uint32_t pos = ci_pos(x0, x1);
+                            uint32_t x = 0;
+                            if (pos >= kWin || pos < valid_from || !w) atomicOr(bad, 2u);
+                            else x = w[pos];
+                            aw[q] = (aw[q] & ~(0xffu << (8 * k))) | (x << (8 * k));
+                        }
                     }
                 }
                 A[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
@@ -352,13 +372,18 @@ __global__ void __launch_bounds__(256)
     pp_ci_crc_kernel(const CiSeg *__restrict__ segs, const uint32_t *__restrict__ piece_base, int S, uint32_t npieces,
                      const uint8_t *__restrict__ slots, uint32_t *__restrict__ crcs)
 {
-    __shared__ uint32_t tab[256], shift_parts[256], red[8];
+    __shared__ uint32_t tab[4][256], shift_parts[256], red[8];  // tab[k][i]: byte i followed by k zero bytes
     const uint32_t t = threadIdx.x;
     {
         uint32_t c = t;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
-        tab[t] = c;
+        tab[0][t] = c;
         shift_parts[t] = ci_xpow(8u * kCrcPart * t);  // t parts further on
+    }
+    __syncthreads();
+    for (int k = 1; k < 4; k++) {
+        const uint32_t p = tab[k - 1][t];
+        tab[k][t] = (p >> 8) ^ tab[0][p & 0xffu];
     }
     __syncthreads();
     for (uint32_t piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
@@ -372,16 +397,24 @@ __global__ void __launch_bounds__(256)
             const uint32_t from = pfrom + kCrcPart * t, n = t + 1u < K ? kCrcPart : r;
             const uint4 *src = reinterpret_cast<const uint4 *>(slots + g.a_off + from);
             c = 0xffffffffu;
-            for (uint32_t i = 0; i < n / 16u; i++) {
-                const uint4 v = src[i];
-                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t n16 = n / 16u;
+            for (uint32_t i0 = 0; i0 < n16; i0 += 4u) {  // four loads in flight in front of the dependent CRC steps
+                uint4 v4[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int u = 0; u < 4; u++) v4[u] = i0 + (uint32_t)u < n16 ? src[i0 + (uint32_t)u] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) c = tab[(c ^ (wv[q] >> (8 * k))) & 0xffu] ^ (c >> 8);
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + (uint32_t)u >= n16) break;
+                    const uint32_t wv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {  // four bytes per step: four independent lookups
+                        c ^= wv[q];
+                        c = tab[3][c & 0xffu] ^ tab[2][(c >> 8) & 0xffu] ^ tab[1][(c >> 16) & 0xffu] ^ tab[0][c >> 24];
+                    }
+                }
             }
             const uint8_t *p = slots + g.a_off + from;
-            for (uint32_t i = n & ~15u; i < n; i++) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+            for (uint32_t i = n & ~15u; i < n; i++) c = tab[0][(c ^ p[i]) & 0xffu] ^ (c >> 8);
             c ^= 0xffffffffu;
             // K-2-t whole parts and the last part's r bytes follow this one
             if (t + 1u < K) c = ci_mulmod(ci_mulmod(c, shift_parts[K - 2u - t]), r == kCrcPart ? shift_parts[1] : ci_xpow(8u * r));
