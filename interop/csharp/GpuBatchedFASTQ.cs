@@ -35,6 +35,32 @@ public sealed unsafe class GpuBatchedFASTQ : IEnumerable<FastqRecord>, IDisposab
         Check(LibPpB200.pp_job_info_get(_job, out _info));
     }
 
+    /// <summary>Core.BuildDeflateIndex (Decompressor/Core.cs:14-131) on the GPU: writes the same index file
+    /// IndexIO.Serialize(Core.BuildDeflateIndex(file, chunksize)) writes, ~160x faster (pp_index_create_gpu);
+    /// input the GPU entry point declines (-106: more than one gzip member; -4: not enough device memory)
+    /// goes through the host pass, which is the reference's own zlib loop.</summary>
+    public static void CreateIndexFile(string gzipPath, string indexPath, uint chunksize, int device = 0)
+    {
+        Check(LibPpB200.pp_open(device, out var ctx));
+        var len = new FileInfo(gzipPath).Length;
+        Check(LibPpB200.pp_host_alloc((nuint)len, out var gz));
+        try
+        {
+            using (var fs = File.OpenRead(gzipPath))
+                fs.ReadExactly(new Span<byte>((void*)gz, checked((int)len)));
+            int rc = LibPpB200.pp_index_create_gpu(ctx, (byte*)gz, (nuint)len, chunksize, 0, out var ix, out _);
+            if (rc == -106 || rc == -4) rc = LibPpB200.pp_index_create((byte*)gz, (nuint)len, chunksize, 0, out ix);
+            Check(rc);                                   // ZException where Core.cs:33,74 throws; -104 = Core.cs:93
+            Check(LibPpB200.pp_index_serialize(ix, indexPath));
+            LibPpB200.pp_index_free(ix);
+        }
+        finally
+        {
+            LibPpB200.pp_host_free(gz);
+            LibPpB200.pp_close(ctx);
+        }
+    }
+
     public long Count => _info.total_records;   // what Benchmark/Naive.cs:158-162 measures
 
     public IEnumerator<FastqRecord> GetEnumerator()
