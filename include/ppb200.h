@@ -320,8 +320,8 @@ typedef struct pp_create_stats {  /* where pp_index_create_gpu's time went (CUDA
  * are then chained through the segments and the bytes resolved; '@' statistics per block (Core.cs:86)
  * feed the reference's own checkpoint rule (Core.cs:98-125), and the windows / offsets of the chosen
  * points are gathered on the device.  ISIZE and CRC-32 of the trailer are verified (zlib: -3).
- * gz: one complete gzip member; more members or trailing bytes: PP_E_UNSUPPORTED, use
- * pp_index_create.  PP_E_RECORD_TOO_LONG / PP_INDEX_LIFT_RECORD_CAP as pp_index_create.  A stream that is
+ * gz: one complete gzip member; more members or trailing bytes, or a stream of pathologically
+ * small blocks (< 64 compressed bytes on average): PP_E_UNSUPPORTED, use pp_index_create.  PP_E_RECORD_TOO_LONG / PP_INDEX_LIFT_RECORD_CAP as pp_index_create.  A stream that is
  * both damaged and holds an over-long record may report the other of the two errors.  Device memory:
  * about twice the inflated size; PP_MEM_ERROR when the device cannot provide it (pp_index_create then is
  * the way).  stats may be NULL.

@@ -520,6 +520,7 @@ static int create_gpu(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, uint32_t ch
     int passes = 0;
     int rc = scan_blocks_resident(device, sm_count, st, comp.as<uint8_t>(), gz, gz_len, hdr, 0, chain, land, total_out,
                                   scan_kernel_ms, passes);
+    if (rc == PP_BUF_ERROR) return PP_E_UNSUPPORTED;  // blocks of < 64 compressed bytes on average: the record areas overflow
     if (rc != PP_OK) return rc;
     mark();  // 2
     const uint64_t end_byte = (land + 7u) >> 3;
