@@ -1150,6 +1150,8 @@ def test_gpu_create_index_errors_like_zlib(device):
     assert code(np.concatenate([gz, gz])) == -106
     assert code(np.concatenate([gz, np.zeros(3, np.uint8)])) == -106
     assert code(np.frombuffer(b"not a gzip file at all, just text" * 10, np.uint8)) == -3
+    # a flush every 40 bytes: two blocks per ~35 compressed bytes, more than the scan's record areas hold -> declined
+    assert code(corpus.gz_member(data[:300000], 6, flush_every=40)) in (0, -106)
     # a fixed-codes block whose first symbol is a match: distance 1 with nothing in front of it
     hdr = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"
     # bits: BFINAL=1, BTYPE=01, length code 257 (len 3) = 0000001, distance code 0 = 00000, EOB = 0000000
