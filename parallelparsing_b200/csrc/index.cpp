@@ -76,11 +76,29 @@ bool index_build_compact_windows(const pp_index *ix)
     return true;
 }
 
+// First touch of a large fresh allocation, by several threads: the kernel maps the pages while the device is still
+// busy, instead of one fault after the other under the copy that fills them (32 MB of windows at 10 M reads:
+// 3-15 ms single-threaded, 320 MB at 100 M reads: 100 ms).
+static void prefault(uint8_t *p, size_t bytes)
+{
+    if (bytes < (8u << 20)) return;
+    const unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([=]() {
+            const size_t lo = (size_t)t * per, hi = std::min(bytes, lo + per);
+            for (size_t o = lo; o < hi; o += 4096) ((volatile uint8_t *)p)[o] = 0;
+        });
+    for (auto &x : th) x.join();
+}
+
 void pp_index::reserve_windows(size_t points)
 {
     if (points <= win_cap) return;
     void *p = nullptr;
     if (posix_memalign(&p, 4096, points * (size_t)PP_WINSIZE) != 0) throw std::bad_alloc();
+    prefault((uint8_t *)p, points * (size_t)PP_WINSIZE);
     if (windows) {
         pp_internal_unpin_index(this);
         memcpy(p, windows, std::min(win_cap, output.size()) * (size_t)PP_WINSIZE);
