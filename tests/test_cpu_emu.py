@@ -200,3 +200,54 @@ def test_dual_inflate_with_position_coded_windows_reconstructs_the_stream(kind, 
     assert np.array_equal(got, ref)
     if kind == "dynamic":
         assert dependent > 0
+
+
+def test_window_chain_as_a_parallel_scan_of_maps():
+    """createindex.cu CHAIN: the window behind a segment as a function of the window in front of it (per byte:
+    a final value, or 0x8000 | position in the window in front), composed over all segments by a Hillis-Steele
+    scan — the same windows as walking the segments in order.  Includes segments shorter than a window (the
+    old window slides) and the first segment (nothing in front of it)."""
+    data = corpus.fastq(2500, fixed=150, seed=9)
+    gz = corpus.gz_member(data, 6, flush_every=9000)       # many short blocks: segments shorter than 32 KB occur
+    bits, outs, kinds, end, tot = O.block_stops(gz)
+    ref = np.frombuffer(zlib.decompress(gz.tobytes(), 47), np.uint8)
+    wa, wb = _coded_windows()
+    rng = np.random.default_rng(2)
+    firsts = [0]
+    while firsts[-1] + 1 < len(bits):
+        firsts.append(min(len(bits) - 1, firsts[-1] + int(rng.integers(1, 9))))
+    firsts = sorted(set(firsts))
+    maps, lens = [], []
+    for si, b0 in enumerate(firsts):
+        b1 = firsts[si + 1] if si + 1 < len(firsts) else len(bits)
+        sb, o0 = int(bits[b0]), int(outs[b0])
+        o1 = int(outs[b1]) if b1 < len(bits) else int(tot)
+        st, a, b = E.inflate_chunk_dual(gz, (sb + 7) // 8, (8 - sb % 8) % 8, gz.size, wa, wb, o1 - o0, 64, 27)
+        assert st == 0
+        n = min(o1 - o0, 32768)
+        a32, b32 = a[a.size - n:].astype(np.uint32), b[b.size - n:].astype(np.uint32)
+        tail = np.where(a32 == b32, a32, 0x8000 | (a32 + 256 * ((b32 - a32 - 1) & 0xFF)))
+        slide = 0x8000 | (np.arange(32768 - n, dtype=np.uint32) + n)      # window byte j <- old window byte j + n
+        maps.append(np.concatenate([slide, tail]).astype(np.uint32))
+        lens.append(o1 - o0)
+    assert min(lens) < 32768 < max(lens)
+    # in order, as a serial walk would do it
+    serial, w = [], np.zeros(32768, np.uint32)
+    for m in maps:
+        w = np.where(m & 0x8000, w[m & 0x7FFF], m & 0xFF)
+        serial.append(w)
+    # Hillis-Steele: P[s] = P[s] o P[s-d], d = 1, 2, 4, ...
+    P, d = [m.copy() for m in maps], 1
+    while d < len(P):
+        Q = [p.copy() for p in P]
+        for s in range(d, len(P)):
+            dep = (P[s] & 0x8000) != 0
+            Q[s] = np.where(dep, P[s - d][P[s] & 0x7FFF], P[s])
+        P, d = Q, 2 * d
+    ends = np.cumsum(lens)
+    for s in range(len(P)):
+        got = np.where(P[s] & 0x8000, 0, P[s] & 0xFF)                # what still points in front of the stream: zero
+        assert np.array_equal(got, serial[s]), s
+        e = int(ends[s])
+        want = np.concatenate([np.zeros(max(0, 32768 - e), np.uint8), ref[max(0, e - 32768): e]])
+        assert np.array_equal(got.astype(np.uint8), want), s
