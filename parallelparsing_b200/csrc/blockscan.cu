@@ -335,7 +335,7 @@ extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int
     try {
         CKS(cudaSetDevice(device));
         const size_t comp_base = gz_len & ~(size_t)15, comp_pad = 4096 + 16;   // zeroed tail: reads past the end see zeros
-        CKS(cudaMalloc(&d_comp, comp_base + comp_pad));
+        CKS(cudaMallocAsync((void **)&d_comp, comp_base + comp_pad, st));   // the device's pool (threshold lifted by pp_open)
         CKS(cudaMemsetAsync(d_comp + comp_base, 0, comp_pad, st));
         CKS(cudaMemcpyAsync(d_comp, gz, gz_len, cudaMemcpyHostToDevice, st));
         rc = scan_blocks_resident(device, sm_count, st, d_comp, gz, gz_len, hdr, segment_bytes, chain, land, out_total,
@@ -355,6 +355,6 @@ extern "C" int pp_scan_blocks(pp_ctx *ctx, const uint8_t *gz, size_t gz_len, int
 done:
     if (kernel_ms) *kernel_ms = ms_total;
     if (passes) *passes = npass;
-    cudaFree(d_comp);
+    if (d_comp) cudaFreeAsync(d_comp, st);
     return rc;
 }
