@@ -909,32 +909,7 @@ PP_DEV uint32_t seg_pos_at_output(const Sm &sm, uint32_t start, uint32_t limit, 
     return wp * 32u - cnt;
 }
 
-// Pull mode (the compressed input is pinned HOST memory read over PCIe): while a window's tokens are emitted and
-// resolved, the CTA's threads copy the NEXT window's compressed bytes — 16 bytes per thread and resolve tile —
-// from the host into this CTA's staging area in device memory, so that the next STAGE finds them there instead
-// of waiting ~50 us for the link (the link itself delivers 51 GB/s to SM reads; what the synchronous STAGE
-// leaves of it is 40).
-struct Prefetch {
-    const uint8_t *src;   // host bytes of the next window's base (16-byte aligned); null: nothing to fetch
-    uint8_t *dst;         // staging area of this CTA (device memory)
-    uint32_t bytes;       // to stage: a whole window, multiple of 16
-    uint32_t avail;       // bytes that exist at src; what lies behind reads as zero
-};
-PP_DEV void prefetch_unit(const Prefetch &pf, uint32_t off)   // one 16-byte unit, load and store at once
-{
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (off + 16u <= pf.avail) {
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(pf.src + off);
-        w[0] = q[0]; w[1] = q[1]; w[2] = q[2]; w[3] = q[3];
-    } else {
-        for (uint32_t k = 0; k < 16u && off + k < pf.avail; k++) w[k >> 2] |= (uint32_t)pf.src[off + k] << (8u * (k & 3u));
-    }
-    uint32_t *d = reinterpret_cast<uint32_t *>(pf.dst + off);
-    d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; d[3] = w[3];
-}
-
 struct WindowOut {
-    uint32_t pf_rel;     // pull mode: byte offset (from this window's base) of the window that was prefetched, or ~0
     uint32_t next_bit;   // window-relative bit after the last symbol used
     uint32_t need_bit;   // window-relative bit up to which the compressed input was really needed
     uint32_t produced;   // output bytes (clipped to the room left)
@@ -1175,9 +1150,8 @@ PP_DEV void expand_tile(const Sm &sm, const uint16_t *ent, const uint32_t *mask,
     }
 }
 
-template <bool PULL = false>
 PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uint32_t a, uint32_t total, uint32_t nlive,
-                           uint32_t rshift, Prefetch pf = Prefetch{nullptr, nullptr, 0u, 0u})
+                           uint32_t rshift)
 {
     const int T = PP_NT;
     const uint32_t R = (uint32_t)T * kTileB;
@@ -1229,27 +1203,9 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uin
     PP_END_T
     PP_SYNC();
     uint32_t tile = 0;
-#ifdef PP_HOST_EMU
-    if (PULL && pf.src)
-        for (uint32_t off = 0; off < pf.bytes; off += 16u) prefetch_unit(pf, off);
-#endif
     for (uint32_t tb = 0; tb < vend; tb += R, tile++) {
         const uint32_t cb = tile & 1u;
         const int32_t near_lo = (int32_t)(tb > a ? tb : a);  // sources below this are final in global memory
-#ifndef PP_HOST_EMU
-        // pull mode: this thread's 16 bytes of the next window, in flight from the host while the tile is resolved
-        uint4 pfv = make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t pfo = (tile * (uint32_t)T + threadIdx.x) * 16u;
-        const bool pfa = PULL && pf.src != nullptr && pfo < pf.bytes;
-        if (pfa) {
-            if (pfo + 16u <= pf.avail) pfv = *reinterpret_cast<const uint4 *>(pf.src + pfo);
-            else {
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
-                for (uint32_t k = 0; k < 16u && pfo + k < pf.avail; k++) w[k >> 2] |= (uint32_t)pf.src[pfo + k] << (8u * (k & 3u));
-                pfv = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-#endif
         // EXPAND: the byte's token is the last head at or before it
         PP_FOR_W(t)
         expand_prev(tt.mask + cb * (R / 32u), tt.wprev, (uint32_t)t);
@@ -1341,18 +1297,9 @@ PP_DEV void resolve_window(const Sm &sm, const uint32_t *tok, uint8_t *outp, uin
             }
         }
         PP_END_W
-#ifndef PP_HOST_EMU
-        if (pfa) *reinterpret_cast<uint4 *>(pf.dst + pfo) = pfv;
-#endif
         PP_SYNC();  // stores visible to the next tile's gathers; res free again; the next tile's tokens are in place
         PP_PHASE(PH_R_CHASE);
     }
-#ifndef PP_HOST_EMU
-    if (PULL && pf.src) {  // a window of fewer tiles than the staging area has 16-byte units per thread: the rest now
-        for (uint32_t off = (tile * (uint32_t)T + threadIdx.x) * 16u; off < pf.bytes; off += (uint32_t)T * 16u) prefetch_unit(pf, off);
-        __syncthreads();   // the staging area is complete before anyone reads it
-    }
-#endif
 }
 
 // The decode half of a window — GUESS, SYNC, SCAN — which needs no history and writes no output:
@@ -1485,11 +1432,9 @@ PP_DEV WindowCount count_window(const Sm &sm, uint32_t s0, uint32_t room)
 // One window of a Huffman block: GUESS, SYNC, SCAN (count_window), then EMIT and RESOLVE.
 // outp2 (dual output, GPU CreateIndex): the same tokens resolved a second time against a second history —
 // one Huffman decode, two LZ77 resolves.  outp2 has outp's alignment modulo 16.
-// pull (PULL): src = host pointer of THIS window's base with `avail` bytes behind it, dst = the CTA's staging area,
-// bytes = a window's staged size; the window that starts where this one ends is fetched while this one is resolved.
-template <bool DUAL = false, bool PULL = false>
+template <bool DUAL = false>
 PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32_t rshift, uint8_t *outp, uint32_t room,
-                                uint8_t *outp2 = nullptr, Prefetch pull = Prefetch{nullptr, nullptr, 0u, 0u})
+                                uint8_t *outp2 = nullptr)
 {
     const int T = PP_NT;
     const WindowCount c = count_window(sm, s0, room);
@@ -1510,25 +1455,10 @@ PP_DEV WindowOut huffman_window(const Sm &sm, uint32_t s0, uint32_t *tok, uint32
     PP_SYNC();
     PP_PHASE(PH_EMIT);
     // RESOLVE
-    uint32_t pf_rel = 0xffffffffu;
-    if (PULL) {
-        // nothing to fetch when this window completes the chunk's output or the data is bad
-        Prefetch pf = Prefetch{nullptr, nullptr, 0u, 0u};
-        if (pull.src && produced < room && c.flag != F_BAD) {
-            pf_rel = (c.next_bit >> 3) & ~15u;
-            pf.src = pull.src + pf_rel;
-            pf.dst = pull.dst;
-            pf.bytes = pull.bytes;
-            pf.avail = pull.avail > pf_rel ? pull.avail - pf_rel : 0u;
-        }
-        resolve_window<true>(sm, tok, outp, a, produced, nlive, rshift, pf);
-    } else {
-        resolve_window(sm, tok, outp, a, produced, nlive, rshift);
-    }
+    resolve_window(sm, tok, outp, a, produced, nlive, rshift);
     if (DUAL) resolve_window(sm, tok, outp2, a, produced, nlive, rshift);
     PP_PHASE(PH_RESOLVE);
     WindowOut w;
-    w.pf_rel = pf_rel;
     w.next_bit = c.next_bit;
     w.need_bit = c.need_bit;
     w.produced = produced;
@@ -1610,22 +1540,10 @@ struct DualOut {
     uint64_t slot_delta;  // multiple of 128
     uint64_t lead_delta;  // multiple of 16
 };
-// The next window out of this CTA's staging area (pull mode), where resolve_window's prefetch put it.
-PP_DEV void stage_from_staging(const Sm &sm, const uint8_t *stage, uint32_t words)
-{
-    const int T = PP_NT;
-    PP_SYNC();  // every thread is done with the previous contents of cw
-    PP_FOR_T(t)
-    for (uint32_t i = (uint32_t)t; i < words / 4u; i += (uint32_t)T)
-        reinterpret_cast<uint4 *>(sm.cw)[i] = reinterpret_cast<const uint4 *>(stage)[i];
-    PP_END_T
-    PP_SYNC();
-}
-
-template <bool DUAL = false, bool PULL = false>
+template <bool DUAL = false>
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                           const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
-                          const ByteGate *gate = nullptr, DualOut dual = DualOut{0, 0}, uint8_t *pull_stage = nullptr)
+                          const ByteGate *gate = nullptr, DualOut dual = DualOut{0, 0})
 {
     const int T = PP_NT;
     uint8_t *slot = slots + d.slot_off;
@@ -1669,18 +1587,12 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     uint32_t produced = 0;
     int status = 0;
     bool need_header = true, last = false;
-    uint64_t staged_base = ~0ull;  // pull mode: the base whose window sits in the staging area
     while (produced < out_len) {
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
         PP_PHASE(PH_OTHER);
-        if (PULL && staged_base == base_byte) {
-            stage_from_staging(sm, pull_stage, cww);
-        } else {
-            if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
-            if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
-        }
-        staged_base = ~0ull;
+        if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
+        if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
         PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
         if (need_header) {
@@ -1716,16 +1628,8 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
             PP_PHASE(PH_HEADER);
             need_header = false;
         }
-        Prefetch pull = Prefetch{nullptr, nullptr, 0u, 0u};
-        if (PULL && pull_stage && base_byte < comp_bytes) {
-            pull.src = comp + base_byte;
-            pull.dst = pull_stage;
-            pull.bytes = cww * 4u;
-            pull.avail = comp_bytes - base_byte < 0xffffffffull ? (uint32_t)(comp_bytes - base_byte) : 0xffffffffu;
-        }
-        const WindowOut w = huffman_window<DUAL, PULL>(sm, s0, tok, rshift, out + produced, out_len - produced,
-                                                       DUAL ? out + dual.slot_delta + produced : nullptr, pull);
-        if (PULL && w.pf_rel != 0xffffffffu) staged_base = base_byte + w.pf_rel;
+        const WindowOut w = huffman_window<DUAL>(sm, s0, tok, rshift, out + produced, out_len - produced,
+                                                 DUAL ? out + dual.slot_delta + produced : nullptr);
         produced += w.produced;
         bit = base_byte * 8u + w.next_bit;
         // Core.cs:174: the reference throws DATA_ERROR when zlib wants input past the end of fileBuffer

@@ -51,15 +51,11 @@ struct InflateLaunch {
     int grid = 0;            // resident CTAs (SMs x CTAs per SM)
     uint32_t *map = nullptr; // token/index scratch: grid x scratch_words_for(threads) words
     int *counter = nullptr;  // chunk counter the CTAs pull work from
-    uint8_t *pull_stage = nullptr;  // grid x pull_stride bytes of device memory (pull mode prefetch), owned by the context
-    uint32_t pull_stride = 0;
 };
 // Optional host <-> kernel hand-shakes of the inflate kernel.
 struct InflateSync {
     ppinf::ByteGate gate = {nullptr, 0, 0};  // pipelined upload: which bytes are in place (mark == null: all)
     uint32_t *done = nullptr;                             // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
-    uint8_t *pull_stage = nullptr;                        // pull mode (comp is pinned host memory): per-CTA staging areas in device
-    uint32_t pull_stride = 0;                             // memory for the prefetched next window (null: no prefetch), bytes per CTA
 };
 int inflate_max_ctas_per_sm(int threads);
 cudaError_t inflate_set_max_smem(int threads);

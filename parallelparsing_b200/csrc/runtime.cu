@@ -72,7 +72,6 @@ struct pp_ctx {
     InflateLaunch wide, dense;
     uint32_t *d_map = nullptr;
     int *d_counter = nullptr;
-    uint8_t *d_pull = nullptr;   // pull mode: one staging area per resident CTA for the prefetched next window
     int parse_per_sm = 0;  // resident CTAs of the parse kernel per SM (its look-back needs a resident grid)
     // pinned + mapped host arenas of finished jobs, kept for the next job of this context: cudaHostAlloc and
     // cudaFreeHost are driver calls that map into every device of the process (1-2 ms each with several GPUs)
@@ -103,15 +102,6 @@ static int ctx_setup_inflate(pp_ctx *c)
     CK(cudaMalloc(&c->d_counter, sizeof(int)));
     c->wide.map = c->dense.map = c->d_map;
     c->wide.counter = c->dense.counter = c->d_counter;
-    // pull mode (PP_JOB_ZEROCOPY): a window's worth of compressed bytes per CTA, filled while the window before is resolved
-    c->wide.pull_stride = (ppinf::cw_words_for(t_wide) * 4u + 127u) & ~127u;
-    c->dense.pull_stride = (ppinf::cw_words_for(t_dense) * 4u + 127u) & ~127u;
-    const size_t pull_bytes = std::max((size_t)c->wide.pull_stride * (size_t)c->wide.grid,
-                                       (size_t)c->dense.pull_stride * (size_t)c->dense.grid);
-    if (!getenv("PPB200_NO_PULL_PREFETCH")) {
-        CK(cudaMalloc(&c->d_pull, pull_bytes));
-        c->wide.pull_stage = c->dense.pull_stage = c->d_pull;
-    }
     c->parse_per_sm = parse_max_ctas_per_sm();
     if (c->parse_per_sm < 1) {
         fprintf(stderr, "ppb200: parse kernel does not fit an SM\n");
@@ -357,7 +347,6 @@ void pp_close(pp_ctx *ctx)
         }
     cudaFree(ctx->d_map);
     cudaFree(ctx->d_counter);
-    cudaFree(ctx->d_pull);
     for (auto &a : ctx->arenas) cudaFreeHost(a.first);
     delete ctx;
 }
@@ -825,12 +814,8 @@ static int job_execute_locked(pp_job *j, bool stream_done)
         CK(cudaHostGetDevicePointer(&dp, j->h_done, 0));
         sy.done = (uint32_t *)dp;
     }
-    const InflateLaunch &cfg = j->ctx->inflate_cfg(j->n);
-    if (j->zero_copy) {  // the input is pinned host memory: the next window is fetched while the current one is resolved
-        sy.pull_stage = cfg.pull_stage;
-        sy.pull_stride = cfg.pull_stride;
-    }
-    CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, cfg, st, sy));
+    CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
+                      st, sy));
     launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)
     CK(cudaEventRecord(j->ev[3], st));
     CK(cudaEventRecord(j->ev_exec_done, st));
