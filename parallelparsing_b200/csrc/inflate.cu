@@ -7,7 +7,7 @@
 
 namespace pp {
 
-template <bool DUAL>
+template <bool DUAL, bool PULL>
 __device__ __forceinline__ void inflate_kernel_body(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp,
                                                     uint64_t comp_bytes, uint8_t *slots, const uint8_t *__restrict__ lead,
                                                     ChunkResult *__restrict__ results, uint32_t *scratch, size_t scratch_words,
@@ -34,7 +34,7 @@ __device__ __forceinline__ void inflate_kernel_body(const ChunkDesc *__restrict_
         // `comp` was aligned down to 16 bytes for the bulk copies: the chunk's bits sit comp_shift bytes further in
         d.in_bit += 8ull * comp_shift;
         d.in_limit += comp_shift;
-        ppinf::inflate_chunk<DUAL>(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate, dual);
+        ppinf::inflate_chunk<DUAL, PULL>(sm, d, comp, comp_bytes, slots, lead, map, results[k], stage_phase, &sy.gate, dual);
         if (sy.done && threadIdx.x == 0) {
             // streamed download: tell the host (mapped pinned memory) that this chunk's bytes are final
             __threadfence_system();
@@ -48,8 +48,19 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
                       uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
                       uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy)
 {
-    inflate_kernel_body<false>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
-                               comp_shift, sy, ppinf::DualOut{0, 0});
+    inflate_kernel_body<false, false>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
+                                      comp_shift, sy, ppinf::DualOut{0, 0});
+}
+
+// Pull mode: `comp` is pinned host memory and the PCIe link is the limit; a window re-uses the bytes the window
+// before it already brought over (stage_window_reuse).
+__global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
+    pp_inflate_pull_kernel(const ChunkDesc *__restrict__ descs, int n, const uint8_t *__restrict__ comp, uint64_t comp_bytes,
+                           uint8_t *slots, const uint8_t *__restrict__ lead, ChunkResult *__restrict__ results,
+                           uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy)
+{
+    inflate_kernel_body<false, true>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
+                                     comp_shift, sy, ppinf::DualOut{0, 0});
 }
 
 // GPU CreateIndex: every chunk decoded once and resolved twice, against two histories (createindex.cu).
@@ -59,8 +70,8 @@ __global__ void __launch_bounds__(ppinf::kMaxThreads, 1)
                            uint32_t *scratch, size_t scratch_words, int *next_chunk, uint32_t comp_shift, InflateSync sy,
                            ppinf::DualOut dual)
 {
-    inflate_kernel_body<true>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
-                              comp_shift, sy, dual);
+    inflate_kernel_body<true, false>(descs, n, comp, comp_bytes, slots, lead, results, scratch, scratch_words, next_chunk,
+                                     comp_shift, sy, dual);
 }
 
 // Debug aid: cycles thread 0 of every CTA spent per phase since the last call (and reset).
@@ -82,7 +93,10 @@ cudaError_t inflate_set_max_smem(int threads)
     cudaError_t e = cudaFuncSetAttribute(pp_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ppinf::sm_bytes_for(threads));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pp_inflate_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(pp_inflate_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)ppinf::sm_bytes_for(threads));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pp_inflate_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)ppinf::sm_bytes_for(threads));
 }
 
@@ -113,8 +127,12 @@ cudaError_t launch_inflate(const ChunkDesc *descs, int n, const uint8_t *comp, u
     if (e != cudaSuccess) return e;
     const size_t smem = ppinf::sm_bytes_for(cfg.threads);
     const int grid = n < cfg.grid ? n : cfg.grid;
-    pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
-                                                        ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy);
+    if (sy.pull)
+        pp_inflate_pull_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
+                                                                 ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy);
+    else
+        pp_inflate_kernel<<<grid, cfg.threads, smem, st>>>(descs, n, comp, comp_bytes, slots, lead, results, cfg.map,
+                                                            ppinf::scratch_words_for(cfg.threads), cfg.counter, comp_shift, sy);
     return cudaGetLastError();
 }
 

@@ -355,6 +355,57 @@ PP_DEV bool stage_window(const Sm &sm, const uint8_t *comp, uint64_t comp_bytes,
 #endif
 }
 
+// Pull mode (the compressed input is pinned HOST memory, every staged byte crosses PCIe and the link is the limit:
+// 51.5 GB/s to SM reads, profiles/src/pull_probe.cu).  A window is staged whole (~63 KB) but usually ends with its
+// block (~57 KB), and the next window starts where it ended: the last few KB of what is staged are the first few
+// KB of the next window.  RESOLVE's scratch overwrites only the front of cw (resolve_scratch_bytes), so when the
+// next window starts behind that, its head is moved down inside shared memory and only the rest is fetched:
+// `delta` = new base - old base (multiple of 16, >= resolve_scratch_bytes(T), < 4 * words).
+PP_DEV bool stage_window_reuse(const Sm &sm, const uint8_t *comp, uint64_t comp_bytes, uint64_t byte_off, uint32_t words,
+                               uint32_t &phase, uint32_t delta)
+{
+    const int T = PP_NT;
+    const uint32_t want = words * 4u, keep = want - delta;  // keep < delta: source and destination do not overlap
+    PP_SYNC();  // every thread is done with the previous contents of cw
+    PP_FOR_T(t)
+    for (uint32_t i = (uint32_t)t; i < keep / 16u; i += (uint32_t)T)
+        reinterpret_cast<uint4 *>(sm.cw)[i] = reinterpret_cast<const uint4 *>(sm.cw)[delta / 16u + i];
+    PP_END_T
+    PP_SYNC();  // the old bytes are read before the new ones land on them
+    const uint64_t off = byte_off + keep;
+    const uint64_t avail = off < comp_bytes ? comp_bytes - off : 0;
+    const uint32_t need = delta;                                    // bytes [keep, want) of the window
+    const uint32_t have = avail < need ? (uint32_t)avail : need;
+    const uint32_t nbytes = have & ~15u;
+    const uint32_t tail = have - nbytes;
+#ifdef PP_HOST_EMU
+    if (have) memcpy((uint8_t *)sm.cw + keep, comp + off, have);
+    memset((uint8_t *)sm.cw + keep + have, 0, need - have);
+    (void)phase;
+    (void)tail;
+    return true;
+#else
+    if (threadIdx.x == 0 && nbytes) {
+        mbar_expect_tx(sm.bar, nbytes);
+        for (uint32_t o = 0; o < nbytes; o += 32768u) {
+            const uint32_t n = nbytes - o < 32768u ? nbytes - o : 32768u;
+            tma_load((uint8_t *)sm.cw + keep + o, comp + off + o, n, sm.bar);
+        }
+    }
+    if (nbytes < need) {
+        if (threadIdx.x < 16u)
+            ((uint8_t *)sm.cw)[keep + nbytes + threadIdx.x] = threadIdx.x < tail ? comp[off + nbytes + threadIdx.x] : (uint8_t)0;
+        for (uint32_t i = (keep + nbytes) / 4u + 4u + threadIdx.x; i < words; i += blockDim.x) sm.cw[i] = 0;
+    }
+    bool ok = true;
+    if (nbytes) {
+        ok = mbar_wait(sm.bar, phase & 1u);
+        phase++;
+    }
+    return __syncthreads_and(ok ? 1 : 0) != 0;
+#endif
+}
+
 // ---- block-wide exclusive prefix sum over a[0..T) (in place); returns the total ----
 PP_DEV uint32_t block_excl_scan(const Sm &sm, uint32_t *a)
 {
@@ -1006,6 +1057,13 @@ struct TileTok {
 };
 // tiles one window may produce before it is cut short (its row map must fit the staging buffer)
 PP_HD uint32_t max_tiles_for(int T) { return 16u * (uint32_t)T; }
+// Bytes at the front of cw that RESOLVE uses as scratch (ent, mask x2, wprev, tfirst — the layout resolve_window gives
+// them), rounded up to 128: what lies behind survives a window.
+PP_HD uint32_t resolve_scratch_bytes(int T)
+{
+    const uint32_t R = (uint32_t)T * kTileB;
+    return (4u * R + 4u * 3u * (R / 32u) + 2u * (max_tiles_for(T) + 2u) + 127u) & ~127u;
+}
 
 // One row's tokens of tile `tile` -> ent / mask.  Device: the lanes of the calling warp take
 // consecutive tokens, three loads in flight per lane.  Emulation: one thread walks the row.
@@ -1540,7 +1598,7 @@ struct DualOut {
     uint64_t slot_delta;  // multiple of 128
     uint64_t lead_delta;  // multiple of 16
 };
-template <bool DUAL = false>
+template <bool DUAL = false, bool PULL = false>
 PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp, uint64_t comp_bytes, uint8_t *slots,
                           const uint8_t *lead_src, uint32_t *scratch, ChunkResult &res, uint32_t &stage_phase,
                           const ByteGate *gate = nullptr, DualOut dual = DualOut{0, 0})
@@ -1587,12 +1645,19 @@ PP_DEV void inflate_chunk(const Sm &sm, const ChunkDesc &d, const uint8_t *comp,
     uint32_t produced = 0;
     int status = 0;
     bool need_header = true, last = false;
+    uint64_t prev_base = ~0ull;  // PULL: base of the window whose staged bytes (those behind RESOLVE's scratch) are still in cw
+    const uint32_t keep_from = PULL ? resolve_scratch_bytes(T) : 0u;
     while (produced < out_len) {
         if ((bit >> 3) > d.in_limit) { status = -3; break; }  // Core.cs:174: out of input
         const uint64_t base_byte = (bit >> 3) & ~(uint64_t)15;
         PP_PHASE(PH_OTHER);
         if (!gate_wait(sm, gate, base_byte, base_byte + 4ull * cww)) { status = -100; break; }
-        if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
+        if (PULL && prev_base != ~0ull && base_byte >= prev_base + keep_from && base_byte < prev_base + 4ull * cww) {
+            if (!stage_window_reuse(sm, comp, comp_bytes, base_byte, cww, stage_phase, (uint32_t)(base_byte - prev_base))) { status = -100; break; }
+        } else {
+            if (!stage_window(sm, comp, comp_bytes, base_byte, cww, stage_phase)) { status = -100; break; }
+        }
+        prev_base = base_byte;
         PP_PHASE(PH_STAGE);
         uint32_t s0 = (uint32_t)(bit - base_byte * 8u);
         if (need_header) {

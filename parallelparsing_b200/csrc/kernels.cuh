@@ -56,6 +56,7 @@ struct InflateLaunch {
 struct InflateSync {
     ppinf::ByteGate gate = {nullptr, 0, 0};  // pipelined upload: which bytes are in place (mark == null: all)
     uint32_t *done = nullptr;                             // mapped pinned host memory: done[k] = 1 when chunk k's bytes are final
+    bool pull = false;                                    // comp is pinned host memory: the kernel variant that re-uses staged bytes
 };
 int inflate_max_ctas_per_sm(int threads);
 cudaError_t inflate_set_max_smem(int threads);

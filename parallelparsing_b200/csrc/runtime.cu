@@ -814,6 +814,7 @@ static int job_execute_locked(pp_job *j, bool stream_done)
         CK(cudaHostGetDevicePointer(&dp, j->h_done, 0));
         sy.done = (uint32_t *)dp;
     }
+    sy.pull = j->zero_copy && !getenv("PPB200_NO_PULL_REUSE");  // the input crosses PCIe: staged bytes are re-used
     CK(launch_inflate(j->d_descs, j->n, comp, comp_bytes, j->d_slots, lead, j->d_results, j->ctx->inflate_cfg(j->n),
                       st, sy));
     launches += j->n > 0 ? 1 : 0;  // (the chunk-counter memset is not a kernel)

@@ -35,6 +35,28 @@ int emu_inflate_chunk(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t 
     res[0] = r.produced; res[1] = r.newlines; res[2] = r.min_byte; res[3] = r.end_bit;
     return r.status;
 }
+// Pull mode: a window re-uses the staged bytes the window before it left behind RESOLVE's scratch.
+int emu_inflate_chunk_pull(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t in_bit, uint64_t in_limit,
+                           uint8_t *slot, const uint8_t *lead, uint32_t lead_len, uint32_t out_len, uint64_t *res)
+{
+    ppinf::g_T = T;
+    ppinf::ChunkDesc d;
+    d.in_bit = in_bit; d.in_limit = in_limit; d.slot_off = 0; d.lead_src = 0;
+    d.lead_len = lead_len; d.out_len = out_len; d.prefix_len = 0; d.prefix_nl = 0;
+    ppinf::ChunkResult r;
+    uint8_t *raw = (uint8_t *)aligned_alloc(128, ppinf::sm_bytes_for(T));
+    uint32_t *map = (uint32_t *)aligned_alloc(128, (ppinf::scratch_words_for(T) * 4 + 127) / 128 * 128);
+    memset(map, 0xff, ppinf::scratch_words_for(T) * 4);
+    memset(raw, 0xff, ppinf::sm_bytes_for(T));
+    ppinf::Sm sm;
+    ppinf::sm_carve(sm, raw, T);
+    uint32_t phase = 0;
+    ppinf::inflate_chunk<false, true>(sm, d, comp, comp_bytes, slot, lead, map, r, phase);
+    free(raw);
+    free(map);
+    res[0] = r.produced; res[1] = r.newlines; res[2] = r.min_byte; res[3] = r.end_bit;
+    return r.status;
+}
 // Dual output (GPU CreateIndex): one decode, resolved against two histories; slot holds both outputs,
 // the second one slot_delta bytes after the first; lead holds both histories, lead_len apart.
 int emu_inflate_chunk_dual(int T, const uint8_t *comp, uint64_t comp_bytes, uint64_t in_bit, uint64_t in_limit,

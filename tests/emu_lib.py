@@ -53,6 +53,25 @@ def inflate_chunk(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window
     return st, slot[lead_len: lead_len + int(res[0])], int(res[1]), int(res[2]), int(res[3])
 
 
+def inflate_chunk_pull(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window: np.ndarray, out_len: int,
+                       T=64, subw=31, exact_extent=False):
+    """inflate_chunk<PULL>: as inflate_chunk, every window re-using the staged bytes the window before it left.
+    exact_extent: the compressed buffer ends where gz ends (no padding behind it, as a caller's pinned buffer)."""
+    L = lib(subw)
+    L.emu_inflate_chunk_pull.restype = C.c_int
+    L.emu_inflate_chunk_pull.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    pad = (-gz.size) % 16
+    comp = np.concatenate([gz, np.zeros(pad + 64, np.uint8)])
+    extent = gz.size if exact_extent else comp.size - 64
+    lead_len = window.size
+    slot = np.zeros(lead_len + out_len + 256, np.uint8)
+    res = (C.c_uint64 * 4)()
+    st = L.emu_inflate_chunk_pull(T, comp.ctypes.data, extent, in_byte * 8 - bits, in_limit, slot.ctypes.data,
+                                  window.ctypes.data, lead_len, out_len, res)
+    return st, slot[lead_len: lead_len + int(res[0])], int(res[1]), int(res[2]), int(res[3])
+
+
 def inflate_chunk_dual(gz: np.ndarray, in_byte: int, bits: int, in_limit: int, window_a: np.ndarray, window_b: np.ndarray,
                        out_len: int, T=64, subw=31):
     """One decode, two resolves (inflate_chunk<DUAL>): returns (status, bytes against window_a, bytes against window_b)."""

@@ -251,3 +251,27 @@ def test_window_chain_as_a_parallel_scan_of_maps():
         e = int(ends[s])
         want = np.concatenate([np.zeros(max(0, 32768 - e), np.uint8), ref[max(0, e - 32768): e]])
         assert np.array_equal(got.astype(np.uint8), want), s
+
+
+@pytest.mark.parametrize("kind,T,subw", [("dynamic", 64, 27), ("dynamic", 512, 27), ("dynamic1", 128, 31), ("syncflush", 128, 27),
+                                         ("fixed", 64, 31), ("stored", 64, 31), ("mixed", 64, 27)])
+def test_pull_mode_reuse_of_staged_bytes_equals_plain_decode(kind, T, subw):
+    """inflate_chunk<PULL> (what PP_JOB_ZEROCOPY jobs run): a window that starts behind RESOLVE's scratch inside
+    the bytes staged for the window before it moves them down in shared memory and fetches only the rest —
+    the same bytes, end bit and status as the plain path, with stored blocks in between (the bit cursor
+    jumps: nothing to re-use) and when the buffer ends exactly where the data ends."""
+    kw = dict(dynamic=dict(level=6), dynamic1=dict(level=1), syncflush=dict(level=6, flush_every=30000),
+              fixed=dict(level=6, strategy=zlib.Z_FIXED), stored=dict(level=0), mixed=dict(level=6))[kind]
+    data = corpus.fastq(4000, fixed=150, seed=6)
+    if kind == "mixed":
+        data = data[:200000] + bytes(np.random.default_rng(1).integers(0, 256, 150000, dtype=np.uint8)) + data[200000:400000]
+    gz = corpus.gz_member(data, **kw)
+    ox = O.OracleIndex.build(gz, 1000 if kind != "mixed" else 400, True)
+    outs, ins = ox.outputs(), ox.inputs()
+    for k in range(ox.count - 1):
+        p = ox.point(k)
+        ref = O.extract(gz, ox, k)
+        a = E.inflate_chunk(gz, p["input"], p["bits"], ins[k + 1], p["window"], outs[k + 1] - outs[k], T, subw)
+        for exact in (False, True):
+            b = E.inflate_chunk_pull(gz, p["input"], p["bits"], ins[k + 1], p["window"], outs[k + 1] - outs[k], T, subw, exact)
+            assert b[0] == a[0] == 0 and np.array_equal(b[1], ref) and b[2:] == a[2:], (k, exact)
