@@ -45,10 +45,16 @@ def test_fuzz_random_streams(seed):
     ref_all = np.frombuffer(data, np.uint8)
     outs = ox.outputs()
     for k in range(ox.count - 1):
-        st, got, nl, mb, _ = _emu_chunk(gz, ox, k, T=int(rng.choice([32, 64, 128, 512])))
+        T = int(rng.choice([32, 64, 128, 512]))
+        st, got, nl, mb, eb = _emu_chunk(gz, ox, k, T=T)
         ref = ref_all[outs[k]: outs[k + 1]]
         assert st == 0 and np.array_equal(got, ref), (seed, k)
         assert nl == int((ref == 10).sum())
+        # the pull-mode variant (staged bytes re-used between windows): the same in every respect
+        p = ox.point(k)
+        pst, pgot, pnl, pmb, peb = E.inflate_chunk_pull(gz, p["input"], p["bits"], ox.inputs()[k + 1], p["window"],
+                                                        outs[k + 1] - outs[k], T, 31, exact_extent=bool(k & 1))
+        assert pst == 0 and np.array_equal(pgot, ref) and (pnl, pmb, peb) == (nl, mb, eb), (seed, k)
     # stop points inside blocks (Core.cs:187)
     k = int(rng.integers(0, ox.count - 1))
     full = outs[k + 1] - outs[k]
